@@ -1,0 +1,194 @@
+/* rgb200.h -- C ABI of librgb200.so: the B200-native replacement for Raygun's per-frame
+ * ray-tracing path (TLAS/BLAS build -> raygen / closest-hit / miss recursion -> five compute
+ * post passes -> 8-bit frame).  Plain pointers and sizes only; no CUDA / torch types.
+ *
+ * The reference has no plugin or FFI layer: the seam is the C++ class raygun::render::Raytracer
+ * plus four POD layouts shared between C++ and GLSL.  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; rg_last_error() gives the text.
+ *     Nothing throws across the boundary (the reference aborts via RAYGUN_FATAL, logging.hpp:35-40).
+ *   - uploads copy; host pointers are never retained (the reference keeps host-visible, persistently
+ *     re-mapped buffers, gpu/gpu_buffer.cpp:60-75).
+ *   - one rg_ctx is used from one host thread (the reference render path is single-threaded:
+ *     render/render_system.cpp:332-361).  Work is asynchronous on the context's CUDA stream until
+ *     rg_sync / rg_read_* / rg_get_timings.
+ *   - there is NO CPU fallback: without a CUDA device rg_create fails.
+ */
+#ifndef RGB200_H
+#define RGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rg_ctx rg_ctx;
+
+/* resources/shaders/vertex.def:3-7 == raygun/render/vertex.hpp:27-29 (32 bytes) */
+typedef struct rg_vertex {
+    float position[3];
+    uint32_t mat_index;
+    float normal[3];
+    float pad1;
+} rg_vertex;
+
+/* resources/shaders/gpu_material.def:11-26 == raygun/gpu/gpu_material.hpp (64 bytes) */
+typedef struct rg_material {
+    float diffuse[3];
+    float transparency;
+    float specular[3];
+    float reflectivity;
+    float roughness;
+    float ior;
+    uint32_t effect_id;
+    uint32_t ray_consumption;
+    float emission;
+    float pad0, pad1, pad2;
+} rg_material;
+
+/* resources/shaders/uniform_buffer_object.def:3-17 == raygun/gpu/uniform_buffer.hpp (192 bytes).
+ * Matrices are column-major (GLM).  show_alpha is read as "first byte non-zero" (C++ bool). */
+typedef struct rg_ubo {
+    float view_inverse[16];
+    float proj_inverse[16];
+    float clear_color[3];
+    int32_t num_samples;
+    float light_dir[3];
+    int32_t max_recursions;
+    float time;
+    uint32_t show_alpha;
+    float pad0, pad1;
+    float fade_color[4];
+} rg_ubo;
+
+/* BufferRef offsets of one mesh inside the shared vertex / index buffers, in ELEMENTS
+ * (raygun/gpu/gpu_buffer.hpp:67-76, raygun/render/render_system.cpp:270-305). */
+typedef struct rg_mesh_range {
+    uint32_t vtx_off, vtx_cnt, idx_off, idx_cnt;
+} rg_mesh_range;
+
+/* One TLAS instance: VkAccelerationStructureInstanceKHR as filled by instanceFromEntity
+ * (raygun/render/acceleration_structure.cpp:34-52: 3x4 row-major object->world, mask 0xff,
+ * TriangleCullDisable, customIndex = position in the array) fused with its InstanceOffsetTableEntry
+ * (resources/shaders/instance_offset_table.def:1-3, acceleration_structure.cpp:77-82). 64 bytes. */
+typedef struct rg_instance {
+    float xform[12];
+    uint32_t mesh;    /* which rg_mesh_range / BLAS */
+    uint32_t vtx_off; /* vertexBufferOffset   */
+    uint32_t idx_off; /* indexBufferOffset    */
+    uint32_t mat_off; /* materialBufferOffset */
+} rg_instance;
+
+/* The five GPU sections of the reference profiler (raygun/profiler.def:6-10), from CUDA events,
+ * plus the NVLink gather and device-side ray counters.  A "ray" is one traceRayEXT with a non-zero
+ * cull mask; sky look-ups (cull mask 0, closesthit.rchit:144) are counted separately. */
+typedef struct rg_timings {
+    float as_build_ms;  /* ASBuild  : raytracer.cpp:78-84  */
+    float rt_total_ms;  /* RTTotal  : raytracer.cpp:93,144 */
+    float rt_only_ms;   /* RTOnly   : raytracer.cpp:95,104 */
+    float rough_ms;     /* Rough    : raytracer.cpp:111,123 */
+    float postproc_ms;  /* Postproc : raytracer.cpp:106,142 */
+    float gather_ms;    /* tile gather to the target GPU (no reference counterpart) */
+    uint64_t rays_primary, rays_shadow, rays_reflect, rays_refract, sky_lookups;
+    uint64_t nodes_visited, tris_tested, instances_entered; /* only with RG_COUNT_TRAVERSAL */
+} rg_timings;
+
+/* rg_render flags */
+#define RG_FXAA 1u            /* Raytracer::m_useFXAA (raytracer.cpp:136) */
+#define RG_SRGB8 2u           /* 8-bit target is an SRGB format (vulkan_context.cpp:180) */
+#define RG_STRICT_IEEE 4u     /* keep the 0/0 of closesthit.rchit:257 (SURVEY hazard 8); default NaN-free */
+#define RG_DEBUG_IDS 8u       /* also write primary-hit instance / primitive ids */
+#define RG_COUNT_TRAVERSAL 16u/* instrumented traversal counters (slower) */
+#define RG_NO_GATHER 32u      /* skip the peer gather even if a target is set */
+
+/* rg_read_image selectors; order mirrors the ImGui "Image" combo (raytracer.cpp:379-392) */
+enum { RG_IMG_FINAL = 0, RG_IMG_BASE = 1, RG_IMG_NORMAL = 2, RG_IMG_ROUGH = 3, RG_IMG_TRANSITIONS = 4, RG_IMG_ROUGH_A = 5, RG_IMG_ROUGH_B = 6 };
+
+/* Raytracer::Raytracer() (raytracer.cpp:38-52): images are sized from the window size. */
+int rg_create(rg_ctx** out, int cuda_device, uint32_t width, uint32_t height);
+void rg_destroy(rg_ctx* ctx);
+/* RenderSystem::reload() -> new Raytracer (render_system.cpp:77-78) */
+int rg_resize(rg_ctx* ctx, uint32_t width, uint32_t height);
+const char* rg_last_error(const rg_ctx* ctx);
+
+/* Multi-GPU screen split (no reference counterpart; the reference is single-device,
+ * vulkan_context.cpp:165).  The context renders only pixels [x0,x1) x [y0,y1) of the full
+ * width x height frame (plus an internal halo so the post chain is bit-identical to a
+ * single-GPU frame).  Default region = whole frame. */
+int rg_set_region(rg_ctx* ctx, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1);
+
+/* RenderSystem::setupModelBuffers / updateModelBuffers (render_system.cpp:192-233, :270-330) */
+int rg_upload_geometry(rg_ctx* ctx, const rg_vertex* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices,
+                       const rg_mesh_range* meshes, uint32_t n_meshes);
+int rg_upload_materials(rg_ctx* ctx, const rg_material* materials, uint32_t n_materials);
+
+/* Raytracer::setupBottomLevelAS (raytracer.cpp:54-74; BottomLevelAS acceleration_structure.cpp:140-194):
+ * builds the BLAS of every uploaded mesh; synchronous like the reference's fence wait. */
+int rg_build_blas(rg_ctx* ctx);
+/* Extension (BASELINE config 4; the reference never refits): new vertex records for one mesh
+ * (same count), topology kept, boxes refitted bottom-up and re-quantised. */
+int rg_refit_blas(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vertices);
+
+/* Raytracer::setupTopLevelAS (raytracer.cpp:76-85; TopLevelAS acceleration_structure.cpp:55-138):
+ * called every frame; rebuilds the TLAS from scratch on the device.  The caller performs the entity
+ * DFS of acceleration_structure.cpp:63-85 (raygun_b200/host does). */
+int rg_set_instances(rg_ctx* ctx, const rg_instance* instances, uint32_t n_instances);
+
+/* RenderSystem::updateUniformBuffer + Raytracer::updateRenderTarget (render_system.cpp:246-268, raytracer.cpp:149-171) */
+int rg_set_ubo(rg_ctx* ctx, const rg_ubo* ubo);
+
+/* Raytracer::doRaytracing (raytracer.cpp:87-147) + the blit to the 8-bit target (render_system.cpp:130-144). */
+int rg_render(rg_ctx* ctx, uint32_t flags);
+int rg_sync(rg_ctx* ctx);
+
+/* Read-back.  dst is tightly packed width x height (full frame when no region is set, else the region).
+ * rg_read_rgba8: 4 bytes / pixel.  rg_read_image: 8 bytes / pixel (4 x binary16), 1 byte for RG_IMG_TRANSITIONS. */
+int rg_read_rgba8(rg_ctx* ctx, void* dst);
+int rg_read_image(rg_ctx* ctx, int which, void* dst);
+int rg_read_ids(rg_ctx* ctx, uint32_t* instance_ids, uint32_t* primitive_ids);
+/* Profiler::getTimeRangeMS (profiler.cpp:50-53) for the last rendered frame. */
+int rg_get_timings(rg_ctx* ctx, rg_timings* out);
+
+/* Device-resident variants (no host copies): pointers are CUDA device pointers on the context's GPU. */
+int rg_set_instances_device(rg_ctx* ctx, const rg_instance* d_instances, uint32_t n_instances);
+int rg_set_ubo_device(rg_ctx* ctx, const rg_ubo* d_ubo);
+/* Device address of the RGBA8 frame buffer (region-sized, row pitch = region width * 4). */
+int rg_framebuffer_device_ptr(rg_ctx* ctx, void** d_ptr);
+
+/* Tile gather over NVLink: the final kernel (FXAA + 8-bit convert) stores this context's region
+ * straight into `d_target` (a width x height RGBA8 frame that may live on a PEER GPU: either a
+ * pointer in the same process with peer access enabled, or one opened from a CUDA IPC handle). */
+int rg_set_gather_target(rg_ctx* ctx, void* d_target_rgba8);
+/* 64-byte cudaIpcMemHandle_t of this context's full-frame gather buffer (allocated on demand) and
+ * its opening on another process' context. */
+int rg_gather_buffer_export(rg_ctx* ctx, void* handle64, void** d_ptr);
+int rg_gather_buffer_open(rg_ctx* ctx, const void* handle64, void** d_ptr);
+int rg_gather_buffer_close(rg_ctx* ctx, void* d_ptr);
+/* Read the full-frame gather buffer of this context (GPU 0) to the host. */
+int rg_read_gathered_rgba8(rg_ctx* ctx, void* dst);
+
+/* Builder introspection for the parity tests (Morton / sort output must be bit-exact):
+ * sorted Morton keys and the primitive order of one mesh's BLAS, and of the current TLAS. */
+int rg_debug_blas_sort(rg_ctx* ctx, uint32_t mesh, uint32_t* keys_sorted, uint32_t* prim_order, uint32_t capacity);
+int rg_debug_tlas_sort(rg_ctx* ctx, uint32_t* keys_sorted, uint32_t* inst_order, uint32_t capacity);
+/* Closest-hit queries straight into the traversal kernel (n rays: org xyz, dir xyz, tmin, tmax = 8 floats each);
+ * out: t,u,v (3 floats) + inst, prim (2 u32) per ray; inst = 0xffffffff on miss. */
+int rg_debug_trace_rays(rg_ctx* ctx, const float* rays8, uint32_t n, float* tuv, uint32_t* inst_prim);
+/* Counts: wide nodes, triangles, bytes of the BLAS set and of the current TLAS. */
+int rg_debug_bvh_stats(rg_ctx* ctx, uint64_t* out8);
+
+/* Post-chain parity helpers: replace the G-buffer (base, normal, rough: width x height x 4 binary16 each) with caller
+ * data and run rough_prepare .. fxaa + blit on it.  Full-frame region only. */
+int rg_debug_upload_gbuffer(rg_ctx* ctx, const void* base, const void* normal, const void* rough);
+int rg_debug_run_post(rg_ctx* ctx, uint32_t flags);
+
+/* Number of kernels this library launched on the context since creation (bench: gpu_launches). */
+uint64_t rg_launch_count(const rg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGB200_H */

@@ -1,0 +1,653 @@
+// rg_api.cu -- the C ABI of librgb200.so (include/rgb200.h): context, uploads, per-frame command stream.
+// Mirrors raygun::render::Raytracer (raygun/render/raytracer.{hpp,cpp}) for the one path this library replaces.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rgb200.h"
+#include "rg_build.cuh"
+#include "rg_post.cuh"
+#include "rg_trace.cuh"
+
+using namespace rg;
+
+static_assert(sizeof(rg_vertex) == 32 && sizeof(rg_material) == 64 && sizeof(rg_ubo) == 192 && sizeof(rg_instance) == 64 && sizeof(rg_mesh_range) == 16,
+              "POD layouts must match the reference's .def files");
+
+namespace {
+
+constexpr int kHalo = 40;  // post-chain dependency radius: 1 (prepare) + 10 (blur) + 28 (FXAA search + bilinear) = 39 -> 40
+
+struct MeshBlas {
+    rg_mesh_range range{};
+    LbvhScratch scratch;
+    uint32_t nodeOffset = 0, nNodes = 0, triOffset = 0, nTris = 0;
+    bool built = false;
+};
+
+enum { EV_AS0, EV_AS1, EV_RT0, EV_RTONLY1, EV_ROUGH0, EV_ROUGH1, EV_POST1, EV_GATHER1, EV_N };
+
+}  // namespace
+
+struct rg_ctx {
+    int device = 0, numSms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    uint32_t W = 0, H = 0;
+    int ix0 = 0, iy0 = 0, ix1 = 0, iy1 = 0;   // interior region
+    int rx0 = 0, ry0 = 0, rw = 0, rh = 0;     // rendered rectangle (region + halo)
+    uint2 *base = nullptr, *normal = nullptr, *rough = nullptr, *final_ = nullptr, *roughA = nullptr, *roughB = nullptr;
+    signed char* trans = nullptr;
+    uint32_t *rgba8 = nullptr, *idInst = nullptr, *idPrim = nullptr;
+    uint32_t* gatherOwn = nullptr;     // full-frame buffer owned by this context (GPU 0 role)
+    uint32_t* gatherTarget = nullptr;  // where the final kernel stores the region (may be peer memory)
+
+    void* dVertices = nullptr; uint32_t nVertices = 0;
+    uint32_t* dIndices = nullptr; uint32_t nIndices = 0;
+    void* dMaterials = nullptr; uint32_t nMaterials = 0;
+    std::vector<MeshBlas> meshes;
+    Node8* blasNodes = nullptr; Tri* tris = nullptr; uint32_t nodeCap = 0, triCap = 0, nodesUsed = 0, trisUsed = 0;
+    float* dMeshBoxes = nullptr;
+
+    rg_instance* dInstRaw = nullptr; InstTrav* dInstTrav = nullptr; InstShade* dInstShade = nullptr; uint32_t* dMeshRoots = nullptr;
+    uint32_t instCap = 0, nInst = 0;
+    LbvhScratch tlasScratch;
+    Node8* tlasNodes = nullptr; InstTrav* tlasLeaves = nullptr;
+    rg_instance* hInstPinned = nullptr; uint32_t hInstCap = 0;
+
+    float* dUbo = nullptr; rg_ubo hUbo{}; rg_ubo* hUboPinned = nullptr; bool uboOnDevice = false;
+    uint32_t* dWork = nullptr; unsigned long long* dCounters = nullptr;
+    cudaEvent_t ev[EV_N]{};
+    bool haveFrame = false, haveAs = false, blasBuilt = false;
+    uint32_t lastFlags = 0;
+};
+
+namespace {
+
+int fail(rg_ctx* c, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if(c) c->err = buf;
+    return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while(0)
+#define USE_DEVICE() CK(cudaSetDevice(ctx->device))
+
+void freeImages(rg_ctx* c) {
+    cudaFree(c->base); cudaFree(c->normal); cudaFree(c->rough); cudaFree(c->final_); cudaFree(c->roughA); cudaFree(c->roughB); cudaFree(c->trans);
+    cudaFree(c->rgba8); cudaFree(c->idInst); cudaFree(c->idPrim);
+    c->base = c->normal = c->rough = c->final_ = c->roughA = c->roughB = nullptr; c->trans = nullptr; c->rgba8 = c->idInst = c->idPrim = nullptr;
+}
+
+int allocImages(rg_ctx* ctx) {
+    freeImages(ctx);
+    ctx->rx0 = ctx->ix0 - kHalo < 0 ? 0 : ctx->ix0 - kHalo;
+    ctx->ry0 = ctx->iy0 - kHalo < 0 ? 0 : ctx->iy0 - kHalo;
+    const int rx1 = ctx->ix1 + kHalo > (int)ctx->W ? (int)ctx->W : ctx->ix1 + kHalo;
+    const int ry1 = ctx->iy1 + kHalo > (int)ctx->H ? (int)ctx->H : ctx->iy1 + kHalo;
+    ctx->rw = rx1 - ctx->rx0; ctx->rh = ry1 - ctx->ry0;
+    const size_t n = (size_t)ctx->rw * ctx->rh;
+    uint2** imgs[6] = {&ctx->base, &ctx->normal, &ctx->rough, &ctx->final_, &ctx->roughA, &ctx->roughB};
+    for(auto p: imgs) { CK(cudaMalloc(p, n * sizeof(uint2))); CK(cudaMemsetAsync(*p, 0, n * sizeof(uint2), ctx->stream)); }
+    CK(cudaMalloc(&ctx->trans, n)); CK(cudaMemsetAsync(ctx->trans, 0, n, ctx->stream));
+    CK(cudaMalloc(&ctx->idInst, n * 4)); CK(cudaMalloc(&ctx->idPrim, n * 4));
+    CK(cudaMemsetAsync(ctx->idInst, 0xff, n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->idPrim, 0xff, n * 4, ctx->stream));
+    const size_t ni = (size_t)(ctx->ix1 - ctx->ix0) * (ctx->iy1 - ctx->iy0);
+    CK(cudaMalloc(&ctx->rgba8, ni * 4)); CK(cudaMemsetAsync(ctx->rgba8, 0, ni * 4, ctx->stream));
+    ctx->haveFrame = false;
+    return 0;
+}
+
+// world->object from the 3x4 (binary64, explicitly rounded operations; same formula as oracle/orc_scene.cpp invert3x4)
+__global__ void k_prepare_instances(const rg_instance* __restrict__ raw, uint32_t n, const uint32_t* __restrict__ meshRoots, uint32_t nMeshes,
+                                    InstTrav* __restrict__ trav, InstShade* __restrict__ shade) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const rg_instance in = raw[i];
+    const float* m = in.xform;
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], k = m[10];
+#define DM(x, y) __dmul_rn((x), (y))
+#define DS(x, y) __dsub_rn((x), (y))
+#define DA(x, y) __dadd_rn((x), (y))
+    const double A = DS(DM(e, k), DM(f, h)), B = -DS(DM(d, k), DM(f, g)), C = DS(DM(d, h), DM(e, g));
+    const double det = DA(DA(DM(a, A), DM(b, B)), DM(c, C));
+    const double r = __ddiv_rn(1.0, det);
+    double R[9];
+    R[0] = DM(A, r); R[1] = DM(-DS(DM(b, k), DM(c, h)), r); R[2] = DM(DS(DM(b, f), DM(c, e)), r);
+    R[3] = DM(B, r); R[4] = DM(DS(DM(a, k), DM(c, g)), r); R[5] = DM(-DS(DM(a, f), DM(c, d)), r);
+    R[6] = DM(C, r); R[7] = DM(-DS(DM(a, h), DM(b, g)), r); R[8] = DM(DS(DM(a, e), DM(b, d)), r);
+    const double tx = m[3], ty = m[7], tz = m[11];
+    InstTrav t;
+    for(int rr = 0; rr < 3; ++rr) {
+        t.w2o[rr * 4 + 0] = (float)R[rr * 3 + 0]; t.w2o[rr * 4 + 1] = (float)R[rr * 3 + 1]; t.w2o[rr * 4 + 2] = (float)R[rr * 3 + 2];
+        t.w2o[rr * 4 + 3] = (float)(-DA(DA(DM(R[rr * 3 + 0], tx), DM(R[rr * 3 + 1], ty)), DM(R[rr * 3 + 2], tz)));
+    }
+#undef DM
+#undef DS
+#undef DA
+    t.blasRoot = in.mesh < nMeshes ? meshRoots[in.mesh] : kInvalid;
+    t.instId = i; t.pad0 = t.pad1 = 0;
+    trav[i] = t;
+    InstShade s;
+    for(int j = 0; j < 12; ++j) s.o2w[j] = m[j];
+    s.vtxOff = in.vtx_off; s.idxOff = in.idx_off; s.matOff = in.mat_off; s.mesh = in.mesh < nMeshes ? in.mesh : 0;
+    shade[i] = s;
+}
+
+int ensureInstanceCapacity(rg_ctx* ctx, uint32_t n) {
+    if(n <= ctx->instCap) return 0;
+    cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
+    const uint32_t cap = n + n / 2 + 16;
+    CK(cudaMalloc(&ctx->dInstRaw, sizeof(rg_instance) * (size_t)cap));
+    CK(cudaMalloc(&ctx->dInstTrav, sizeof(InstTrav) * (size_t)cap));
+    CK(cudaMalloc(&ctx->dInstShade, sizeof(InstShade) * (size_t)cap));
+    CK(cudaMalloc(&ctx->tlasNodes, sizeof(Node8) * (size_t)cap));
+    CK(cudaMalloc(&ctx->tlasLeaves, sizeof(InstTrav) * (size_t)cap));
+    ctx->instCap = cap;
+    ctx->tlasScratch.reserve(cap);
+    return 0;
+}
+
+int buildTlasFromRaw(rg_ctx* ctx, uint32_t n) {
+    ctx->nInst = n;
+    CK(cudaEventRecord(ctx->ev[EV_AS0], ctx->stream));
+    if(n) {
+        k_prepare_instances<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dInstRaw, n, ctx->dMeshRoots, (uint32_t)ctx->meshes.size(), ctx->dInstTrav,
+                                                                      ctx->dInstShade);
+        ctx->launches++;
+        const uint64_t before = ctx->tlasScratch.launches;
+        buildTlas(ctx->tlasScratch, ctx->dInstTrav, ctx->dInstShade, ctx->dMeshBoxes, n, ctx->tlasNodes, ctx->tlasLeaves, ctx->stream);
+        ctx->launches += ctx->tlasScratch.launches - before;
+    }
+    CK(cudaEventRecord(ctx->ev[EV_AS1], ctx->stream));
+    CK(cudaGetLastError());
+    ctx->haveAs = true;
+    return 0;
+}
+
+void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
+    p.tlasNodes = c->tlasNodes; p.tlasLeaves = c->tlasLeaves; p.blasNodes = c->blasNodes; p.tris = c->tris; p.instShade = c->dInstShade;
+    p.vertices = (const float4*)c->dVertices; p.indices = c->dIndices; p.materials = (const float4*)c->dMaterials; p.ubo = c->dUbo;
+    p.nInst = c->nInst; p.W = c->W; p.H = c->H; p.rx0 = (uint32_t)c->rx0; p.ry0 = (uint32_t)c->ry0; p.rw = (uint32_t)c->rw; p.rh = (uint32_t)c->rh;
+    p.base = c->base; p.normal = c->normal; p.rough = c->rough;
+    p.idInst = (flags & RG_DEBUG_IDS) ? c->idInst : nullptr; p.idPrim = (flags & RG_DEBUG_IDS) ? c->idPrim : nullptr;
+    p.workCounter = c->dWork; p.counters = c->dCounters; p.flags = flags;
+}
+
+void fillPostParams(rg_ctx* c, PostParams& p, uint32_t flags) {
+    p.base = c->base; p.normal = c->normal; p.rough = c->rough; p.final_ = c->final_; p.roughA = c->roughA; p.roughB = c->roughB;
+    p.fxaaOut = c->base;  // fxaa.comp:35 writes baseImage; the host then swaps base <-> final (raytracer.cpp:138-140)
+    p.trans = c->trans; p.rgba8 = c->rgba8; p.gather = (flags & RG_NO_GATHER) ? nullptr : c->gatherTarget;
+    p.W = (int)c->W; p.H = (int)c->H; p.rx0 = c->rx0; p.ry0 = c->ry0; p.rw = c->rw; p.rh = c->rh;
+    p.ix0 = c->ix0; p.iy0 = c->iy0; p.ix1 = c->ix1; p.iy1 = c->iy1;
+    p.fade = make_float4(c->hUbo.fade_color[0], c->hUbo.fade_color[1], c->hUbo.fade_color[2], c->hUbo.fade_color[3]);
+    p.showAlpha = (c->hUbo.show_alpha & 0xffu) != 0;
+    p.flags = flags;
+}
+
+int runPost(rg_ctx* ctx, uint32_t flags) {
+    PostParams pp; fillPostParams(ctx, pp, flags);
+    CK(cudaEventRecord(ctx->ev[EV_ROUGH0], ctx->stream));
+    launchRoughPrepare(pp, ctx->stream);
+    launchRoughBlur(pp, ctx->stream);
+    CK(cudaEventRecord(ctx->ev[EV_ROUGH1], ctx->stream));
+    launchPostprocess(pp, ctx->stream);
+    launchFxaaBlit(pp, ctx->stream);
+    ctx->launches += 1 + 20 + 1 + 1;
+    if(flags & RG_FXAA) { uint2* t = ctx->base; ctx->base = ctx->final_; ctx->final_ = t; }
+    CK(cudaEventRecord(ctx->ev[EV_POST1], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_GATHER1], ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int readRegion(rg_ctx* ctx, const void* dImg, size_t bpp, void* dst) {
+    const size_t w = (size_t)(ctx->ix1 - ctx->ix0), h = (size_t)(ctx->iy1 - ctx->iy0);
+    const char* src = (const char*)dImg + ((size_t)(ctx->iy0 - ctx->ry0) * ctx->rw + (size_t)(ctx->ix0 - ctx->rx0)) * bpp;
+    CK(cudaMemcpy2DAsync(dst, w * bpp, src, (size_t)ctx->rw * bpp, w * bpp, h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rg_create(rg_ctx** out, int cuda_device, uint32_t width, uint32_t height) {
+    if(!out) return 1;
+    *out = nullptr;
+    int nDev = 0;
+    if(cudaGetDeviceCount(&nDev) != cudaSuccess || nDev <= 0 || cuda_device < 0 || cuda_device >= nDev) {
+        fprintf(stderr, "rgb200: no CUDA device %d available (there is no CPU fallback)\n", cuda_device);
+        return 2;
+    }
+    if(width == 0 || height == 0) return 3;
+    rg_ctx* ctx = new rg_ctx();
+    ctx->device = cuda_device;
+    if(cudaSetDevice(cuda_device) != cudaSuccess) { delete ctx; return 4; }
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, cuda_device);
+    ctx->numSms = prop.multiProcessorCount;
+    if(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 5; }
+    for(auto& e: ctx->ev) cudaEventCreate(&e);
+    cudaMalloc(&ctx->dUbo, 192); cudaMemset(ctx->dUbo, 0, 192);
+    cudaMalloc(&ctx->dWork, 4); cudaMalloc(&ctx->dCounters, 8 * 8); cudaMemset(ctx->dCounters, 0, 64);
+    cudaMallocHost(&ctx->hUboPinned, sizeof(rg_ubo));
+    ctx->W = width; ctx->H = height; ctx->ix0 = 0; ctx->iy0 = 0; ctx->ix1 = (int)width; ctx->iy1 = (int)height;
+    if(allocImages(ctx)) { fprintf(stderr, "rgb200: %s\n", ctx->err.c_str()); rg_destroy(ctx); return 6; }
+    *out = ctx;
+    return 0;
+}
+
+void rg_destroy(rg_ctx* ctx) {
+    if(!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    freeImages(ctx);
+    cudaFree(ctx->gatherOwn);
+    cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes);
+    cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->dMeshRoots); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
+    cudaFree(ctx->dUbo); cudaFree(ctx->dWork); cudaFree(ctx->dCounters);
+    cudaFreeHost(ctx->hInstPinned); cudaFreeHost(ctx->hUboPinned);
+    for(auto& m: ctx->meshes) m.scratch.release();
+    ctx->tlasScratch.release();
+    for(auto& e: ctx->ev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* rg_last_error(const rg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+uint64_t rg_launch_count(const rg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rg_resize(rg_ctx* ctx, uint32_t width, uint32_t height) {
+    if(!ctx || !width || !height) return fail(ctx, "rg_resize: bad size");
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->W = width; ctx->H = height; ctx->ix0 = 0; ctx->iy0 = 0; ctx->ix1 = (int)width; ctx->iy1 = (int)height;
+    cudaFree(ctx->gatherOwn); ctx->gatherOwn = nullptr;
+    return allocImages(ctx);
+}
+
+int rg_set_region(rg_ctx* ctx, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
+    if(!ctx) return 1;
+    if(x0 >= x1 || y0 >= y1 || x1 > ctx->W || y1 > ctx->H) return fail(ctx, "rg_set_region: bad rectangle");
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ix0 = (int)x0; ctx->iy0 = (int)y0; ctx->ix1 = (int)x1; ctx->iy1 = (int)y1;
+    return allocImages(ctx);
+}
+
+int rg_upload_geometry(rg_ctx* ctx, const rg_vertex* vertices, uint32_t n_vertices, const uint32_t* indices, uint32_t n_indices, const rg_mesh_range* meshes,
+                       uint32_t n_meshes) {
+    if(!ctx) return 1;
+    if((n_vertices && !vertices) || (n_indices && !indices) || (n_meshes && !meshes)) return fail(ctx, "rg_upload_geometry: null input");
+    for(uint32_t m = 0; m < n_meshes; ++m) {
+        const rg_mesh_range& r = meshes[m];
+        if((uint64_t)r.vtx_off + r.vtx_cnt > n_vertices || (uint64_t)r.idx_off + r.idx_cnt > n_indices || r.idx_cnt % 3)
+            return fail(ctx, "rg_upload_geometry: mesh %u out of range", m);
+        for(uint32_t k = 0; k < r.idx_cnt; ++k)
+            if(indices[r.idx_off + k] >= r.vtx_cnt) return fail(ctx, "rg_upload_geometry: mesh %u index %u out of range", m, k);
+    }
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); ctx->dVertices = nullptr; ctx->dIndices = nullptr;
+    CK(cudaMalloc(&ctx->dVertices, (size_t)(n_vertices ? n_vertices : 1) * 32));
+    CK(cudaMalloc(&ctx->dIndices, (size_t)(n_indices ? n_indices : 1) * 4));
+    CK(cudaMemcpyAsync(ctx->dVertices, vertices, (size_t)n_vertices * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->dIndices, indices, (size_t)n_indices * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nVertices = n_vertices; ctx->nIndices = n_indices;
+    for(auto& m: ctx->meshes) m.scratch.release();
+    ctx->meshes.clear(); ctx->meshes.resize(n_meshes);
+    for(uint32_t m = 0; m < n_meshes; ++m) ctx->meshes[m].range = meshes[m];
+    ctx->nodesUsed = ctx->trisUsed = 0;
+    ctx->haveAs = false; ctx->blasBuilt = false;
+    cudaFree(ctx->dMeshBoxes); cudaFree(ctx->dMeshRoots); ctx->dMeshBoxes = nullptr; ctx->dMeshRoots = nullptr;
+    CK(cudaMalloc(&ctx->dMeshBoxes, sizeof(float) * 6 * ((size_t)n_meshes + 1)));
+    CK(cudaMalloc(&ctx->dMeshRoots, sizeof(uint32_t) * ((size_t)n_meshes + 1)));
+    return 0;
+}
+
+int rg_upload_materials(rg_ctx* ctx, const rg_material* materials, uint32_t n_materials) {
+    if(!ctx) return 1;
+    if(n_materials && !materials) return fail(ctx, "rg_upload_materials: null input");
+    USE_DEVICE();
+    if(n_materials > ctx->nMaterials || !ctx->dMaterials) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->dMaterials); ctx->dMaterials = nullptr;
+        CK(cudaMalloc(&ctx->dMaterials, (size_t)(n_materials ? n_materials : 1) * 64));
+    }
+    CK(cudaMemcpyAsync(ctx->dMaterials, materials, (size_t)n_materials * 64, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->nMaterials = n_materials;
+    return 0;
+}
+
+int rg_build_blas(rg_ctx* ctx) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    uint64_t totalTris = 0;
+    for(auto& m: ctx->meshes) totalTris += m.range.idx_cnt / 3;
+    const uint32_t needNodes = (uint32_t)(totalTris + ctx->meshes.size() + 1), needTris = (uint32_t)(totalTris + 1);
+    bool rebuildAll = false;
+    if(needNodes > ctx->nodeCap || needTris > ctx->triCap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->blasNodes); cudaFree(ctx->tris); ctx->blasNodes = nullptr; ctx->tris = nullptr;
+        CK(cudaMalloc(&ctx->blasNodes, sizeof(Node8) * (size_t)needNodes));
+        CK(cudaMalloc(&ctx->tris, sizeof(Tri) * (size_t)needTris));
+        ctx->nodeCap = needNodes; ctx->triCap = needTris; ctx->nodesUsed = ctx->trisUsed = 0;
+        rebuildAll = true;
+    }
+    std::vector<uint32_t> roots(ctx->meshes.size() + 1, kInvalid);
+    for(size_t m = 0; m < ctx->meshes.size(); ++m) {
+        MeshBlas& mb = ctx->meshes[m];
+        if(rebuildAll) mb.built = false;
+        if(!mb.built) {  // only missing BLASes are built (raytracer.cpp:65-69)
+            mb.nodeOffset = ctx->nodesUsed; mb.triOffset = ctx->trisUsed;
+            TriSource src{ctx->dVertices, ctx->dIndices, mb.range.vtx_off, mb.range.idx_off, mb.range.idx_cnt / 3};
+            const uint64_t before = mb.scratch.launches;
+            buildBlas(mb.scratch, src, ctx->blasNodes, mb.nodeOffset, ctx->tris, mb.triOffset, &mb.nNodes, &mb.nTris, ctx->dMeshBoxes + 6 * m, ctx->stream);
+            ctx->launches += mb.scratch.launches - before;
+            ctx->nodesUsed += mb.nNodes; ctx->trisUsed += mb.nTris;
+            mb.built = true;
+        }
+        roots[m] = mb.nTris ? mb.nodeOffset : kInvalid;
+    }
+    CK(cudaMemcpyAsync(ctx->dMeshRoots, roots.data(), sizeof(uint32_t) * roots.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    ctx->blasBuilt = true;
+    return 0;
+}
+
+int rg_refit_blas(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vertices) {
+    if(!ctx) return 1;
+    if(mesh >= ctx->meshes.size() || !ctx->meshes[mesh].built) return fail(ctx, "rg_refit_blas: mesh %u has no BLAS", mesh);
+    if(!new_vertices) return fail(ctx, "rg_refit_blas: null input");
+    USE_DEVICE();
+    MeshBlas& mb = ctx->meshes[mesh];
+    CK(cudaMemcpyAsync((char*)ctx->dVertices + (size_t)mb.range.vtx_off * 32, new_vertices, (size_t)mb.range.vtx_cnt * 32, cudaMemcpyHostToDevice, ctx->stream));
+    TriSource src{ctx->dVertices, ctx->dIndices, mb.range.vtx_off, mb.range.idx_off, mb.range.idx_cnt / 3};
+    const uint64_t before = mb.scratch.launches;
+    CK(cudaEventRecord(ctx->ev[EV_AS0], ctx->stream));
+    refitBlas(mb.scratch, src, ctx->blasNodes, mb.nodeOffset, mb.nNodes, ctx->tris, mb.triOffset, ctx->dMeshBoxes + 6 * mesh, ctx->stream);
+    CK(cudaEventRecord(ctx->ev[EV_AS1], ctx->stream));
+    ctx->launches += mb.scratch.launches - before;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int rg_set_instances(rg_ctx* ctx, const rg_instance* instances, uint32_t n_instances) {
+    if(!ctx) return 1;
+    if(n_instances && !instances) return fail(ctx, "rg_set_instances: null input");
+    if(!ctx->blasBuilt) return fail(ctx, "rg_set_instances: call rg_build_blas first");
+    for(uint32_t i = 0; i < n_instances; ++i)
+        if(instances[i].mesh >= ctx->meshes.size()) return fail(ctx, "rg_set_instances: instance %u references mesh %u", i, instances[i].mesh);
+    USE_DEVICE();
+    if(ensureInstanceCapacity(ctx, n_instances ? n_instances : 1)) return 1;
+    if(n_instances > ctx->hInstCap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFreeHost(ctx->hInstPinned); ctx->hInstPinned = nullptr;
+        CK(cudaMallocHost(&ctx->hInstPinned, sizeof(rg_instance) * (size_t)(n_instances + n_instances / 2 + 16)));
+        ctx->hInstCap = n_instances + n_instances / 2 + 16;
+    }
+    if(n_instances) {
+        CK(cudaStreamSynchronize(ctx->stream));  // the pinned staging buffer may still be in flight
+        memcpy(ctx->hInstPinned, instances, sizeof(rg_instance) * (size_t)n_instances);
+        CK(cudaMemcpyAsync(ctx->dInstRaw, ctx->hInstPinned, sizeof(rg_instance) * (size_t)n_instances, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return buildTlasFromRaw(ctx, n_instances);
+}
+
+int rg_set_instances_device(rg_ctx* ctx, const rg_instance* d_instances, uint32_t n_instances) {
+    if(!ctx) return 1;
+    if(!ctx->blasBuilt) return fail(ctx, "rg_set_instances_device: call rg_build_blas first");
+    USE_DEVICE();
+    if(ensureInstanceCapacity(ctx, n_instances ? n_instances : 1)) return 1;
+    if(n_instances) CK(cudaMemcpyAsync(ctx->dInstRaw, d_instances, sizeof(rg_instance) * (size_t)n_instances, cudaMemcpyDeviceToDevice, ctx->stream));
+    return buildTlasFromRaw(ctx, n_instances);
+}
+
+int rg_set_ubo(rg_ctx* ctx, const rg_ubo* ubo) {
+    if(!ctx || !ubo) return fail(ctx, "rg_set_ubo: null input");
+    if(ubo->num_samples < 1 || ubo->num_samples > 64) return fail(ctx, "rg_set_ubo: numSamples %d out of range 1..64", ubo->num_samples);
+    if(ubo->max_recursions < 0 || ubo->max_recursions > kMaxRecursions) return fail(ctx, "rg_set_ubo: maxRecursions %d out of range 0..%d", ubo->max_recursions, kMaxRecursions);
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hUbo = *ubo;
+    *ctx->hUboPinned = *ubo;
+    CK(cudaMemcpyAsync(ctx->dUbo, ctx->hUboPinned, 192, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int rg_set_ubo_device(rg_ctx* ctx, const rg_ubo* d_ubo) {
+    if(!ctx || !d_ubo) return fail(ctx, "rg_set_ubo_device: null input");
+    USE_DEVICE();
+    CK(cudaMemcpyAsync(ctx->dUbo, d_ubo, 192, cudaMemcpyDeviceToDevice, ctx->stream));
+    // fade / showAlpha are kernel parameters of the post passes: fetch the tail of the UBO
+    CK(cudaMemcpyAsync(ctx->hUboPinned, d_ubo, 192, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hUbo = *ctx->hUboPinned;
+    return 0;
+}
+
+int rg_render(rg_ctx* ctx, uint32_t flags) {
+    if(!ctx) return 1;
+    if(!ctx->haveAs) return fail(ctx, "rg_render: no acceleration structure (rg_build_blas + rg_set_instances first)");
+    USE_DEVICE();
+    CK(cudaMemsetAsync(ctx->dWork, 0, 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dCounters, 0, 64, ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_RT0], ctx->stream));
+    TraceParams tp; fillTraceParams(ctx, tp, flags);
+    launchTrace(tp, ctx->numSms, ctx->stream);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[EV_RTONLY1], ctx->stream));
+    if(runPost(ctx, flags)) return 1;
+    ctx->haveFrame = true; ctx->lastFlags = flags;
+    return 0;
+}
+
+int rg_sync(rg_ctx* ctx) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int rg_read_rgba8(rg_ctx* ctx, void* dst) {
+    if(!ctx || !dst) return fail(ctx, "rg_read_rgba8: null");
+    USE_DEVICE();
+    const size_t n = (size_t)(ctx->ix1 - ctx->ix0) * (ctx->iy1 - ctx->iy0) * 4;
+    CK(cudaMemcpyAsync(dst, ctx->rgba8, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rg_read_image(rg_ctx* ctx, int which, void* dst) {
+    if(!ctx || !dst) return fail(ctx, "rg_read_image: null");
+    USE_DEVICE();
+    switch(which) {
+    case RG_IMG_FINAL: return readRegion(ctx, ctx->final_, 8, dst);
+    case RG_IMG_BASE: return readRegion(ctx, ctx->base, 8, dst);
+    case RG_IMG_NORMAL: return readRegion(ctx, ctx->normal, 8, dst);
+    case RG_IMG_ROUGH: return readRegion(ctx, ctx->rough, 8, dst);
+    case RG_IMG_TRANSITIONS: return readRegion(ctx, ctx->trans, 1, dst);
+    case RG_IMG_ROUGH_A: return readRegion(ctx, ctx->roughA, 8, dst);
+    case RG_IMG_ROUGH_B: return readRegion(ctx, ctx->roughB, 8, dst);
+    default: return fail(ctx, "rg_read_image: bad selector %d", which);
+    }
+}
+
+int rg_read_ids(rg_ctx* ctx, uint32_t* instance_ids, uint32_t* primitive_ids) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    if(instance_ids && readRegion(ctx, ctx->idInst, 4, instance_ids)) return 1;
+    if(primitive_ids && readRegion(ctx, ctx->idPrim, 4, primitive_ids)) return 1;
+    return 0;
+}
+
+int rg_get_timings(rg_ctx* ctx, rg_timings* out) {
+    if(!ctx || !out) return fail(ctx, "rg_get_timings: null");
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    memset(out, 0, sizeof(*out));
+    if(ctx->haveAs) cudaEventElapsedTime(&out->as_build_ms, ctx->ev[EV_AS0], ctx->ev[EV_AS1]);
+    if(ctx->haveFrame) {
+        cudaEventElapsedTime(&out->rt_total_ms, ctx->ev[EV_RT0], ctx->ev[EV_POST1]);
+        cudaEventElapsedTime(&out->rt_only_ms, ctx->ev[EV_RT0], ctx->ev[EV_RTONLY1]);
+        cudaEventElapsedTime(&out->rough_ms, ctx->ev[EV_ROUGH0], ctx->ev[EV_ROUGH1]);
+        cudaEventElapsedTime(&out->postproc_ms, ctx->ev[EV_RTONLY1], ctx->ev[EV_POST1]);
+        cudaEventElapsedTime(&out->gather_ms, ctx->ev[EV_POST1], ctx->ev[EV_GATHER1]);
+        unsigned long long c[8];
+        CK(cudaMemcpy(c, ctx->dCounters, sizeof c, cudaMemcpyDeviceToHost));
+        out->rays_primary = c[0]; out->rays_shadow = c[1]; out->rays_reflect = c[2]; out->rays_refract = c[3]; out->sky_lookups = c[4];
+        out->nodes_visited = c[5]; out->tris_tested = c[6]; out->instances_entered = c[7];
+    }
+    cudaGetLastError();
+    return 0;
+}
+
+int rg_framebuffer_device_ptr(rg_ctx* ctx, void** d_ptr) {
+    if(!ctx || !d_ptr) return 1;
+    *d_ptr = ctx->rgba8;
+    return 0;
+}
+
+int rg_set_gather_target(rg_ctx* ctx, void* d_target_rgba8) {
+    if(!ctx) return 1;
+    ctx->gatherTarget = (uint32_t*)d_target_rgba8;
+    return 0;
+}
+
+int rg_gather_buffer_export(rg_ctx* ctx, void* handle64, void** d_ptr) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    if(!ctx->gatherOwn) {
+        CK(cudaMalloc(&ctx->gatherOwn, (size_t)ctx->W * ctx->H * 4));
+        CK(cudaMemset(ctx->gatherOwn, 0, (size_t)ctx->W * ctx->H * 4));
+    }
+    if(handle64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->gatherOwn));
+        memcpy(handle64, &h, 64);
+    }
+    if(d_ptr) *d_ptr = ctx->gatherOwn;
+    return 0;
+}
+
+int rg_gather_buffer_open(rg_ctx* ctx, const void* handle64, void** d_ptr) {
+    if(!ctx || !handle64 || !d_ptr) return fail(ctx, "rg_gather_buffer_open: null");
+    USE_DEVICE();
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int rg_gather_buffer_close(rg_ctx* ctx, void* d_ptr) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    if(ctx->gatherTarget == d_ptr) ctx->gatherTarget = nullptr;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaIpcCloseMemHandle(d_ptr));
+    return 0;
+}
+
+int rg_read_gathered_rgba8(rg_ctx* ctx, void* dst) {
+    if(!ctx || !dst) return fail(ctx, "rg_read_gathered_rgba8: null");
+    if(!ctx->gatherOwn) return fail(ctx, "rg_read_gathered_rgba8: no gather buffer on this context");
+    USE_DEVICE();
+    CK(cudaMemcpyAsync(dst, ctx->gatherOwn, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- parity / introspection entry points ----------------------------------------------------------------
+int rg_debug_blas_sort(rg_ctx* ctx, uint32_t mesh, uint32_t* keys_sorted, uint32_t* prim_order, uint32_t capacity) {
+    if(!ctx) return 1;
+    if(mesh >= ctx->meshes.size() || !ctx->meshes[mesh].built) return fail(ctx, "rg_debug_blas_sort: mesh %u has no BLAS", mesh);
+    USE_DEVICE();
+    MeshBlas& mb = ctx->meshes[mesh];
+    const uint32_t n = mb.range.idx_cnt / 3;
+    if(capacity < n) return fail(ctx, "rg_debug_blas_sort: capacity %u < %u", capacity, n);
+    if(n) {
+        CK(cudaMemcpy(keys_sorted, mb.scratch.keys[mb.scratch.sortedBuf], 4 * (size_t)n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(prim_order, mb.scratch.vals[mb.scratch.sortedBuf], 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int rg_debug_tlas_sort(rg_ctx* ctx, uint32_t* keys_sorted, uint32_t* inst_order, uint32_t capacity) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    const uint32_t n = ctx->nInst;
+    if(capacity < n) return fail(ctx, "rg_debug_tlas_sort: capacity %u < %u", capacity, n);
+    CK(cudaStreamSynchronize(ctx->stream));
+    if(n) {
+        CK(cudaMemcpy(keys_sorted, ctx->tlasScratch.keys[ctx->tlasScratch.sortedBuf], 4 * (size_t)n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(inst_order, ctx->tlasScratch.vals[ctx->tlasScratch.sortedBuf], 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int rg_debug_trace_rays(rg_ctx* ctx, const float* rays8, uint32_t n, float* tuv, uint32_t* inst_prim) {
+    if(!ctx) return 1;
+    if(!ctx->haveAs) return fail(ctx, "rg_debug_trace_rays: no acceleration structure");
+    USE_DEVICE();
+    float *dR = nullptr, *dT = nullptr; uint32_t* dI = nullptr;
+    CK(cudaMalloc(&dR, 32 * (size_t)(n + 1))); CK(cudaMalloc(&dT, 12 * (size_t)(n + 1))); CK(cudaMalloc(&dI, 8 * (size_t)(n + 1)));
+    CK(cudaMemcpyAsync(dR, rays8, 32 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    TraceParams tp; fillTraceParams(ctx, tp, 0);
+    launchTraceRays(tp, dR, n, dT, dI, ctx->stream);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(tuv, dT, 12 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(inst_prim, dI, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dR); cudaFree(dT); cudaFree(dI);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int rg_debug_bvh_stats(rg_ctx* ctx, uint64_t* out8) {
+    if(!ctx || !out8) return 1;
+    out8[0] = ctx->nodesUsed; out8[1] = ctx->trisUsed;
+    out8[2] = (uint64_t)ctx->nodesUsed * sizeof(Node8) + (uint64_t)ctx->trisUsed * sizeof(Tri);
+    uint32_t c[4] = {0, 0, 0, 0};
+    if(ctx->tlasScratch.counters) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); cudaMemcpy(c, ctx->tlasScratch.counters, sizeof c, cudaMemcpyDeviceToHost); }
+    out8[3] = ctx->nInst ? c[2] : 0; out8[4] = ctx->nInst ? c[3] : 0;
+    out8[5] = (uint64_t)out8[3] * sizeof(Node8) + (uint64_t)out8[4] * sizeof(InstTrav);
+    out8[6] = ctx->meshes.size(); out8[7] = ctx->nInst;
+    return 0;
+}
+
+// Parity helpers for the post chain: replace the G-buffer with caller data (region-sized, tightly packed) and run
+// rough_prepare .. fxaa + blit on it.  Only meaningful when no region split is active.
+int rg_debug_upload_gbuffer(rg_ctx* ctx, const void* base, const void* normal, const void* rough) {
+    if(!ctx || !base || !normal || !rough) return fail(ctx, "rg_debug_upload_gbuffer: null");
+    if(ctx->rw != (int)ctx->W || ctx->rh != (int)ctx->H) return fail(ctx, "rg_debug_upload_gbuffer: needs the full-frame region");
+    USE_DEVICE();
+    const size_t n = (size_t)ctx->W * ctx->H * 8;
+    CK(cudaMemcpyAsync(ctx->base, base, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->normal, normal, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->rough, rough, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rg_debug_run_post(rg_ctx* ctx, uint32_t flags) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    CK(cudaEventRecord(ctx->ev[EV_RT0], ctx->stream));
+    CK(cudaEventRecord(ctx->ev[EV_RTONLY1], ctx->stream));
+    if(runPost(ctx, flags)) return 1;
+    ctx->haveFrame = true; ctx->lastFlags = flags;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,637 @@
+// rg_build.cu -- LBVH builder for sm_100a: primitive boxes -> 30-bit Morton keys -> LSD radix sort
+// (8-bit digits, stable) -> Karras 2012 hierarchy -> bottom-up refit -> collapse to compressed 8-wide nodes.
+//
+// Replaces the driver-side acceleration-structure builds of the reference
+// (raygun/render/acceleration_structure.cpp:134 TLAS per frame, :193 BLAS per mesh).
+// The sort key is contractually bit-exact with oracle/orc_api.cpp (mortonOf): every operation below is an
+// explicitly rounded single binary32 operation (__fadd_rn & co are never contracted into FMAs).
+#include "rg_build.cuh"
+
+#include <cfloat>
+#include <cstdio>
+
+namespace rg {
+
+#define RG_CUDA_OK(x) do { cudaError_t e_ = (x); if(e_ != cudaSuccess) { fprintf(stderr, "rgb200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); } } while(0)
+
+namespace {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;
+
+__device__ __forceinline__ int encodeFloat(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float decodeFloat(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ uint32_t expandBits10(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__global__ void k_init_build(int32_t* sceneBox, uint32_t* counters) {
+    if(threadIdx.x < 3) sceneBox[threadIdx.x] = 0x7fffffff;
+    else if(threadIdx.x < 6) sceneBox[threadIdx.x] = (int)0x80000000;
+    if(threadIdx.x < 8) counters[threadIdx.x] = 0;
+}
+
+__device__ __forceinline__ void reduceSceneBox(const float lo[3], const float hi[3], bool valid, int32_t* sceneBox) {
+    // warp reduce, then one atomic per warp and axis
+#pragma unroll
+    for(int a = 0; a < 3; ++a) {
+        int l = valid ? encodeFloat(lo[a]) : 0x7fffffff, h = valid ? encodeFloat(hi[a]) : (int)0x80000000;
+#pragma unroll
+        for(int o = 16; o; o >>= 1) { l = min(l, __shfl_xor_sync(0xffffffffu, l, o)); h = max(h, __shfl_xor_sync(0xffffffffu, h, o)); }
+        if((threadIdx.x & 31) == 0) { atomicMin(&sceneBox[a], l); atomicMax(&sceneBox[3 + a], h); }
+    }
+}
+
+// Per-triangle box (min / max of the three vertex positions; exact) + scene box.
+__global__ void k_tri_boxes(const float4* __restrict__ vertices /*2 float4 per vertex*/, const uint32_t* __restrict__ indices, uint32_t vtxOff,
+                            uint32_t idxOff, uint32_t nTri, Aabb* __restrict__ primBox, int32_t* sceneBox) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    const bool valid = p < nTri;
+    if(valid) {
+#pragma unroll
+        for(int k = 0; k < 3; ++k) {
+            const uint32_t vi = vtxOff + indices[idxOff + 3 * p + k];
+            const float4 v = vertices[2 * (size_t)vi];
+            lo[0] = fminf(lo[0], v.x); lo[1] = fminf(lo[1], v.y); lo[2] = fminf(lo[2], v.z);
+            hi[0] = fmaxf(hi[0], v.x); hi[1] = fmaxf(hi[1], v.y); hi[2] = fmaxf(hi[2], v.z);
+        }
+        Aabb b; for(int a = 0; a < 3; ++a) { b.lo[a] = lo[a]; b.hi[a] = hi[a]; }
+        primBox[p] = b;
+    }
+    reduceSceneBox(lo, hi, valid, sceneBox);
+}
+
+// Per-instance world box: the 8 corners of the mesh box mapped by the 3x4, each coordinate
+// ((m0*x + m1*y) + m2*z) + m3 in single rounded operations (oracle: orc_instance_world_box).
+__global__ void k_inst_boxes(const InstShade* __restrict__ inst, const float* __restrict__ meshBoxes, uint32_t nInst, Aabb* __restrict__ primBox,
+                             int32_t* sceneBox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    const bool valid = i < nInst;
+    if(valid) {
+        const InstShade in = inst[i];
+        const float* mb = meshBoxes + 6 * in.mesh;
+        const bool empty = mb[0] > mb[3];
+        if(empty) {  // empty mesh: degenerate box at the instance origin, never entered (blasRoot invalid)
+            for(int a = 0; a < 3; ++a) lo[a] = hi[a] = in.o2w[4 * a + 3];
+        } else {
+            for(int c = 0; c < 8; ++c) {
+                const float x = (c & 1) ? mb[3] : mb[0], y = (c & 2) ? mb[4] : mb[1], z = (c & 4) ? mb[5] : mb[2];
+#pragma unroll
+                for(int r = 0; r < 3; ++r) {
+                    const float w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(in.o2w[4 * r], x), __fmul_rn(in.o2w[4 * r + 1], y)), __fmul_rn(in.o2w[4 * r + 2], z)),
+                                              in.o2w[4 * r + 3]);
+                    lo[r] = fminf(lo[r], w); hi[r] = fmaxf(hi[r], w);
+                }
+            }
+        }
+        Aabb b; for(int a = 0; a < 3; ++a) { b.lo[a] = lo[a]; b.hi[a] = hi[a]; }
+        primBox[i] = b;
+    }
+    reduceSceneBox(lo, hi, valid, sceneBox);
+}
+
+__global__ void k_morton(const Aabb* __restrict__ primBox, uint32_t n, const int32_t* __restrict__ sceneBox, uint32_t* __restrict__ keys,
+                         uint32_t* __restrict__ vals) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if(p >= n) return;
+    const Aabb b = primBox[p];
+    uint32_t q[3];
+#pragma unroll
+    for(int a = 0; a < 3; ++a) {
+        const float slo = decodeFloat(sceneBox[a]), shi = decodeFloat(sceneBox[3 + a]);
+        const float c = __fmul_rn(__fadd_rn(b.lo[a], b.hi[a]), 0.5f);
+        const float ext = __fsub_rn(shi, slo);
+        const float s = ext > 0.0f ? __fdiv_rn(1024.0f, ext) : 0.0f;
+        float v = __fmul_rn(__fsub_rn(c, slo), s);
+        v = v > 0.0f ? v : 0.0f;
+        v = v < 1023.0f ? v : 1023.0f;
+        q[a] = __float2uint_rz(v);
+    }
+    keys[p] = (expandBits10(q[0]) << 2) | (expandBits10(q[1]) << 1) | expandBits10(q[2]);
+    vals[p] = p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stable LSD radix sort, 8-bit digits.  Tile = 256 threads x 8 keys; warp w owns 256 consecutive keys.
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t numTiles,
+                                                            uint32_t* __restrict__ histG) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kSortTile;
+#pragma unroll
+    for(int j = 0; j < kSortItems; ++j) {
+        const uint32_t i = base + j * kSortThreads + threadIdx.x;
+        if(i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    histG[threadIdx.x * numTiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// Exclusive scan of histG (digit-major), single block.
+__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ histG, uint32_t count) {
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    if(threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for(uint32_t base = 0; base < count; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < count ? histG[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for(int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if(lane >= (uint32_t)o) x += y; }
+        if(lane == 31) warpSums[warp] = x;
+        __syncthreads();
+        if(warp == 0) {
+            uint32_t w = warpSums[lane];
+#pragma unroll
+            for(int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if(lane >= (uint32_t)o) w += y; }
+            warpSums[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t warpOff = warp ? warpSums[warp - 1] : 0u;
+        const uint32_t c = carry;
+        if(i < count) histG[i] = c + warpOff + x - v;
+        __syncthreads();
+        if(threadIdx.x == 1023) carry = c + warpOff + x;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ valsIn, uint32_t n,
+                                                               int shift, uint32_t numTiles, const uint32_t* __restrict__ histG,
+                                                               uint32_t* __restrict__ keysOut, uint32_t* __restrict__ valsOut) {
+    __shared__ uint32_t whist[kSortThreads / 32][256];
+    __shared__ uint32_t gbase[256];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for(int w = 0; w < kSortThreads / 32; ++w) whist[w][threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * kSortTile + warp * (32 * kSortItems);
+    uint32_t key[kSortItems], val[kSortItems], local[kSortItems];
+#pragma unroll
+    for(int j = 0; j < kSortItems; ++j) {
+        const uint32_t i = base + j * 32 + lane;
+        const bool valid = i < n;
+        key[j] = valid ? keysIn[i] : 0u;
+        val[j] = valid ? valsIn[i] : 0u;
+        const uint32_t digit = valid ? ((key[j] >> shift) & 255u) : 0xffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t b = 0;
+        if(valid) b = whist[warp][digit];
+        __syncwarp();
+        if(valid && rank == 0) whist[warp][digit] = b + __popc(peers);
+        __syncwarp();
+        local[j] = b + rank;
+    }
+    __syncthreads();
+    {
+        uint32_t running = 0;
+#pragma unroll
+        for(int w = 0; w < kSortThreads / 32; ++w) { const uint32_t c = whist[w][threadIdx.x]; whist[w][threadIdx.x] = running; running += c; }
+        gbase[threadIdx.x] = histG[threadIdx.x * numTiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for(int j = 0; j < kSortItems; ++j) {
+        const uint32_t i = base + j * 32 + lane;
+        if(i < n) {
+            const uint32_t digit = (key[j] >> shift) & 255u;
+            const uint32_t pos = gbase[digit] + whist[warp][digit] + local[j];
+            keysOut[pos] = key[j];
+            valsOut[pos] = val[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Karras 2012: one thread per internal node.
+__device__ __forceinline__ int deltaKey(const uint32_t* __restrict__ keys, int n, int i, int j) {
+    if(j < 0 || j >= n) return -1;
+    const uint32_t a = keys[i], b = keys[j];
+    return a == b ? 32 + __clz((uint32_t)i ^ (uint32_t)j) : __clz(a ^ b);
+}
+
+__global__ void k_hierarchy(const uint32_t* __restrict__ keys, uint32_t n, BNode* __restrict__ bnodes, uint2* __restrict__ range,
+                            uint32_t* __restrict__ parent, uint32_t* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int N = (int)n;
+    if(i >= N - 1) return;
+    const int d = (deltaKey(keys, N, i, i + 1) - deltaKey(keys, N, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = deltaKey(keys, N, i, i - d);
+    int lmax = 2;
+    while(deltaKey(keys, N, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for(int t = lmax >> 1; t >= 1; t >>= 1)
+        if(deltaKey(keys, N, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = deltaKey(keys, N, i, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if(deltaKey(keys, N, i, i + (s + t) * d) > dnode) s += t;
+    } while(t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int first = min(i, j), last = max(i, j);
+    const uint32_t left = (first == gamma) ? (kLeafBit | (uint32_t)gamma) : (uint32_t)gamma;
+    const uint32_t right = (last == gamma + 1) ? (kLeafBit | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+    bnodes[i].left = left; bnodes[i].right = right;
+    range[i] = make_uint2((uint32_t)first, (uint32_t)last);
+    flags[i] = 0;
+    if(left & kLeafBit) parent[(N - 1) + gamma] = (uint32_t)i; else parent[gamma] = (uint32_t)i;
+    if(right & kLeafBit) parent[(N - 1) + gamma + 1] = (uint32_t)i; else parent[gamma + 1] = (uint32_t)i;
+    if(i == 0) parent[0] = kInvalid;
+}
+
+__device__ __forceinline__ void loadRefBox(uint32_t ref, const BNode* bnodes, const Aabb* primBox, const uint32_t* vals, float lo[3], float hi[3]) {
+    if(ref & kLeafBit) {
+        const Aabb b = primBox[vals[ref & ~kLeafBit]];
+        for(int a = 0; a < 3; ++a) { lo[a] = b.lo[a]; hi[a] = b.hi[a]; }
+    } else {
+        const BNode b = bnodes[ref];
+        for(int a = 0; a < 3; ++a) { lo[a] = b.lo[a]; hi[a] = b.hi[a]; }
+    }
+}
+
+// Bottom-up refit: one thread per leaf; the second thread to arrive at a node computes its box.
+__global__ void k_refit_binary(uint32_t n, BNode* bnodes, const Aabb* __restrict__ primBox, const uint32_t* __restrict__ vals,
+                               const uint32_t* __restrict__ parent, uint32_t* flags) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if(s >= n) return;
+    uint32_t node = parent[(n - 1) + s];
+    while(node != kInvalid) {
+        __threadfence();
+        if(atomicAdd(&flags[node], 1u) == 0u) return;  // first arrival: sibling not done yet
+        __threadfence();
+        volatile BNode* vb = bnodes;
+        const uint32_t l = vb[node].left, r = vb[node].right;
+        float lo[3], hi[3], lo2[3], hi2[3];
+        if(l & kLeafBit) { const Aabb b = primBox[vals[l & ~kLeafBit]]; for(int a = 0; a < 3; ++a) { lo[a] = b.lo[a]; hi[a] = b.hi[a]; } }
+        else { for(int a = 0; a < 3; ++a) { lo[a] = vb[l].lo[a]; hi[a] = vb[l].hi[a]; } }
+        if(r & kLeafBit) { const Aabb b = primBox[vals[r & ~kLeafBit]]; for(int a = 0; a < 3; ++a) { lo2[a] = b.lo[a]; hi2[a] = b.hi[a]; } }
+        else { for(int a = 0; a < 3; ++a) { lo2[a] = vb[r].lo[a]; hi2[a] = vb[r].hi[a]; } }
+        for(int a = 0; a < 3; ++a) { vb[node].lo[a] = fminf(lo[a], lo2[a]); vb[node].hi[a] = fmaxf(hi[a], hi2[a]); }
+        node = parent[node];
+    }
+}
+
+__global__ void k_reset_flags(uint32_t* flags, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < n) flags[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Collapse the binary tree into 8-wide compressed nodes; one thread per wide node, level by level.
+struct LeafSourceTri { const float4* vertices; const uint32_t* indices; uint32_t vtxOff, idxOff; Tri* out; };
+struct LeafSourceInst { const InstTrav* inst; InstTrav* out; };
+
+__device__ __forceinline__ uint32_t refCount(uint32_t ref, const uint2* range) {
+    if(ref & kLeafBit) return 1u;
+    const uint2 r = range[ref];
+    return r.y - r.x + 1u;
+}
+__device__ __forceinline__ uint32_t refFirst(uint32_t ref, const uint2* range) { return (ref & kLeafBit) ? (ref & ~kLeafBit) : range[ref].x; }
+
+__device__ __forceinline__ void writeLeafPrim(const LeafSourceTri& src, uint32_t dst, uint32_t primId) {
+    const uint32_t i0 = src.indices[src.idxOff + 3 * primId], i1 = src.indices[src.idxOff + 3 * primId + 1], i2 = src.indices[src.idxOff + 3 * primId + 2];
+    const float4 a = src.vertices[2 * (size_t)(src.vtxOff + i0)], b = src.vertices[2 * (size_t)(src.vtxOff + i1)], c = src.vertices[2 * (size_t)(src.vtxOff + i2)];
+    float4* o = reinterpret_cast<float4*>(src.out + dst);
+    o[0] = make_float4(a.x, a.y, a.z, __uint_as_float(primId));
+    o[1] = make_float4(b.x, b.y, b.z, 0.0f);
+    o[2] = make_float4(c.x, c.y, c.z, 0.0f);
+}
+__device__ __forceinline__ void writeLeafPrim(const LeafSourceInst& src, uint32_t dst, uint32_t primId) { src.out[dst] = src.inst[primId]; }
+
+// Quantise one wide node from its children's boxes.  Conservative in exact arithmetic: the decoded
+// planes p + q * 2^e (exact in binary64) never cut into a child box.
+__device__ void quantizeNode(Node8& nd, const float (*clo)[3], const float (*chi)[3], const int* slotOfChild, int nChildren) {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for(int c = 0; c < nChildren; ++c)
+        for(int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], clo[c][a]); hi[a] = fmaxf(hi[a], chi[c][a]); }
+    nd.px = lo[0]; nd.py = lo[1]; nd.pz = lo[2];
+    uint8_t eb[3];
+    float scale[3];
+    for(int a = 0; a < 3; ++a) {
+        const float ext = hi[a] - lo[a];
+        int k = 0;
+        if(ext > 0.0f) (void)frexpf(ext / 255.0f, &k); else k = -120;
+        k = max(-120, min(120, k));
+        // fl(hi - lo) may round down: make sure 255 steps really reach hi
+        while((double)lo[a] + 255.0 * (double)__uint_as_float((uint32_t)(k + 127) << 23) < (double)hi[a]) ++k;
+        eb[a] = (uint8_t)(k + 127);
+        scale[a] = __uint_as_float((uint32_t)eb[a] << 23);
+    }
+    nd.ex = eb[0]; nd.ey = eb[1]; nd.ez = eb[2];
+    uint8_t* qlo[3] = {nd.qlox, nd.qloy, nd.qloz};
+    uint8_t* qhi[3] = {nd.qhix, nd.qhiy, nd.qhiz};
+    for(int s = 0; s < 8; ++s)
+        for(int a = 0; a < 3; ++a) { qlo[a][s] = 255; qhi[a][s] = 0; }  // empty: inverted box
+    for(int c = 0; c < nChildren; ++c) {
+        const int s = slotOfChild[c];
+        for(int a = 0; a < 3; ++a) {
+            const float inv = 1.0f / scale[a];
+            int ql = (int)floorf((clo[c][a] - lo[a]) * inv), qh = (int)ceilf((chi[c][a] - lo[a]) * inv);
+            ql = max(0, min(255, ql)); qh = max(0, min(255, qh));
+            while(ql > 0 && (double)lo[a] + (double)ql * (double)scale[a] > (double)clo[c][a]) --ql;
+            while(qh < 255 && (double)lo[a] + (double)qh * (double)scale[a] < (double)chi[c][a]) ++qh;
+            qlo[a][s] = (uint8_t)ql; qhi[a][s] = (uint8_t)qh;
+        }
+    }
+}
+
+template <class LeafSource>
+__global__ void k_collapse_level(const uint2* __restrict__ queueIn, const uint32_t* __restrict__ nInPtr, uint2* __restrict__ queueOut, uint32_t* nOutPtr,
+                                 uint32_t* nodeCounter, uint32_t* primCounter, const BNode* __restrict__ bnodes, const uint2* __restrict__ range,
+                                 const Aabb* __restrict__ primBox, const uint32_t* __restrict__ vals, Node8* __restrict__ nodes, uint32_t nodeOffset,
+                                 uint32_t primOffset, LeafSource leafSrc, uint32_t* __restrict__ wideRef) {
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if(item >= *nInPtr) return;
+    const uint2 it = queueIn[item];
+    const uint32_t bref = it.x, wide = it.y;
+
+    uint32_t c[8];
+    int n;
+    if(bref & kLeafBit) { c[0] = bref; n = 1; }
+    else { c[0] = bnodes[bref].left; c[1] = bnodes[bref].right; n = 2; }
+
+    // phase 0: open subtrees with more than kMaxLeafPrims primitives (largest surface first);
+    // phase 1: with free slots left, open small subtrees too (tighter boxes, one primitive per slot).
+    for(int phase = 0; phase < 2; ++phase) {
+        while(n < 8) {
+            int best = -1; float bestArea = -1.0f;
+            for(int k = 0; k < n; ++k) {
+                const uint32_t cnt = refCount(c[k], range);
+                const bool open = phase == 0 ? (cnt > (uint32_t)kMaxLeafPrims) : (cnt > 1u);
+                if(!open) continue;
+                float lo[3], hi[3];
+                loadRefBox(c[k], bnodes, primBox, vals, lo, hi);
+                const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+                const float area = dx * dy + dy * dz + dz * dx;
+                if(area > bestArea) { bestArea = area; best = k; }
+            }
+            if(best < 0) break;
+            const uint32_t r = c[best];
+            c[best] = bnodes[r].left;
+            c[n++] = bnodes[r].right;
+        }
+    }
+
+    float clo[8][3], chi[8][3];
+    float ctr[3] = {0, 0, 0}, nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for(int k = 0; k < n; ++k) {
+        loadRefBox(c[k], bnodes, primBox, vals, clo[k], chi[k]);
+        for(int a = 0; a < 3; ++a) { nlo[a] = fminf(nlo[a], clo[k][a]); nhi[a] = fmaxf(nhi[a], chi[k][a]); }
+    }
+    for(int a = 0; a < 3; ++a) ctr[a] = 0.5f * (nlo[a] + nhi[a]);
+
+    // greedy octant assignment: slot bit 2/1/0 = +x/+y/+z side of the node centre
+    int slotOfChild[8];
+    {
+        bool childDone[8] = {false, false, false, false, false, false, false, false};
+        bool slotDone[8] = {false, false, false, false, false, false, false, false};
+        float d[8][3];
+        for(int k = 0; k < n; ++k)
+            for(int a = 0; a < 3; ++a) d[k][a] = 0.5f * (clo[k][a] + chi[k][a]) - ctr[a];
+        for(int round = 0; round < n; ++round) {
+            float bestCost = -FLT_MAX; int bk = -1, bs = -1;
+            for(int k = 0; k < n; ++k) {
+                if(childDone[k]) continue;
+                for(int s = 0; s < 8; ++s) {
+                    if(slotDone[s]) continue;
+                    const float cost = ((s & 4) ? d[k][0] : -d[k][0]) + ((s & 2) ? d[k][1] : -d[k][1]) + ((s & 1) ? d[k][2] : -d[k][2]);
+                    if(cost > bestCost) { bestCost = cost; bk = k; bs = s; }
+                }
+            }
+            childDone[bk] = true; slotDone[bs] = true; slotOfChild[bk] = bs;
+        }
+    }
+
+    Node8 nd;
+    quantizeNode(nd, clo, chi, slotOfChild, n);
+
+    uint32_t refOfSlot[8];
+    for(int s = 0; s < 8; ++s) { refOfSlot[s] = kInvalid; nd.meta[s] = 0; }
+    uint32_t imask = 0, nInternal = 0, nPrims = 0;
+    for(int k = 0; k < n; ++k) {
+        refOfSlot[slotOfChild[k]] = c[k];
+        const uint32_t cnt = refCount(c[k], range);
+        if(cnt > (uint32_t)kMaxLeafPrims) { imask |= 1u << slotOfChild[k]; ++nInternal; } else nPrims += cnt;
+    }
+    const uint32_t childBase = nInternal ? atomicAdd(nodeCounter, nInternal) : 0u;
+    const uint32_t primBase = nPrims ? atomicAdd(primCounter, nPrims) : 0u;
+    const uint32_t qBase = nInternal ? atomicAdd(nOutPtr, nInternal) : 0u;
+    uint32_t ci = 0, po = 0;
+    for(int s = 0; s < 8; ++s) {
+        const uint32_t r = refOfSlot[s];
+        if(wideRef) wideRef[(size_t)wide * 8 + s] = r;
+        if(r == kInvalid) continue;
+        const uint32_t cnt = refCount(r, range);
+        if(cnt > (uint32_t)kMaxLeafPrims) {
+            nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+            queueOut[qBase + ci] = make_uint2(r, childBase + ci);
+            ++ci;
+        } else {
+            nd.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | po);
+            const uint32_t first = refFirst(r, range);
+            for(uint32_t k = 0; k < cnt; ++k) writeLeafPrim(leafSrc, primOffset + primBase + po + k, vals[first + k]);
+            po += cnt;
+        }
+    }
+    nd.imask = (uint8_t)imask;
+    nd.childBase = nodeOffset + childBase;
+    nd.primBase = primOffset + primBase;
+    nodes[nodeOffset + wide] = nd;
+}
+
+__global__ void k_collapse_seed(uint2* queue, uint32_t* counters, uint32_t n) {
+    // root item: binary node 0 (or the single leaf) -> wide node 0
+    queue[0] = make_uint2(n >= 2 ? 0u : kLeafBit, 0u);
+    counters[0] = 1; counters[1] = 0; counters[2] = 1; counters[3] = 0;
+}
+
+// Refit of the wide nodes after the binary boxes changed: re-quantise every node from wideRef.
+template <class LeafSource>
+__global__ void k_requantize(uint32_t nWide, Node8* __restrict__ nodes, uint32_t nodeOffset, uint32_t primOffset, const uint32_t* __restrict__ wideRef,
+                             const BNode* __restrict__ bnodes, const uint2* __restrict__ range, const Aabb* __restrict__ primBox,
+                             const uint32_t* __restrict__ vals, LeafSource leafSrc) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if(w >= nWide) return;
+    Node8 nd = nodes[nodeOffset + w];
+    float clo[8][3], chi[8][3];
+    int slotOfChild[8];
+    int n = 0;
+    for(int s = 0; s < 8; ++s) {
+        const uint32_t r = wideRef[(size_t)w * 8 + s];
+        if(r == kInvalid) continue;
+        loadRefBox(r, bnodes, primBox, vals, clo[n], chi[n]);
+        slotOfChild[n++] = s;
+        const uint32_t cnt = refCount(r, range);
+        if(cnt <= (uint32_t)kMaxLeafPrims) {
+            const uint32_t first = refFirst(r, range), off = nd.meta[s] & 31u;
+            for(uint32_t k = 0; k < cnt; ++k) writeLeafPrim(leafSrc, nd.primBase + off + k, vals[first + k]);
+        }
+    }
+    const uint8_t imask = nd.imask;
+    uint8_t meta[8];
+    for(int s = 0; s < 8; ++s) meta[s] = nd.meta[s];
+    const uint32_t cb = nd.childBase, pb = nd.primBase;
+    quantizeNode(nd, clo, chi, slotOfChild, n);
+    nd.imask = imask; nd.childBase = cb; nd.primBase = pb;
+    for(int s = 0; s < 8; ++s) nd.meta[s] = meta[s];
+    nodes[nodeOffset + w] = nd;
+    (void)primOffset;
+}
+
+__global__ void k_store_root_box(const int32_t* sceneBox, float* out, uint32_t n) {
+    if(threadIdx.x < 6) {
+        if(n == 0) out[threadIdx.x] = threadIdx.x < 3 ? 1.0f : -1.0f;  // empty: inverted
+        else out[threadIdx.x] = decodeFloat(sceneBox[threadIdx.x]);
+    }
+}
+
+inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+void radixSort(LbvhScratch& s, uint32_t n, cudaStream_t st) {
+    const uint32_t numTiles = cdiv(n, kSortTile);
+    int cur = 0;
+    for(int pass = 0; pass < 4; ++pass) {
+        const int shift = 8 * pass;
+        k_sort_hist<<<numTiles, kSortThreads, 0, st>>>(s.keys[cur], n, shift, numTiles, s.hist);
+        k_sort_scan<<<1, 1024, 0, st>>>(s.hist, 256u * numTiles);
+        k_sort_scatter<<<numTiles, kSortThreads, 0, st>>>(s.keys[cur], s.vals[cur], n, shift, numTiles, s.hist, s.keys[cur ^ 1], s.vals[cur ^ 1]);
+        s.launches += 3;
+        cur ^= 1;
+    }
+    s.sortedBuf = (uint32_t)cur;  // 4 passes -> back in buffer 0
+}
+
+template <class LeafSource>
+void collapseHostDriven(LbvhScratch& s, uint32_t n, Node8* nodes, uint32_t nodeOffset, uint32_t primOffset, LeafSource leafSrc, uint32_t* nNodes,
+                        uint32_t* nPrims, cudaStream_t st) {
+    k_collapse_seed<<<1, 1, 0, st>>>(s.queue[0], s.counters, n);
+    s.launches++;
+    int in = 0;
+    uint32_t count = 1;
+    const uint32_t* keysUnused = nullptr; (void)keysUnused;
+    while(count) {
+        k_collapse_level<LeafSource><<<cdiv(count, 64), 64, 0, st>>>(s.queue[in], &s.counters[in], s.queue[in ^ 1], &s.counters[in ^ 1], &s.counters[2],
+                                                                      &s.counters[3], s.bnodes, s.range, s.primBox, s.vals[s.sortedBuf], nodes, nodeOffset,
+                                                                      primOffset, leafSrc, s.wideRef);
+        s.launches++;
+        uint32_t h[4];
+        RG_CUDA_OK(cudaMemcpyAsync(h, s.counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+        RG_CUDA_OK(cudaStreamSynchronize(st));
+        count = h[in ^ 1];
+        *nNodes = h[2]; *nPrims = h[3];
+        RG_CUDA_OK(cudaMemsetAsync(&s.counters[in], 0, sizeof(uint32_t), st));
+        in ^= 1;
+    }
+}
+
+}  // namespace
+
+void LbvhScratch::reserve(uint32_t n) {
+    if(n <= capacity) return;
+    release();
+    capacity = n;
+    const uint32_t numTiles = cdiv(n, kSortTile);
+    RG_CUDA_OK(cudaMalloc(&primBox, sizeof(Aabb) * (size_t)n));
+    for(int i = 0; i < 2; ++i) {
+        RG_CUDA_OK(cudaMalloc(&keys[i], 4 * (size_t)n));
+        RG_CUDA_OK(cudaMalloc(&vals[i], 4 * (size_t)n));
+        RG_CUDA_OK(cudaMalloc(&queue[i], sizeof(uint2) * (size_t)n));
+    }
+    RG_CUDA_OK(cudaMalloc(&hist, 4 * 256 * (size_t)numTiles));
+    RG_CUDA_OK(cudaMalloc(&bnodes, sizeof(BNode) * (size_t)n));
+    RG_CUDA_OK(cudaMalloc(&range, sizeof(uint2) * (size_t)n));
+    RG_CUDA_OK(cudaMalloc(&parent, 4 * 2 * (size_t)n));
+    RG_CUDA_OK(cudaMalloc(&flags, 4 * (size_t)n));
+    RG_CUDA_OK(cudaMalloc(&counters, 4 * 16));
+    RG_CUDA_OK(cudaMalloc(&sceneBox, 4 * 6));
+    RG_CUDA_OK(cudaMalloc(&wideRef, 4 * 8 * (size_t)n));
+}
+
+void LbvhScratch::release() {
+    cudaFree(primBox); cudaFree(hist); cudaFree(bnodes); cudaFree(range); cudaFree(parent); cudaFree(flags); cudaFree(counters); cudaFree(sceneBox);
+    cudaFree(wideRef);
+    for(int i = 0; i < 2; ++i) { cudaFree(keys[i]); cudaFree(vals[i]); cudaFree(queue[i]); keys[i] = vals[i] = nullptr; queue[i] = nullptr; }
+    primBox = nullptr; hist = nullptr; bnodes = nullptr; range = nullptr; parent = nullptr; flags = nullptr; counters = nullptr; sceneBox = nullptr;
+    wideRef = nullptr;
+    capacity = 0;
+}
+
+namespace {
+void lbvhCommon(LbvhScratch& s, uint32_t n, cudaStream_t st) {
+    k_morton<<<cdiv(n, 256), 256, 0, st>>>(s.primBox, n, s.sceneBox, s.keys[0], s.vals[0]);
+    s.launches++;
+    radixSort(s, n, st);
+    if(n >= 2) {
+        k_hierarchy<<<cdiv(n - 1, 128), 128, 0, st>>>(s.keys[s.sortedBuf], n, s.bnodes, s.range, s.parent, s.flags);
+        k_refit_binary<<<cdiv(n, 128), 128, 0, st>>>(n, s.bnodes, s.primBox, s.vals[s.sortedBuf], s.parent, s.flags);
+        s.launches += 2;
+    }
+}
+}  // namespace
+
+void buildBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t nodeOffset, Tri* trisBase, uint32_t triOffset, uint32_t* nNodes,
+               uint32_t* nTris, float* rootBoxOut, cudaStream_t st) {
+    const uint32_t n = src.nTri;
+    *nNodes = 0; *nTris = 0;
+    s.reserve(n ? n : 1);
+    k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters);
+    s.launches++;
+    if(n == 0) { k_store_root_box<<<1, 32, 0, st>>>(s.sceneBox, rootBoxOut, 0); s.launches++; RG_CUDA_OK(cudaStreamSynchronize(st)); return; }
+    k_tri_boxes<<<cdiv(n, 256), 256, 0, st>>>((const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, n, s.primBox, s.sceneBox);
+    s.launches++;
+    lbvhCommon(s, n, st);
+    LeafSourceTri ls{(const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, trisBase};
+    collapseHostDriven(s, n, nodesBase, nodeOffset, triOffset, ls, nNodes, nTris, st);
+    k_store_root_box<<<1, 32, 0, st>>>(s.sceneBox, rootBoxOut, n);
+    s.launches++;
+    RG_CUDA_OK(cudaStreamSynchronize(st));
+}
+
+void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t nodeOffset, uint32_t nNodes, Tri* trisBase, uint32_t triOffset,
+               float* rootBoxOut, cudaStream_t st) {
+    const uint32_t n = src.nTri;
+    if(n == 0) return;
+    k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters + 4);  // keep queue / node counters; counters+4 is scratch
+    k_tri_boxes<<<cdiv(n, 256), 256, 0, st>>>((const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, n, s.primBox, s.sceneBox);
+    s.launches += 2;
+    if(n >= 2) {
+        k_reset_flags<<<cdiv(n - 1, 256), 256, 0, st>>>(s.flags, n - 1);
+        k_refit_binary<<<cdiv(n, 128), 128, 0, st>>>(n, s.bnodes, s.primBox, s.vals[s.sortedBuf], s.parent, s.flags);
+        s.launches += 2;
+    }
+    LeafSourceTri ls{(const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, trisBase};
+    k_requantize<LeafSourceTri><<<cdiv(nNodes, 64), 64, 0, st>>>(nNodes, nodesBase, nodeOffset, triOffset, s.wideRef, s.bnodes, s.range, s.primBox,
+                                                                 s.vals[s.sortedBuf], ls);
+    k_store_root_box<<<1, 32, 0, st>>>(s.sceneBox, rootBoxOut, n);
+    s.launches += 2;
+}
+
+void buildTlas(LbvhScratch& s, const InstTrav* instTrav, const InstShade* instShade, const float* meshBoxes, uint32_t nInst, Node8* tlasNodes,
+               InstTrav* tlasLeavesOut, cudaStream_t st) {
+    const uint32_t n = nInst;
+    s.reserve(n ? n : 1);
+    k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters);
+    s.launches++;
+    if(n == 0) return;
+    k_inst_boxes<<<cdiv(n, 128), 128, 0, st>>>(instShade, meshBoxes, n, s.primBox, s.sceneBox);
+    s.launches++;
+    lbvhCommon(s, n, st);
+    LeafSourceInst ls{instTrav, tlasLeavesOut};
+    uint32_t nNodes = 0, nPrims = 0;
+    collapseHostDriven(s, n, tlasNodes, 0, 0, ls, &nNodes, &nPrims, st);
+}
+
+}  // namespace rg

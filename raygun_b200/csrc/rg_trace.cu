@@ -1,0 +1,656 @@
+// rg_trace.cu -- persistent-thread ray generation + two-level wide-BVH traversal + Whitted shading for sm_100a.
+//
+// Replaces the reference's ray-tracing pipeline (raygun/render/raytracer.cpp:99 traceRaysKHR) and its four shaders:
+//   raygen      resources/shaders/raygen.rgen:30-39, raygen.h:37-115
+//   closest hit resources/shaders/closesthit.rchit:74-268
+//   miss 0 / 1  resources/shaders/miss.rmiss:38-83, shadowMiss.rmiss:30-34
+// B200 has no RT cores, so traceRayEXT becomes a software traversal of compressed 8-wide nodes (rg_types.cuh) and
+// the shader recursion becomes an explicit per-lane stack of frames: each lane owns one pixel and walks that pixel's
+// ray tree depth-first in the reference's order (shadow -> reflection -> refraction), with ONE mutable payload, so
+// every stale-state effect of the GLSL (SURVEY.md 8a hazards 1-6) is reproduced.  Lanes that finish a pixel are
+// refilled from a global work counter with warp vote / shuffle compaction, so a warp keeps traversing 32 live rays.
+//
+// Ray / triangle arithmetic is bit-identical to the oracle (explicitly rounded operations, never contracted):
+// watertight Woop test, t preserved across the instance transform, ties resolved to the smallest (instance, primitive).
+#include "rg_trace.cuh"
+
+#include <cuda_fp16.h>
+
+#include "../../include/rgb200.h"
+
+namespace rg {
+
+namespace {
+
+enum { RT_GENERIC = 0, RT_SHADOW_TRACE = 1, RT_SHADOW_INTERNAL = 2 };
+enum { CNT_PRIMARY = 0, CNT_SHADOW = 1, CNT_REFLECT = 2, CNT_REFRACT = 3, CNT_SKY = 4, CNT_NODES = 5, CNT_TRIS = 6, CNT_INST = 7, CNT_N = 8 };
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 normalize(V3 a) { const float r = 1.0f / sqrtf(dot(a, a)); return a * r; }
+__device__ __forceinline__ V3 mix3(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float glmod(float x, float y) { return x - y * floorf(x / y); }
+__device__ __forceinline__ V3 reflect3(V3 I, V3 N) { return I - N * (dot(N, I) * 2.0f); }
+__device__ __forceinline__ V3 refract3(V3 I, V3 N, float eta) {
+    const float d = dot(N, I);
+    const float k = 1.0f - eta * eta * (1.0f - d * d);
+    if(!(k >= 0.0f)) return v3(0.0f, 0.0f, 0.0f);
+    return eta * I - (eta * d + sqrtf(k)) * N;
+}
+
+// ------------------------------------------------------------------------------------------------ traversal
+struct RayCtx {
+    float ox, oy, oz, dx, dy, dz;
+    float inx, iny, inz;  // 1/d scaled down (near planes)
+    float ifx, ify, ifz;  // 1/d scaled up (far planes)  -> the slab test is conservative
+    float Sx, Sy, Sz;     // Woop shear
+    uint32_t octinv;      // bit 2/1/0 set when d.x/d.y/d.z >= 0
+    int kx, ky, kz;
+};
+
+__device__ __forceinline__ float sel3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
+
+__device__ __forceinline__ void setupRay(RayCtx& r, float ox, float oy, float oz, float dx, float dy, float dz) {
+    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+    const float eps = 1e-30f;
+    const float ix = 1.0f / (fabsf(dx) > eps ? dx : copysignf(eps, dx));
+    const float iy = 1.0f / (fabsf(dy) > eps ? dy : copysignf(eps, dy));
+    const float iz = 1.0f / (fabsf(dz) > eps ? dz : copysignf(eps, dz));
+    const float lo = 1.0f - 4.8e-7f, hi = 1.0f + 4.8e-7f;
+    r.inx = ix * lo; r.iny = iy * lo; r.inz = iz * lo;
+    r.ifx = ix * hi; r.ify = iy * hi; r.ifz = iz * hi;
+    r.octinv = (dx >= 0.0f ? 4u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 1u : 0u);
+    const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+    const int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+    int kx = kz == 2 ? 0 : kz + 1;
+    int ky = kx == 2 ? 0 : kx + 1;
+    const float dkz = sel3(kz, dx, dy, dz);
+    if(dkz < 0.0f) { const int t = kx; kx = ky; ky = t; }
+    r.kx = kx; r.ky = ky; r.kz = kz;
+    r.Sx = __fdiv_rn(sel3(kx, dx, dy, dz), dkz);
+    r.Sy = __fdiv_rn(sel3(ky, dx, dy, dz), dkz);
+    r.Sz = __frcp_rn(dkz);
+}
+
+template <int J>
+__device__ __forceinline__ float byteF(uint32_t w) {  // byte J of w as float: PRMT into the mantissa of 2^23, one FADD
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + J)) - 8388608.0f;
+}
+
+template <int J>
+__device__ __forceinline__ void childTest(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, uint32_t meta4, float anx,
+                                          float any_, float anz, float onx, float ony, float onz, float afx, float afy, float afz, float ofx, float ofy,
+                                          float ofz, float tmin, float tmax, uint32_t octinv, uint32_t& hitmask) {
+    const float tnx = fmaf(byteF<J>(nx), anx, onx), tny = fmaf(byteF<J>(ny), any_, ony), tnz = fmaf(byteF<J>(nz), anz, onz);
+    const float tfx = fmaf(byteF<J>(fx), afx, ofx), tfy = fmaf(byteF<J>(fy), afy, ofy), tfz = fmaf(byteF<J>(fz), afz, ofz);
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    if(tn <= tf) {
+        const uint32_t m = (meta4 >> (8 * J)) & 0xffu;
+        const uint32_t inner = ((m & 0x18u) == 0x18u) ? 1u : 0u;
+        const uint32_t idx = inner ? (24u + ((m & 7u) ^ octinv)) : (m & 31u);
+        hitmask |= (m >> 5) << idx;
+    }
+}
+
+// Watertight ray / triangle test (Woop, Benthin, Wald 2013), no culling; operation order == oracle/orc_scene.cpp intersectTri.
+__device__ __forceinline__ bool triTest(const RayCtx& r, const float4 p0, const float4 p1, const float4 p2, float tmin, float& tOut, float& uOut,
+                                        float& vOut) {
+    const float A0 = __fsub_rn(p0.x, r.ox), A1 = __fsub_rn(p0.y, r.oy), A2 = __fsub_rn(p0.z, r.oz);
+    const float B0 = __fsub_rn(p1.x, r.ox), B1 = __fsub_rn(p1.y, r.oy), B2 = __fsub_rn(p1.z, r.oz);
+    const float C0 = __fsub_rn(p2.x, r.ox), C1 = __fsub_rn(p2.y, r.oy), C2 = __fsub_rn(p2.z, r.oz);
+    const float Akz = sel3(r.kz, A0, A1, A2), Bkz = sel3(r.kz, B0, B1, B2), Ckz = sel3(r.kz, C0, C1, C2);
+    const float Ax = __fsub_rn(sel3(r.kx, A0, A1, A2), __fmul_rn(r.Sx, Akz)), Ay = __fsub_rn(sel3(r.ky, A0, A1, A2), __fmul_rn(r.Sy, Akz));
+    const float Bx = __fsub_rn(sel3(r.kx, B0, B1, B2), __fmul_rn(r.Sx, Bkz)), By = __fsub_rn(sel3(r.ky, B0, B1, B2), __fmul_rn(r.Sy, Bkz));
+    const float Cx = __fsub_rn(sel3(r.kx, C0, C1, C2), __fmul_rn(r.Sx, Ckz)), Cy = __fsub_rn(sel3(r.ky, C0, C1, C2), __fmul_rn(r.Sy, Ckz));
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+    if(U == 0.0f || V == 0.0f || W == 0.0f) {  // rare: exact edge hit, redo in binary64 (products of floats are exact there)
+        U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
+        V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
+        W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
+    }
+    if((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    const float det = __fadd_rn(__fadd_rn(U, V), W);
+    if(det == 0.0f) return false;
+    const float Az = __fmul_rn(r.Sz, Akz), Bz = __fmul_rn(r.Sz, Bkz), Cz = __fmul_rn(r.Sz, Ckz);
+    const float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
+    const float rcp = __frcp_rn(det);
+    const float t = __fmul_rn(T, rcp);
+    if(!(t > tmin)) return false;
+    tOut = t; uOut = __fmul_rn(V, rcp); vOut = __fmul_rn(W, rcp);
+    return true;
+}
+
+// Closest hit in [tmin, tmax] (exclusive).  hit.inst == kInvalid on miss.
+template <bool COUNT>
+__device__ __forceinline__ void traverse(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin, float tmax,
+                                         Hit& hit, uint32_t* cnt) {
+    hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.inst = kInvalid; hit.prim = kInvalid;
+    if(P.nInst == 0) return;
+    if(dx == 0.0f && dy == 0.0f && dz == 0.0f) return;       // zero direction (refract on total internal reflection): miss
+    if(!(dx == dx && dy == dy && dz == dz && ox == ox && oy == oy && oz == oz)) return;  // NaN ray: miss
+
+    RayCtx r;
+    setupRay(r, ox, oy, oz, dx, dy, dz);
+    uint2 stack[kStackSize];
+    int sp = 0;
+    uint2 ng = make_uint2(0u, 0x80000000u);
+    uint2 tg = make_uint2(0u, 0u);
+    bool inBlas = false;
+    uint32_t curInst = kInvalid;
+    const Node8* nodes = P.tlasNodes;
+
+    while(true) {
+        if(ng.y & 0xff000000u) {
+            const int bit = 31 - __clz(ng.y);
+            ng.y &= ~(1u << bit);
+            const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
+            const uint32_t rel = __popc(ng.y & 0xffu & ((1u << slot) - 1u));
+            if((ng.y & 0xff000000u) && sp < kStackSize) stack[sp++] = ng;
+            const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
+            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            if(COUNT) cnt[CNT_NODES]++;
+            const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
+                        sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
+            const float px = __uint_as_float(n0.x) - r.ox, py = __uint_as_float(n0.y) - r.oy, pz = __uint_as_float(n0.z) - r.oz;
+            const float anx = sx * r.inx, any_ = sy * r.iny, anz = sz * r.inz, onx = px * r.inx, ony = py * r.iny, onz = pz * r.inz;
+            const float afx = sx * r.ifx, afy = sy * r.ify, afz = sz * r.ifz, ofx = px * r.ifx, ofy = py * r.ify, ofz = pz * r.ifz;
+            const bool negx = r.dx < 0.0f, negy = r.dy < 0.0f, negz = r.dz < 0.0f;
+            uint32_t hitmask = 0;
+            {   // slots 0..3
+                const uint32_t lx = n2.x, ly = n2.z, lz = n3.x, hx = n3.z, hy = n4.x, hz = n4.z;
+                const uint32_t nx = negx ? hx : lx, fx = negx ? lx : hx, ny = negy ? hy : ly, fy = negy ? ly : hy, nz = negz ? hz : lz, fz = negz ? lz : hz;
+                childTest<0>(nx, ny, nz, fx, fy, fz, n1.z, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+                childTest<1>(nx, ny, nz, fx, fy, fz, n1.z, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+                childTest<2>(nx, ny, nz, fx, fy, fz, n1.z, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+                childTest<3>(nx, ny, nz, fx, fy, fz, n1.z, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+            }
+            {   // slots 4..7
+                const uint32_t lx = n2.y, ly = n2.w, lz = n3.y, hx = n3.w, hy = n4.y, hz = n4.w;
+                const uint32_t nx = negx ? hx : lx, fx = negx ? lx : hx, ny = negy ? hy : ly, fy = negy ? ly : hy, nz = negz ? hz : lz, fz = negz ? lz : hz;
+                childTest<0>(nx, ny, nz, fx, fy, fz, n1.w, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+                childTest<1>(nx, ny, nz, fx, fy, fz, n1.w, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+                childTest<2>(nx, ny, nz, fx, fy, fz, n1.w, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+                childTest<3>(nx, ny, nz, fx, fy, fz, n1.w, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+            }
+            ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+            tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+        } else {
+            tg = ng;
+            ng = make_uint2(0u, 0u);
+        }
+
+        while(tg.y) {
+            const int bit = __ffs(tg.y) - 1;
+            tg.y &= tg.y - 1u;
+            if(!inBlas) {
+                const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + (tg.x + bit));
+                const uint4 l3 = __ldg(lp + 3);
+                if(l3.x == kInvalid) continue;  // instance of an empty mesh
+                const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+                if(sp + 3 <= kStackSize) {
+                    if(tg.y) stack[sp++] = tg;
+                    if(ng.y & 0xff000000u) stack[sp++] = ng;
+                    stack[sp++] = make_uint2(kInvalid, 0u);
+                } else continue;  // stack exhausted: skip (never with sane scenes)
+                if(COUNT) cnt[CNT_INST]++;
+                // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
+                const float* w0 = reinterpret_cast<const float*>(&l0); const float* w1 = reinterpret_cast<const float*>(&l1);
+                const float* w2 = reinterpret_cast<const float*>(&l2);
+                const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0[0], ox), __fmul_rn(w0[1], oy)), __fmul_rn(w0[2], oz)), w0[3]);
+                const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1[0], ox), __fmul_rn(w1[1], oy)), __fmul_rn(w1[2], oz)), w1[3]);
+                const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2[0], ox), __fmul_rn(w2[1], oy)), __fmul_rn(w2[2], oz)), w2[3]);
+                const float odx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
+                const float ody = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
+                const float odz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
+                if(odx == 0.0f && ody == 0.0f && odz == 0.0f) { sp -= 1; if(ng.y & 0xff000000u) sp -= 1; if(tg.y) sp -= 1; continue; }
+                setupRay(r, oox, ooy, ooz, odx, ody, odz);
+                curInst = l3.y;
+                inBlas = true;
+                nodes = P.blasNodes;
+                ng = make_uint2(l3.x, 0x80000000u);
+                tg = make_uint2(0u, 0u);
+                break;
+            } else {
+                const float4* tp = reinterpret_cast<const float4*>(P.tris + (tg.x + bit));
+                const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+                if(COUNT) cnt[CNT_TRIS]++;
+                float t, u, v;
+                if(triTest(r, p0, p1, p2, tmin, t, u, v)) {
+                    const uint32_t prim = __float_as_uint(p0.w);
+                    if(t < hit.t || (t == hit.t && t < tmax && (curInst < hit.inst || (curInst == hit.inst && prim < hit.prim)))) {
+                        hit.t = t; hit.u = u; hit.v = v; hit.inst = curInst; hit.prim = prim;
+                    }
+                }
+            }
+        }
+
+        if(!(ng.y & 0xff000000u)) {
+            bool done = false;
+            while(true) {
+                if(sp == 0) { done = true; break; }
+                ng = stack[--sp];
+                if(ng.x == kInvalid) {  // leave the instance: back to the world-space ray
+                    inBlas = false; nodes = P.tlasNodes;
+                    setupRay(r, ox, oy, oz, dx, dy, dz);
+                    continue;
+                }
+                break;
+            }
+            if(done) break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ shading
+// raygen.h:37-67
+__constant__ float2 c_aaOffsets[3][8] = {
+    {{0.25f, 0.25f}, {-0.25f, -0.25f}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}},
+    {{-0.125f, -0.375f}, {0.375f, -0.125f}, {-0.375f, 0.125f}, {0.125f, 0.375f}, {0, 0}, {0, 0}, {0, 0}, {0, 0}},
+    {{0.0625f, -0.1875f}, {-0.0625f, 0.1875f}, {0.3125f, 0.0625f}, {-0.1875f, -0.3125f}, {-0.3125f, 0.3125f}, {-0.4375f, -0.0625f}, {0.1875f, 0.4375f}, {0.4375f, -0.4375f}},
+};
+__device__ __forceinline__ float2 aaOffset(int numSamples, int i) {
+    const int n = numSamples < 8 ? numSamples : 8;
+    if(n < 2) return make_float2(0.0f, 0.0f);
+    return c_aaOffsets[n == 2 ? 0 : (n <= 4 ? 1 : 2)][i & 7];
+}
+
+// miss.rmiss:38-74 with the constants of :78; normalize(0) is kept 0 (SURVEY hazard 7)
+__device__ V3 skyColor(V3 d, V3 lightDir) {
+    const bool zero = d.x == 0.0f && d.y == 0.0f && d.z == 0.0f;
+    const V3 rayDir = zero ? v3(0, 0, 0) : normalize(d);
+    const float y = fabsf(d.y + 1.5f) / 3.0f;
+    const V3 sd = normalize(-lightDir) - rayDir;
+    float sun = 1.0f - sqrtf(dot(sd, sd));
+    sun = clampf(sun, 0.0f, 2.0f);
+    float glow = clampf(sun, 0.0f, 1.0f);
+    sun = powf(sun, 80.0f);
+    sun *= 1000.0f;
+    sun = clampf(sun, 0.0f, 16.0f);
+    glow = powf(glow, 6.0f) * 1.0f;
+    glow = powf(glow, y);
+    glow = clampf(glow, 0.0f, 1.0f);
+    sun *= powf(y * y, 1.0f / 1.65f);
+    glow *= powf(y * y, 1.0f / 2.0f);
+    sun += glow;
+    const V3 sunColor = v3(1.0f, 0.6f, 0.05f) * sun;
+    const float atmosphere = sqrtf(1.0f - y);
+    float scatter = powf(4.0f - lightDir.y, 1.0f / 15.0f);
+    scatter = 1.0f - clampf(scatter, 0.8f, 1.0f);
+    const V3 scatterColor = mix3(v3(1.0f, 1.0f, 1.0f), v3(1.0f, 0.3f, 0.0f) * 1.5f, scatter);
+    const V3 skyScatter = mix3(v3(0.2f, 0.4f, 0.8f), scatterColor, atmosphere / 1.3f);
+    return sunColor + skyScatter;
+}
+
+// frame layout (words) in local memory
+enum {
+    F_ORG = 0, F_DIR = 3, F_N = 6, F_T = 9, F_DIFF = 10, F_SPEC = 13, F_TRANSP = 16, F_REFL = 17, F_ROUGH = 18, F_IOR = 19, F_EMIS = 20, F_FLAGS = 21,
+    F_BASE = 22, F_RCOL = 25, F_RDEPTH = 28, F_RECDEPTH = 29, F_WORDS = 30
+};
+enum { FR_GEN = 0, FR_SHI = 1 };
+enum { ST_SHADOW_RET = 0, ST_TRY_REFLECT = 1, ST_REFLECT_RET = 2, ST_TRY_REFRACT = 3, ST_REFRACT_RET_FRONT = 4, ST_REFRACT_RET_BACK = 5, ST_COMBINE = 6 };
+
+__device__ __forceinline__ uint32_t f2h(float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); }
+__device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) { return make_uint2(f2h(x) | (f2h(y) << 16), f2h(z) | (f2h(w) << 16)); }
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_trace(const TraceParams P) {
+    __shared__ float s_ubo[48];
+    if(threadIdx.x < 48) s_ubo[threadIdx.x] = P.ubo[threadIdx.x];
+    __syncthreads();
+    const float* VI = s_ubo;       // viewInverse, column-major
+    const float* PI = s_ubo + 16;  // projInverse
+    const int numSamples = __float_as_int(s_ubo[35]);
+    const V3 L = v3(s_ubo[36], s_ubo[37], s_ubo[38]);
+    int maxRec = __float_as_int(s_ubo[39]);
+    maxRec = maxRec > kMaxRecursions ? kMaxRecursions : maxRec;
+    const bool strictIeee = (P.flags & RG_STRICT_IEEE) != 0;
+
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t tilesX = (P.rw + 7) / 8, tilesY = (P.rh + 3) / 4;
+    const uint32_t total = tilesX * tilesY * 32u;
+
+    float fr[kMaxFrames][F_WORDS];
+    uint32_t cnt[CNT_N];
+#pragma unroll
+    for(int k = 0; k < CNT_N; ++k) cnt[k] = 0;
+
+    // per-pixel state
+    bool active = false, exhausted = false;
+    uint32_t pix = 0, lx = 0, ly = 0;
+    int sample = 0;
+    V3 accColor = v3(0, 0, 0), accNormal = v3(0, 0, 0), accRough = v3(0, 0, 0);
+    float accRoughA = 0, accContrib = 0, accDepth = 0;
+    // payload (payload.h:29-39)
+    V3 hv = v3(0, 0, 0), pNormal = v3(0, 0, 0), pRough = v3(0, 0, 0);
+    float pRoughA = 0, pContrib = 0, depth = 0, curIOR = 1.0f, refDepth = 0;
+    int recDepth = 0;
+    int sp = 0;  // frames
+    // pending ray
+    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 0);
+    float rtmin = 0, rtmax = 0;
+    int rayType = RT_GENERIC, missIndex = 0, rayKind = CNT_PRIMARY;
+    // camera origin: viewInverse * (0,0,0,1) in GLM order (c0*0 + c1*0) + (c2*0 + c3*1)
+    const V3 camO = v3((VI[0] * 0.0f + VI[4] * 0.0f) + (VI[8] * 0.0f + VI[12] * 1.0f), (VI[1] * 0.0f + VI[5] * 0.0f) + (VI[9] * 0.0f + VI[13] * 1.0f),
+                       (VI[2] * 0.0f + VI[6] * 0.0f) + (VI[10] * 0.0f + VI[14] * 1.0f));
+
+    auto primaryRay = [&](int i) {
+        const float2 off = aaOffset(numSamples, i);
+        const float pcx = (float)(P.rx0 + lx) + 0.5f + off.x, pcy = (float)(P.ry0 + ly) + 0.5f + off.y;
+        const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
+        // target = projInverse * (d.x, d.y, 1, 1); direction = viewInverse * (normalize(target.xyz), 0)
+        const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
+                          (PI[2] * ddx + PI[6] * ddy) + (PI[10] + PI[14]));
+        const V3 nt = normalize(tgt);
+        rd = v3((VI[0] * nt.x + VI[4] * nt.y) + (VI[8] * nt.z), (VI[1] * nt.x + VI[5] * nt.y) + (VI[9] * nt.z), (VI[2] * nt.x + VI[6] * nt.y) + (VI[10] * nt.z));
+        ro = camO; rtmin = 0.001f; rtmax = 10000.0f;
+        rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_PRIMARY;
+        hv = v3(0, 0, 0); pNormal = v3(0, 0, 0); pRough = v3(0, 0, 0); pRoughA = 0; pContrib = 0;
+        depth = 0; refDepth = 0; curIOR = 1.0f; recDepth = 0; sp = 0;
+    };
+
+    while(true) {
+        // ---- refill idle lanes (warp vote + prefix compaction over one atomic)
+        uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if(idle) {
+            if(!exhausted && (idle == 0xffffffffu || __popc(idle) >= 8)) {
+                const int n = __popc(idle), leader = __ffs(idle) - 1;
+                uint32_t basew = 0;
+                if((int)lane == leader) basew = atomicAdd(P.workCounter, (uint32_t)n);
+                basew = __shfl_sync(0xffffffffu, basew, leader);
+                if(!active) {
+                    const uint32_t w = basew + __popc(idle & ((1u << lane) - 1u));
+                    if(w < total) {
+                        const uint32_t tile = w >> 5, l = w & 31u;
+                        lx = (tile % tilesX) * 8u + (l & 7u); ly = (tile / tilesX) * 4u + (l >> 3);
+                        if(lx < P.rw && ly < P.rh) {
+                            active = true; pix = ly * P.rw + lx; sample = 0;
+                            accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
+                            primaryRay(0);
+                        }
+                    }
+                }
+                if(basew + (uint32_t)n >= total) exhausted = true;
+                idle = __ballot_sync(0xffffffffu, !active);
+            }
+            if(exhausted && idle == 0xffffffffu) break;
+        }
+        if(!active) continue;
+
+        // ---- trace the pending ray
+        Hit hit;
+        cnt[rayKind]++;
+        traverse<COUNT>(P, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmin, rtmax, hit, cnt);
+        const bool found = hit.inst != kInvalid;
+        if(rayKind == CNT_PRIMARY && sample == 0 && P.idInst) { P.idInst[pix] = hit.inst; P.idPrim[pix] = hit.prim; }
+
+        // ---- shade: closest hit or miss, then resume suspended frames until a new ray is issued
+        bool issue = false;   // a new ray is pending
+        if(found) {
+            // closesthit.rchit:96-109
+            const uint4 is3 = __ldg(reinterpret_cast<const uint4*>(P.instShade + hit.inst) + 3);
+            const uint32_t vtxOff = is3.x, idxOff = is3.y, matOff = is3.z;
+            const uint32_t i0 = __ldg(P.indices + idxOff + 3 * hit.prim), i1 = __ldg(P.indices + idxOff + 3 * hit.prim + 1),
+                           i2 = __ldg(P.indices + idxOff + 3 * hit.prim + 2);
+            const float4 v0p = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0));
+            const float4 n0 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0) + 1), n1 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i1) + 1),
+                         n2 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i2) + 1);
+            const float4* mp = P.materials + 4 * (size_t)(matOff + __float_as_uint(v0p.w));
+            const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+            V3 diffuse = v3(m0.x, m0.y, m0.z), specular = v3(m1.x, m1.y, m1.z);
+            const float transparency = m0.w; float reflectivity = m1.w;
+            const float roughness = m2.x, ior = m2.y, emission = m3.x;
+            const uint32_t effectId = __float_as_uint(m2.z), rayConsumption = __float_as_uint(m2.w);
+
+            const float b0 = 1.0f - hit.u - hit.v;
+            const V3 origin = ro + rd * hit.t;                                        // :114
+            const V3 vn = v3(n0.x, n0.y, n0.z) * b0 + v3(n1.x, n1.y, n1.z) * hit.u + v3(n2.x, n2.y, n2.z) * hit.v;  // :117
+            const float4* ow = reinterpret_cast<const float4*>(P.instShade + hit.inst);
+            const float4 o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2);
+            V3 n = normalize(v3(o0.x * vn.x + o0.y * vn.y + o0.z * vn.z, o1.x * vn.x + o1.y * vn.y + o1.z * vn.z, o2.x * vn.x + o2.y * vn.y + o2.z * vn.z));  // :118-119
+
+            if(effectId == 1u) {  // gridEffect, :74-91
+                const float aa = (refDepth + hit.t + 8.0f) / 30.0f;
+                const float aa2 = aa / 2.0f;
+                float minmod = fminf(fabsf(glmod((origin.x + 1000.0f) * 10.0f + aa2, 20.0f) - aa2), fabsf(glmod((origin.z + 1000.0f) * 10.0f + aa2, 20.0f) - aa2));
+                if(minmod < aa2) {
+                    minmod -= aa2 - (aa * aa) / 3.0f;
+                    minmod *= 3.0f / (aa * aa);
+                    const float f = mixf(aa / 10.0f, 1.0f, minmod);
+                    diffuse = diffuse * f; specular = specular * f; reflectivity *= f;
+                }
+                if(glmod((origin.x + 1000.0f) * 5.0f, 20.0f) < 10.0f && glmod((origin.z + 1000.0f) * 5.0f, 20.0f) < 10.0f) reflectivity *= 1.5f;
+            }
+
+            if(rayType == RT_SHADOW_INTERNAL) {  // :125-152
+                const float thick = clampf(hit.t * (1.0f - transparency) * 10.0f, 0.0f, 1.0f);
+                const V3 nd = normalize(v3(1.1f - diffuse.x, 1.1f - diffuse.y, 1.1f - diffuse.z));
+                const V3 shadowCol = hv - mix3(v3(0, 0, 0), v3(nd.x + 0.1f, nd.y + 0.1f, nd.z + 0.1f), thick);
+                if(recDepth < maxRec) {
+                    float* f = fr[sp++];
+                    f[F_ORG] = shadowCol.x; f[F_ORG + 1] = shadowCol.y; f[F_ORG + 2] = shadowCol.z;
+                    f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
+                    f[F_N] = n.x; f[F_N + 1] = n.y; f[F_N + 2] = n.z;
+                    f[F_IOR] = ior; f[F_FLAGS] = __int_as_float(FR_SHI); f[F_RECDEPTH] = __int_as_float(recDepth);
+                    rayType = RT_SHADOW_TRACE; recDepth++;
+                    ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 0; rayKind = CNT_SHADOW;   // rd unchanged (T3)
+                    issue = true;
+                } else {
+                    hv = shadowCol * 0.4f;
+                }
+            } else if(rayType == RT_SHADOW_TRACE) {  // :153-166
+                if(transparency > 0.0f) {
+                    if(recDepth < maxRec) {   // T2: nothing to do after the child returns except recDepth--, which every
+                        rayType = RT_SHADOW_INTERNAL; recDepth++;                 // resuming frame restores from its own copy
+                        ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
+                        issue = true;
+                    }
+                } else {
+                    hv = hv * mixf(0.4f, 0.8f, clampf(logf(hit.t) / 8.0f, 0.0f, 1.0f));
+                }
+            } else {  // RT_GENERIC, :168-268
+                const bool frontFacing = dot(-rd, n) > 0.0f;
+                if(!frontFacing) n = normalize(-n);
+                const float ndl = dot(-L, n);
+                V3 baseColor = diffuse * fmaxf(ndl, 0.2f);
+                float* f = fr[sp++];
+                f[F_ORG] = origin.x; f[F_ORG + 1] = origin.y; f[F_ORG + 2] = origin.z;
+                f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
+                f[F_N] = n.x; f[F_N + 1] = n.y; f[F_N + 2] = n.z;
+                f[F_T] = hit.t;
+                f[F_DIFF] = diffuse.x; f[F_DIFF + 1] = diffuse.y; f[F_DIFF + 2] = diffuse.z;
+                f[F_SPEC] = specular.x; f[F_SPEC + 1] = specular.y; f[F_SPEC + 2] = specular.z;
+                f[F_TRANSP] = transparency; f[F_REFL] = reflectivity; f[F_ROUGH] = roughness; f[F_IOR] = ior; f[F_EMIS] = emission;
+                f[F_RECDEPTH] = __int_as_float(recDepth);
+                int stage;
+                bool shadowPending = false;
+                if(ndl > 0.07f) {   // :188
+                    if(recDepth < maxRec) {
+                        hv = v3(1.0f, 1.0f, 1.0f);
+                        rayType = RT_SHADOW_TRACE; recDepth++;
+                        ro = origin; rd = -L; rtmin = 0.1f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
+                        shadowPending = true;
+                    }
+                    // recDepth >= max: shadowColor stays 1
+                } else {
+                    const float sm = transparency * transparency;   // pow(t, 2)
+                    const V3 sc = transparency < 1.0f ? mix3(v3(1, 1, 1), diffuse * sm, transparency) : v3(0.4f, 0.4f, 0.4f);
+                    baseColor = baseColor * sc;
+                }
+                if(shadowPending) { stage = ST_SHADOW_RET; issue = true; }
+                else { baseColor = baseColor + diffuse * emission; stage = ST_TRY_REFLECT; }
+                f[F_BASE] = baseColor.x; f[F_BASE + 1] = baseColor.y; f[F_BASE + 2] = baseColor.z;
+                f[F_FLAGS] = __int_as_float(FR_GEN | (stage << 8) | ((frontFacing ? 1 : 0) << 16) | ((int)(rayConsumption & 0xffu) << 20));
+            }
+        } else {
+            if(missIndex == 0) {  // miss.rmiss:76-83
+                const V3 sky = skyColor(rd, L);
+                hv = sky; depth = 10000.0f;
+                if(sp == 0 && recDepth == 0) { pRough = sky; pRoughA = 0.0f; }   // roughValue is only observable for a primary miss
+            } else {              // shadowMiss.rmiss:33
+                hv = v3(1.0f, 1.0f, 1.0f);
+            }
+        }
+
+        // ---- resume suspended frames (the code after each traceRayEXT returns)
+        while(!issue) {
+            if(sp == 0) {   // raygen.h:105-111: the sample's trace returned
+                accColor = accColor + hv; accNormal = accNormal + pNormal; accRough = accRough + pRough; accRoughA += pRoughA;
+                accContrib += pContrib; accDepth += depth;
+                if(++sample < numSamples) { primaryRay(sample); issue = true; }
+                else {      // raygen.h:114 + raygen.rgen:35-38
+                    const float inv = (float)numSamples;
+                    P.base[pix] = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
+                    P.normal[pix] = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
+                    P.rough[pix] = packHalf4(accRough.x / inv, accRough.y / inv, accRough.z / inv, accRoughA / inv);
+                    active = false;
+                    break;
+                }
+                continue;
+            }
+            float* f = fr[sp - 1];
+            const int flags = __float_as_int(f[F_FLAGS]);
+            recDepth = __float_as_int(f[F_RECDEPTH]);   // undoes every recDepth++ / += rayConsumption below this frame
+            if((flags & 0xff) == FR_SHI) {   // closesthit.rchit:136-146, after T3 returned
+                V3 shadowCol = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]);
+                if(depth < 1000.0f) {
+                    hv = hv * shadowCol;
+                } else {
+                    const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
+                    const V3 dir = refract3(D, n, f[F_IOR]);
+                    const float dp = dot(L, dir);
+                    const float dp2 = dp * dp;
+                    shadowCol = shadowCol * (dp2 * dp2 * dp + 0.75f);   // pow(x, 5)
+                    cnt[CNT_SKY]++;   // T4: cull mask 0 -> always miss 0
+                    const V3 sky = skyColor(-dir, L);
+                    depth = 10000.0f;
+                    hv = shadowCol + sky * 0.1f;
+                }
+                sp--;
+                continue;
+            }
+            int stage = (flags >> 8) & 0xff;
+            const bool frontFacing = ((flags >> 16) & 1) != 0;
+            const int rc = (flags >> 20) & 0xff;
+            if(stage == ST_SHADOW_RET) {   // :196-197 then :254-255
+                const V3 diffuse = v3(f[F_DIFF], f[F_DIFF + 1], f[F_DIFF + 2]);
+                V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]) * hv + diffuse * f[F_EMIS];
+                f[F_BASE] = base.x; f[F_BASE + 1] = base.y; f[F_BASE + 2] = base.z;
+                stage = ST_TRY_REFLECT;
+            }
+            if(stage == ST_TRY_REFLECT) {  // :207-221
+                if(recDepth < maxRec && f[F_REFL] > 0.0f) {
+                    const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
+                    recDepth += rc; refDepth += f[F_T];
+                    ro = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]); rd = reflect3(D, n); rtmin = 0.01f; rtmax = 1000.0f;
+                    rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFLECT;
+                    f[F_FLAGS] = __int_as_float((flags & ~0xff00) | (ST_REFLECT_RET << 8));
+                    issue = true;
+                    break;
+                }
+                f[F_RCOL] = 1.0f; f[F_RCOL + 1] = 1.0f; f[F_RCOL + 2] = 1.0f; f[F_RDEPTH] = 0.0f;
+                stage = ST_TRY_REFRACT;
+            }
+            if(stage == ST_REFLECT_RET) {
+                f[F_RCOL] = hv.x * f[F_SPEC]; f[F_RCOL + 1] = hv.y * f[F_SPEC + 1]; f[F_RCOL + 2] = hv.z * f[F_SPEC + 2];
+                f[F_RDEPTH] = depth;
+                stage = ST_TRY_REFRACT;
+            }
+            V3 refractColor = v3(1.0f, 1.0f, 1.0f);
+            if(stage == ST_TRY_REFRACT) {  // :224-251
+                if(recDepth < maxRec && f[F_TRANSP] > 0.0f) {
+                    const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
+                    const float ior = f[F_IOR];
+                    const float eta = frontFacing ? curIOR / ior : ior / 1.0f;
+                    recDepth++;
+                    curIOR = frontFacing ? ior : 1.0f;
+                    ro = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]); rd = refract3(D, n, eta); rtmin = 0.01f; rtmax = 1000.0f;
+                    rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFRACT;
+                    f[F_FLAGS] = __int_as_float((flags & ~0xff00) | ((frontFacing ? ST_REFRACT_RET_FRONT : ST_REFRACT_RET_BACK) << 8));
+                    issue = true;
+                    break;
+                }
+                stage = ST_COMBINE;
+            } else if(stage == ST_REFRACT_RET_FRONT) {
+                refractColor = hv;
+            } else if(stage == ST_REFRACT_RET_BACK) {
+                const V3 diffuse = v3(f[F_DIFF], f[F_DIFF + 1], f[F_DIFF + 2]);
+                refractColor = mix3(v3(1, 1, 1), diffuse, logf(1.0f + f[F_T])) * hv;
+            }
+            // combine, :254-267
+            {
+                const V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]);
+                const V3 reflectColor = v3(f[F_RCOL], f[F_RCOL + 1], f[F_RCOL + 2]);
+                const float transparency = f[F_TRANSP], reflectivity = f[F_REFL], roughness = f[F_ROUGH];
+                const float totalContrib = fmaxf(transparency, reflectivity);
+                float weight = reflectivity / (transparency + reflectivity);
+                if(!strictIeee && (transparency + reflectivity) == 0.0f) weight = 0.0f;   // SURVEY hazard 8
+                const V3 roughCol = mix3(refractColor, reflectColor, weight);
+                hv = mix3(base, roughCol, totalContrib);
+                if(recDepth == 0) {
+                    hv = base;
+                    pNormal = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
+                    pRough = roughCol; pRoughA = fminf((f[F_RDEPTH] / 50.0f) * roughness, roughness / 2.1f);
+                    pContrib = totalContrib;
+                }
+                depth = f[F_T];
+                sp--;
+            }
+        }
+    }
+
+    // ---- ray counters: warp reduce, one atomic per warp and counter
+#pragma unroll
+    for(int k = 0; k < CNT_N; ++k) {
+        if(!COUNT && k >= CNT_NODES) break;
+        unsigned long long v = cnt[k];
+#pragma unroll
+        for(int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if(lane == 0 && v) atomicAdd(P.counters + k, v);
+    }
+}
+
+__global__ void k_trace_rays(const TraceParams P, const float* __restrict__ rays8, uint32_t n, float* __restrict__ tuv, uint32_t* __restrict__ instPrim) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    const float* q = rays8 + 8 * (size_t)i;
+    Hit hit;
+    uint32_t cnt[CNT_N];
+    traverse<false>(P, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], hit, cnt);
+    tuv[3 * i] = hit.t; tuv[3 * i + 1] = hit.u; tuv[3 * i + 2] = hit.v;
+    instPrim[2 * i] = hit.inst; instPrim[2 * i + 1] = hit.prim;
+}
+
+}  // namespace
+
+void launchTrace(const TraceParams& p, int numSms, cudaStream_t stream) {
+    // persistent grid: a multiple of the SM count; resident CTAs per SM limited by registers / local memory
+    int perSm = 0;
+    if(p.flags & RG_COUNT_TRAVERSAL) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<true>, 128, 0);
+        if(perSm < 1) perSm = 1;
+        k_trace<true><<<numSms * perSm, 128, 0, stream>>>(p);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false>, 128, 0);
+        if(perSm < 1) perSm = 1;
+        k_trace<false><<<numSms * perSm, 128, 0, stream>>>(p);
+    }
+}
+
+void launchTraceRays(const TraceParams& p, const float* rays8, uint32_t n, float* tuv, uint32_t* instPrim, cudaStream_t stream) {
+    if(n == 0) return;
+    k_trace_rays<<<(n + 127) / 128, 128, 0, stream>>>(p, rays8, n, tuv, instPrim);
+}
+
+}  // namespace rg

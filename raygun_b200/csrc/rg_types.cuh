@@ -1,0 +1,73 @@
+// rg_types.cuh -- device data layout shared by the builder, the traversal kernel and the C ABI.
+//
+// Layout in HBM (all arrays are plain cudaMalloc allocations owned by rg_ctx):
+//   vertices   n_vtx  x 32 B   the reference's Vertex records, unchanged          (vertex.def:3-7)
+//   indices    n_idx  x  4 B   u32, mesh-local                                     (render_system.cpp:270-305)
+//   materials  n_mat  x 64 B   gpu::Material records, unchanged                    (gpu_material.def:11-26)
+//   nodes      Node8  x 80 B   compressed 8-wide BVH nodes, 5 x 128-bit loads each; all BLASes back to back,
+//                              the per-frame TLAS in its own array
+//   tris       Tri    x 48 B   3 x float4: vertex positions re-laid out in leaf order, w0 = primitive id
+//   tlasLeaves InstTrav x 64 B world->object 3x4 + BLAS root, gathered in TLAS leaf order each frame
+//   instShade  InstShade x 64 B object->world 3x4 + the offset-table entry, indexed by instance id
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rg {
+
+// Compressed 8-wide node (after Ylitie, Karras, Laine 2017).  Child boxes are quantised to 8 bits
+// relative to the node origin p with per-axis power-of-two scale 2^e.  Slot s of a node sits on the
+// (s&4 ? +x : -x, s&2 ? +y : -y, s&1 ? +z : -z) side of the node centre where possible, so XOR-ing the
+// slot with the ray's direction octant yields a front-to-back order without sorting.
+//   meta[s] == 0                    empty slot
+//   meta[s] == 0x20 | (24 + s)      internal child; children are stored contiguously from childBase in slot order
+//   meta[s] == unary(n) << 5 | off  leaf with n in 1..3 primitives starting at primBase + off (off < 24)
+struct alignas(16) Node8 {
+    float px, py, pz;
+    uint8_t ex, ey, ez, imask;
+    uint32_t childBase;
+    uint32_t primBase;
+    uint8_t meta[8];
+    uint8_t qlox[8], qloy[8];
+    uint8_t qloz[8], qhix[8];
+    uint8_t qhiy[8], qhiz[8];
+};
+static_assert(sizeof(Node8) == 80, "Node8 must be 5 x 16 bytes");
+
+struct alignas(16) Tri {  // 48 B
+    float v0x, v0y, v0z; uint32_t prim;
+    float v1x, v1y, v1z; uint32_t pad1;
+    float v2x, v2y, v2z; uint32_t pad2;
+};
+static_assert(sizeof(Tri) == 48, "Tri must be 3 x 16 bytes");
+
+struct alignas(16) InstTrav {  // 64 B
+    float w2o[12];       // world -> object, 3x4 row-major
+    uint32_t blasRoot;   // absolute index of the BLAS root node; 0xffffffff = empty mesh
+    uint32_t instId;     // gl_InstanceCustomIndexEXT
+    uint32_t pad0, pad1;
+};
+static_assert(sizeof(InstTrav) == 64, "InstTrav");
+
+struct alignas(16) InstShade {  // 64 B
+    float o2w[12];  // object -> world, 3x4 row-major
+    uint32_t vtxOff, idxOff, matOff, mesh;
+};
+static_assert(sizeof(InstShade) == 64, "InstShade");
+
+struct Aabb { float lo[3], hi[3]; };
+
+// binary LBVH scratch node (builder only)
+struct BNode {
+    float lo[3]; uint32_t left;   // child index; bit 31 set = leaf (sorted position)
+    float hi[3]; uint32_t right;
+};
+static_assert(sizeof(BNode) == 32, "BNode");
+
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr uint32_t kInvalid = 0xffffffffu;
+constexpr int kMaxLeafPrims = 3;
+
+struct Hit { float t, u, v; uint32_t inst, prim; };
+
+}  // namespace rg
