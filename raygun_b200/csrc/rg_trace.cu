@@ -50,8 +50,7 @@ __device__ __forceinline__ V3 refract3(V3 I, V3 N, float eta) {
 // ------------------------------------------------------------------------------------------------ traversal
 struct RayCtx {
     float ox, oy, oz, dx, dy, dz;
-    float inx, iny, inz;  // 1/d scaled down (near planes)
-    float ifx, ify, ifz;  // 1/d scaled up (far planes)  -> the slab test is conservative
+    float ix, iy, iz;     // 1/d (zero components clamped to +-1e-30)
     float Sx, Sy, Sz;     // Woop shear
     uint32_t octinv;      // bit 2/1/0 set when d.x/d.y/d.z >= 0
     int kx, ky, kz;
@@ -62,12 +61,9 @@ __device__ __forceinline__ float sel3(int k, float x, float y, float z) { return
 __device__ __forceinline__ void setupRay(RayCtx& r, float ox, float oy, float oz, float dx, float dy, float dz) {
     r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
     const float eps = 1e-30f;
-    const float ix = 1.0f / (fabsf(dx) > eps ? dx : copysignf(eps, dx));
-    const float iy = 1.0f / (fabsf(dy) > eps ? dy : copysignf(eps, dy));
-    const float iz = 1.0f / (fabsf(dz) > eps ? dz : copysignf(eps, dz));
-    const float lo = 1.0f - 4.8e-7f, hi = 1.0f + 4.8e-7f;
-    r.inx = ix * lo; r.iny = iy * lo; r.inz = iz * lo;
-    r.ifx = ix * hi; r.ify = iy * hi; r.ifz = iz * hi;
+    r.ix = 1.0f / (fabsf(dx) > eps ? dx : copysignf(eps, dx));
+    r.iy = 1.0f / (fabsf(dy) > eps ? dy : copysignf(eps, dy));
+    r.iz = 1.0f / (fabsf(dz) > eps ? dz : copysignf(eps, dz));
     r.octinv = (dx >= 0.0f ? 4u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 1u : 0u);
     const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
     const int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
@@ -164,8 +160,15 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
             const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
                         sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
             const float px = __uint_as_float(n0.x) - r.ox, py = __uint_as_float(n0.y) - r.oy, pz = __uint_as_float(n0.z) - r.oz;
-            const float anx = sx * r.inx, any_ = sy * r.iny, anz = sz * r.inz, onx = px * r.inx, ony = py * r.iny, onz = pz * r.inz;
-            const float afx = sx * r.ifx, afy = sy * r.ify, afz = sz * r.ifz, ofx = px * r.ifx, ofy = py * r.ify, ofz = pz * r.ifz;
+            // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
+            // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.
+            // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
+            const float anx = sx * r.ix, any_ = sy * r.iy, anz = sz * r.iz;
+            const float afx = anx, afy = any_, afz = anz;
+            const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
+            const float kSlack = 4.8e-7f;
+            const float onx = fmaf(-fabsf(bx), kSlack, bx), ony = fmaf(-fabsf(by), kSlack, by), onz = fmaf(-fabsf(bz), kSlack, bz);
+            const float ofx = fmaf(fabsf(bx), kSlack, bx), ofy = fmaf(fabsf(by), kSlack, by), ofz = fmaf(fabsf(bz), kSlack, bz);
             const bool negx = r.dx < 0.0f, negy = r.dy < 0.0f, negz = r.dz < 0.0f;
             uint32_t hitmask = 0;
             {   // slots 0..3
