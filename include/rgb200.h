@@ -93,7 +93,7 @@ typedef struct rg_timings {
     float postproc_ms;  /* Postproc : raytracer.cpp:106,142 */
     float gather_ms;    /* tile gather to the target GPU (no reference counterpart) */
     uint64_t rays_primary, rays_shadow, rays_reflect, rays_refract, sky_lookups;
-    uint64_t nodes_visited, tris_tested, instances_entered; /* only with RG_COUNT_TRAVERSAL */
+    uint64_t nodes_visited, tris_tested, instances_entered, generic_hits; /* only with RG_COUNT_TRAVERSAL */
 } rg_timings;
 
 /* rg_render flags */
@@ -184,6 +184,12 @@ int rg_debug_bvh_stats(rg_ctx* ctx, uint64_t* out8);
  * data and run rough_prepare .. fxaa + blit on it.  Full-frame region only. */
 int rg_debug_upload_gbuffer(rg_ctx* ctx, const void* base, const void* normal, const void* rough);
 int rg_debug_run_post(rg_ctx* ctx, uint32_t flags);
+
+/* Device-side stopwatch on the context's stream (CUDA events), and an L2 flush (writes a 256 MiB scratch buffer)
+ * for benchmark hygiene.  rg_timer_end synchronises and returns the elapsed milliseconds since rg_timer_begin. */
+int rg_timer_begin(rg_ctx* ctx);
+int rg_timer_end(rg_ctx* ctx, float* ms);
+int rg_flush_l2(rg_ctx* ctx);
 
 /* Number of kernels this library launched on the context since creation (bench: gpu_launches). */
 uint64_t rg_launch_count(const rg_ctx* ctx);

@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "rg_refit_blas", "rg_set_instances", "rg_set_ubo", "rg_render", "rg_sync", "rg_read_rgba8", "rg_read_image", "rg_read_ids", "rg_get_timings",
     "rg_set_instances_device", "rg_set_ubo_device", "rg_framebuffer_device_ptr", "rg_set_gather_target", "rg_gather_buffer_export",
     "rg_gather_buffer_open", "rg_gather_buffer_close", "rg_read_gathered_rgba8", "rg_debug_blas_sort", "rg_debug_tlas_sort", "rg_debug_trace_rays",
-    "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count",
+    "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2",
 )
 
 
@@ -37,7 +37,8 @@ class RgTimings(C.Structure):
     _fields_ = [("as_build_ms", C.c_float), ("rt_total_ms", C.c_float), ("rt_only_ms", C.c_float), ("rough_ms", C.c_float),
                 ("postproc_ms", C.c_float), ("gather_ms", C.c_float),
                 ("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_refract", C.c_uint64),
-                ("sky_lookups", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("instances_entered", C.c_uint64)]
+                ("sky_lookups", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("instances_entered", C.c_uint64),
+                ("generic_hits", C.c_uint64)]
 
 
 _lib = None
@@ -179,6 +180,17 @@ class Raytracer:
         d["rays"] = d["rays_primary"] + d["rays_shadow"] + d["rays_reflect"] + d["rays_refract"]
         return d
 
+    def timer_begin(self):
+        self._ck(self.lib.rg_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.rg_timer_end(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def flush_l2(self):
+        self._ck(self.lib.rg_flush_l2(self.h))
+
     def launch_count(self) -> int:
         return int(self.lib.rg_launch_count(self.h))
 
@@ -210,8 +222,9 @@ class Raytracer:
     def set_gather_target(self, dptr):
         self._ck(self.lib.rg_set_gather_target(self.h, C.c_void_p(dptr or 0)))
 
-    def read_gathered_rgba8(self):
-        out = np.empty((self.height, self.width, 4), np.uint8)
+    def read_gathered_rgba8(self, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.uint8)
         self._ck(self.lib.rg_read_gathered_rgba8(self.h, _p(out)))
         return out
 

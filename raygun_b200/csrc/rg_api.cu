@@ -27,7 +27,7 @@ struct MeshBlas {
     bool built = false;
 };
 
-enum { EV_AS0, EV_AS1, EV_RT0, EV_RTONLY1, EV_ROUGH0, EV_ROUGH1, EV_POST1, EV_GATHER1, EV_N };
+enum { EV_AS0, EV_AS1, EV_RT0, EV_RTONLY1, EV_ROUGH0, EV_ROUGH1, EV_POST1, EV_GATHER1, EV_USER0, EV_USER1, EV_N };
 
 }  // namespace
 
@@ -64,6 +64,7 @@ struct rg_ctx {
     cudaEvent_t ev[EV_N]{};
     bool haveFrame = false, haveAs = false, blasBuilt = false;
     uint32_t lastFlags = 0;
+    void* flushBuf = nullptr;
 };
 
 namespace {
@@ -235,7 +236,7 @@ int rg_create(rg_ctx** out, int cuda_device, uint32_t width, uint32_t height) {
     if(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 5; }
     for(auto& e: ctx->ev) cudaEventCreate(&e);
     cudaMalloc(&ctx->dUbo, 192); cudaMemset(ctx->dUbo, 0, 192);
-    cudaMalloc(&ctx->dWork, 4); cudaMalloc(&ctx->dCounters, 8 * 8); cudaMemset(ctx->dCounters, 0, 64);
+    cudaMalloc(&ctx->dWork, 4); cudaMalloc(&ctx->dCounters, 16 * 8); cudaMemset(ctx->dCounters, 0, 128);
     cudaMallocHost(&ctx->hUboPinned, sizeof(rg_ubo));
     ctx->W = width; ctx->H = height; ctx->ix0 = 0; ctx->iy0 = 0; ctx->ix1 = (int)width; ctx->iy1 = (int)height;
     if(allocImages(ctx)) { fprintf(stderr, "rgb200: %s\n", ctx->err.c_str()); rg_destroy(ctx); return 6; }
@@ -248,7 +249,7 @@ void rg_destroy(rg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     freeImages(ctx);
-    cudaFree(ctx->gatherOwn);
+    cudaFree(ctx->gatherOwn); cudaFree(ctx->flushBuf);
     cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes);
     cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->dMeshRoots); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
     cudaFree(ctx->dUbo); cudaFree(ctx->dWork); cudaFree(ctx->dCounters);
@@ -440,7 +441,7 @@ int rg_render(rg_ctx* ctx, uint32_t flags) {
     if(!ctx->haveAs) return fail(ctx, "rg_render: no acceleration structure (rg_build_blas + rg_set_instances first)");
     USE_DEVICE();
     CK(cudaMemsetAsync(ctx->dWork, 0, 4, ctx->stream));
-    CK(cudaMemsetAsync(ctx->dCounters, 0, 64, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dCounters, 0, 128, ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_RT0], ctx->stream));
     TraceParams tp; fillTraceParams(ctx, tp, flags);
     launchTrace(tp, ctx->numSms, ctx->stream);
@@ -503,8 +504,9 @@ int rg_get_timings(rg_ctx* ctx, rg_timings* out) {
         cudaEventElapsedTime(&out->rough_ms, ctx->ev[EV_ROUGH0], ctx->ev[EV_ROUGH1]);
         cudaEventElapsedTime(&out->postproc_ms, ctx->ev[EV_RTONLY1], ctx->ev[EV_POST1]);
         cudaEventElapsedTime(&out->gather_ms, ctx->ev[EV_POST1], ctx->ev[EV_GATHER1]);
-        unsigned long long c[8];
+        unsigned long long c[16];
         CK(cudaMemcpy(c, ctx->dCounters, sizeof c, cudaMemcpyDeviceToHost));
+        out->generic_hits = c[8];
         out->rays_primary = c[0]; out->rays_shadow = c[1]; out->rays_reflect = c[2]; out->rays_refract = c[3]; out->sky_lookups = c[4];
         out->nodes_visited = c[5]; out->tris_tested = c[6]; out->instances_entered = c[7];
     }
@@ -565,6 +567,31 @@ int rg_read_gathered_rgba8(rg_ctx* ctx, void* dst) {
     USE_DEVICE();
     CK(cudaMemcpyAsync(dst, ctx->gatherOwn, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rg_timer_begin(rg_ctx* ctx) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    CK(cudaEventRecord(ctx->ev[EV_USER0], ctx->stream));
+    return 0;
+}
+
+int rg_timer_end(rg_ctx* ctx, float* ms) {
+    if(!ctx || !ms) return 1;
+    USE_DEVICE();
+    CK(cudaEventRecord(ctx->ev[EV_USER1], ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev[EV_USER1]));
+    CK(cudaEventElapsedTime(ms, ctx->ev[EV_USER0], ctx->ev[EV_USER1]));
+    return 0;
+}
+
+int rg_flush_l2(rg_ctx* ctx) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    const size_t bytes = 256u << 20;  // > 126 MB L2
+    if(!ctx->flushBuf) CK(cudaMalloc(&ctx->flushBuf, bytes));
+    CK(cudaMemsetAsync(ctx->flushBuf, (int)(ctx->launches & 0xff), bytes, ctx->stream));
     return 0;
 }
 

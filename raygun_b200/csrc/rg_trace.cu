@@ -23,7 +23,7 @@ namespace rg {
 namespace {
 
 enum { RT_GENERIC = 0, RT_SHADOW_TRACE = 1, RT_SHADOW_INTERNAL = 2 };
-enum { CNT_PRIMARY = 0, CNT_SHADOW = 1, CNT_REFLECT = 2, CNT_REFRACT = 3, CNT_SKY = 4, CNT_NODES = 5, CNT_TRIS = 6, CNT_INST = 7, CNT_N = 8 };
+enum { CNT_PRIMARY = 0, CNT_SHADOW = 1, CNT_REFLECT = 2, CNT_REFRACT = 3, CNT_SKY = 4, CNT_NODES = 5, CNT_TRIS = 6, CNT_INST = 7, CNT_GENHIT = 8, CNT_N = 9 };
 
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(128) k_trace(const TraceParams P) {
                     hv = hv * mixf(0.4f, 0.8f, clampf(logf(hit.t) / 8.0f, 0.0f, 1.0f));
                 }
             } else {  // RT_GENERIC, :168-268
+                if(COUNT) cnt[CNT_GENHIT]++;
                 const bool frontFacing = dot(-rd, n) > 0.0f;
                 if(!frontFacing) n = normalize(-n);
                 const float ndl = dot(-L, n);

@@ -1,0 +1,49 @@
+"""Screen-space partitioning of one frame across GPUs (one process per GPU) and the gather hand-shake.
+
+The reference is single-device (raygun/vulkan_context.cpp:165); this is the one place the B200 path adds parallelism:
+pixels are independent through ray generation and shading, and the post chain has a bounded dependency radius
+(1 px rough_prepare + 10 px blur + 28 px FXAA search = 39 px), so every rank renders its band plus a 40 px halo against a
+replicated scene and the final kernel stores the band straight into rank 0's frame buffer over NVLink.
+"""
+from __future__ import annotations
+
+HALO = 40
+
+
+def band_region(width: int, height: int, rank: int, world: int, split: str = "columns"):
+    """(x0, y0, x1, y1) owned by `rank`: contiguous, disjoint, covering the frame; sizes differ by at most one pixel."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank / world")
+    if split == "columns":
+        if world > width:
+            raise ValueError("more ranks than columns")
+        return (width * rank) // world, 0, (width * (rank + 1)) // world, height
+    if split == "rows":
+        if world > height:
+            raise ValueError("more ranks than rows")
+        return 0, (height * rank) // world, width, (height * (rank + 1)) // world
+    raise ValueError(f"unknown split {split!r}")
+
+
+def rendered_rect(region, width, height, halo: int = HALO):
+    """Rectangle a rank actually traces: region grown by the halo, clipped to the frame."""
+    x0, y0, x1, y1 = region
+    return max(0, x0 - halo), max(0, y0 - halo), min(width, x1 + halo), min(height, y1 + halo)
+
+
+def overdraw(width, height, world, split="columns", halo: int = HALO) -> float:
+    """Traced pixels over all ranks / frame pixels."""
+    total = 0
+    for r in range(world):
+        x0, y0, x1, y1 = rendered_rect(band_region(width, height, r, world, split), width, height, halo)
+        total += (x1 - x0) * (y1 - y0)
+    return total / float(width * height)
+
+
+def share_gather_handle(dist, rank: int, handle: bytes | None) -> bytes:
+    """Rank 0 publishes the 64-byte CUDA IPC handle of its full-frame buffer; every rank returns it."""
+    obj = [handle if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    if not isinstance(obj[0], (bytes, bytearray)) or len(obj[0]) != 64:
+        raise RuntimeError("gather handle exchange failed")
+    return bytes(obj[0])

@@ -1,0 +1,271 @@
+"""-m gpu: parity of the CUDA path (through the C ABI, numpy host buffers) against the CPU oracle.
+
+Bars (BASELINE.json north_star): Morton / sort output bit-exact; primary-hit instance / primitive ids equal on
+>= 99.99 % of pixels; final 8-bit image PSNR >= 50 dB with <= 2/255 error on >= 99.9 % of pixels.  On top of that the
+post chain is required to be BIT-EXACT when fed the oracle's G-buffer, and a frame split into bands must equal the
+unsplit frame bit for bit."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ID_BAR, PSNR_BAR, ERR_BAR = 0.9999, 50.0, 0.999
+
+
+def _psnr(a, b):
+    mse = float(np.mean((a[..., :3].astype(np.float64) - b[..., :3].astype(np.float64)) ** 2))
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def _check_frame(rt, ref, rg, label):
+    img = rt.read_rgba8()
+    inst, prim = rt.read_ids()
+    idm = float(((inst == ref["inst"]) & (prim == ref["prim"])).mean())
+    d = np.abs(img[..., :3].astype(int) - ref["rgba8"][..., :3].astype(int)).max(axis=2)
+    psnr, frac = _psnr(img, ref["rgba8"]), float((d <= 2).mean())
+    print(f"{label}: id match {idm:.6f}  PSNR {psnr:.2f} dB  <=2/255 on {frac:.5f}")
+    assert idm >= ID_BAR, f"{label}: primary ids match on {idm}"
+    assert psnr >= PSNR_BAR, f"{label}: PSNR {psnr}"
+    assert frac >= ERR_BAR, f"{label}: {frac} of pixels within 2/255"
+    return img
+
+
+@pytest.fixture(scope="module")
+def rgmod():
+    import raygun_b200 as rg
+    return rg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def S():
+    from raygun_b200 import scene
+    return scene
+
+
+def test_morton_sort_bit_exact_blas(rgmod, O, example_scene):
+    rt = rgmod.Raytracer(64, 36)
+    rt.load_scene(example_scene)
+    for m in range(len(example_scene.meshes)):
+        n = int(example_scene.meshes[m, 3]) // 3
+        keys, order = rt.debug_blas_sort(m, n)
+        codes, ref_order, _ = O.morton_triangles(example_scene, m)
+        assert np.array_equal(order, ref_order), f"mesh {m}: primitive order"
+        assert np.array_equal(keys, codes[ref_order]), f"mesh {m}: sorted keys"
+
+
+def test_morton_sort_bit_exact_million_triangles(rgmod, O, S):
+    sd, _ = S.sphere_grid_scene(28, flattened=True)     # 1 003 522 triangles in one mesh
+    rt = rgmod.Raytracer(64, 36)
+    rt.load_scene(sd)
+    n = int(sd.meshes[0, 3]) // 3
+    keys, order = rt.debug_blas_sort(0, n)
+    codes, ref_order, _ = O.morton_triangles(sd, 0)
+    assert np.array_equal(order, ref_order) and np.array_equal(keys, codes[ref_order])
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)
+
+
+def test_morton_sort_bit_exact_tlas_10k_instances(rgmod, O, S):
+    balls = S.AnimatedBalls(100)
+    sd = balls.scene(0.37)
+    rt = rgmod.Raytracer(64, 36)
+    rt.load_scene(sd)
+    n = len(sd.inst_xform)
+    keys, order = rt.debug_tlas_sort(n)
+    pos = sd.positions()
+    boxes = np.zeros((n, 6), np.float32)
+    mesh_boxes = []
+    for m in range(len(sd.meshes)):
+        vo, vc, io, ic = (int(v) for v in sd.meshes[m])
+        p = pos[vo + sd.indices[io:io + ic]]
+        mesh_boxes.append(np.concatenate([p.min(0), p.max(0)]))
+    for i in range(n):
+        boxes[i] = O.instance_world_box(sd.inst_xform[i], mesh_boxes[int(sd.inst_meta[i, 0])])
+    codes, ref_order = O.morton_boxes(boxes)
+    assert np.array_equal(order, ref_order) and np.array_equal(keys, codes[ref_order])
+
+
+@pytest.mark.parametrize("W,H,ns", [(640, 360, 1), (1920, 1080, 4), (100, 60, 2), (333, 187, 3)])
+def test_example_scene_frame_parity(rgmod, O, S, example_scene, oracle_example, W, H, ns):
+    ubo = S.example_ubo(W, H, num_samples=ns, max_recursions=5)
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(example_scene)
+    rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
+    ref = oracle_example.render(ubo, W, H, O.FXAA)
+    _check_frame(rt, ref, rgmod, f"example {W}x{H} S={ns}")
+    tm = rt.timings()
+    c = ref["counters"]
+    for a, b in (("rays_primary", "primary"), ("rays_shadow", "shadow"), ("rays_reflect", "reflect"), ("rays_refract", "refract"), ("sky_lookups", "skylookup")):
+        assert abs(tm[a] - c[b]) <= max(4, 2e-4 * c[b]), (a, tm[a], c[b])
+    assert tm["rays_primary"] == W * H * ns
+    # intermediate images: transitions nearly identical, G-buffer normals tight
+    nrm = np.abs(O.f16_to_f32(rt.read_image(rgmod.IMG_NORMAL)) - O.f16_to_f32(ref["normal"]))
+    assert float((nrm <= 2e-3).mean()) >= 0.9999
+    assert float((rt.read_image(rgmod.IMG_TRANSITIONS) == ref["transitions"]).mean()) >= 0.999
+
+
+@pytest.mark.parametrize("flags_extra", [0, "nofxaa", "srgb"])
+def test_post_chain_bit_exact_on_oracle_gbuffer(rgmod, O, S, example_scene, oracle_example, flags_extra):
+    W, H = 1920, 1080
+    ubo = S.example_ubo(W, H, num_samples=1, fade=(0.1, 0.2, 0.3, 0.25) if flags_extra == "srgb" else (0, 0, 0, 0))
+    oflags = {0: O.FXAA, "nofxaa": 0, "srgb": O.FXAA | O.SRGB8}[flags_extra]
+    gflags = {0: rgmod.RG_FXAA, "nofxaa": 0, "srgb": rgmod.RG_FXAA | rgmod.RG_SRGB8}[flags_extra]
+    ref = oracle_example.render(ubo, W, H, oflags)
+    rt = rgmod.Raytracer(W, H)
+    rt.updateRenderTarget(ubo)
+    gb = ref["gbuffer"]
+    rt.debug_upload_gbuffer(gb["base"], gb["normal"], gb["rough"])
+    rt.debug_run_post(gflags)
+    for name, which in (("final", rgmod.IMG_FINAL), ("base", rgmod.IMG_BASE), ("roughA", rgmod.IMG_ROUGH_A), ("roughB", rgmod.IMG_ROUGH_B),
+                        ("normal", rgmod.IMG_NORMAL), ("rough", rgmod.IMG_ROUGH)):
+        assert np.array_equal(rt.read_image(which), ref[name]), name
+    assert np.array_equal(rt.read_image(rgmod.IMG_TRANSITIONS), ref["transitions"])
+    got = rt.read_rgba8()
+    if flags_extra == "srgb":   # powf differs by an ulp between libm and CUDA: allow one 8-bit step on rgb
+        assert np.abs(got.astype(int) - ref["rgba8"].astype(int)).max() <= 1
+    else:
+        assert np.array_equal(got, ref["rgba8"])
+
+
+def test_show_alpha_debug_path(rgmod, O, S, example_scene, oracle_example):
+    W, H = 160, 90
+    ubo = S.example_ubo(W, H, show_alpha=True)
+    ref = oracle_example.render(ubo, W, H, O.FXAA)
+    rt = rgmod.Raytracer(W, H)
+    rt.updateRenderTarget(ubo)
+    gb = ref["gbuffer"]
+    rt.debug_upload_gbuffer(gb["base"], gb["normal"], gb["rough"])
+    rt.debug_run_post(rgmod.RG_FXAA)
+    for name, which in (("final", rgmod.IMG_FINAL), ("base", rgmod.IMG_BASE), ("normal", rgmod.IMG_NORMAL), ("roughA", rgmod.IMG_ROUGH_A)):
+        assert np.array_equal(rt.read_image(which), ref[name]), name
+    assert np.array_equal(rt.read_image(rgmod.IMG_TRANSITIONS), ref["transitions"])
+
+
+@pytest.mark.parametrize("split", ["columns", "rows"])
+def test_band_split_is_bit_identical_to_full_frame(rgmod, S, example_scene, split):
+    """Multi-GPU path on one GPU: three bands rendered one after the other into one gather buffer == the unsplit frame."""
+    from raygun_b200.parallel import band_region
+    W, H = 480, 270
+    ubo = S.example_ubo(W, H, num_samples=2)
+    full = rgmod.Raytracer(W, H)
+    full.load_scene(example_scene)
+    full.render_frame(ubo, rgmod.RG_FXAA)
+    want = full.read_rgba8()
+    _, target = full.gather_buffer_export()
+    for r in range(3):
+        band = rgmod.Raytracer(W, H)
+        band.set_region(*band_region(W, H, r, 3, split))
+        band.load_scene(example_scene)
+        band.set_gather_target(target)
+        band.render_frame(ubo, rgmod.RG_FXAA)
+        band.sync()
+        x0, y0, x1, y1 = band.region
+        assert np.array_equal(band.read_rgba8(), want[y0:y1, x0:x1])
+        band.close()
+    assert np.array_equal(full.read_gathered_rgba8(), want)
+
+
+def test_sphere_grid_recursion_8_parity(rgmod, O, S):
+    """BASELINE config 3 in small: 6x6 mirror / glass spheres, instanced AND flattened, maxRecursions 8."""
+    W, H = 320, 180
+    for flat in (False, True):
+        sd, vi = S.sphere_grid_scene(6, flattened=flat)
+        ubo = S.make_ubo(vi, S.proj_inverse(W, H), 1, 8)
+        # look at the small grid
+        cam = S.Transform(position=np.array([14, 9, -8], np.float32)); cam.look_at(np.array([6.25, 1, 6.25], np.float32))
+        ubo = S.make_ubo(cam.to_mat4_colmajor(), S.proj_inverse(W, H), 1, 8)
+        rt = rgmod.Raytracer(W, H)
+        rt.load_scene(sd)
+        rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
+        ref = O.OracleScene(sd).render(ubo, W, H, O.FXAA)
+        _check_frame(rt, ref, rgmod, f"spheres6 flat={flat}")
+        assert ref["counters"]["refract"] > 1000 and ref["counters"]["reflect"] > 10000
+
+
+def test_per_frame_tlas_rebuild_animated(rgmod, O, S):
+    """BASELINE config 4 in small: 20x20 bouncing balls, TLAS rebuilt from new transforms every frame."""
+    W, H = 256, 144
+    balls = S.AnimatedBalls(20)
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(balls.scene(0.0))
+    cam = S.Transform(position=np.array([40, 25, -15], np.float32)); cam.look_at(np.array([24, 1, 24], np.float32))
+    ubo = S.make_ubo(cam.to_mat4_colmajor(), S.proj_inverse(W, H), 1, 4)
+    osc = O.OracleScene(balls.scene(0.0))
+    for frame in (1, 7):
+        t = frame / 60.0
+        xf = balls.instances(t)
+        rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS, rt.pack_instances(xf, balls.meta))
+        osc.set_instances(xf, balls.meta)
+        _check_frame(rt, osc.render(ubo, W, H, O.FXAA), rgmod, f"balls t={t:.3f}")
+
+
+def test_blas_refit_matches_rebuild(rgmod, O, S, example_scene):
+    """Extension for config 4: refit after a vertex wobble gives the same hits as a fresh build (oracle = fresh build)."""
+    W, H = 256, 144
+    sd = example_scene
+    ubo = S.example_ubo(W, H)
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(sd)
+    vo, vc = int(sd.meshes[3, 0]), int(sd.meshes[3, 1])     # the ball
+    v = sd.vertices[vo:vo + vc].copy()
+    p = v.view(np.float32)
+    p[:, 0:3] *= (1.0 + 0.25 * np.sin(7.0 * p[:, 1:2])).astype(np.float32)
+    rt.refitBottomLevelAS(3, v)
+    rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS, rt.pack_instances(sd.inst_xform, sd.inst_meta))
+    sd2 = S.SceneData(sd.vertices.copy(), sd.indices, sd.meshes, sd.materials, sd.inst_xform, sd.inst_meta)
+    sd2.vertices[vo:vo + vc] = v
+    _check_frame(rt, O.OracleScene(sd2).render(ubo, W, H, O.FXAA), rgmod, "refit ball")
+
+
+def test_edge_cases(rgmod, O, S, example_scene):
+    W, H = 64, 36
+    ubo = S.example_ubo(W, H)
+    # no instances at all: sky everywhere
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(example_scene)
+    rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS, np.zeros((0, 16), np.uint32))
+    inst, _ = rt.read_ids()
+    assert np.all(inst == 0xffffffff)
+    empty = S.SceneData(np.zeros((0, 8), np.uint32), np.zeros(0, np.uint32), np.zeros((0, 4), np.uint32), np.zeros((0, 16), np.uint32),
+                        np.zeros((0, 12), np.float32), np.zeros((0, 4), np.uint32))
+    ref = O.OracleScene(empty).render(ubo, W, H, O.FXAA)
+    assert np.abs(rt.read_rgba8()[..., :3].astype(int) - ref["rgba8"][..., :3].astype(int)).max() <= 1
+    # a mesh with zero triangles + a single-triangle mesh + one instance of each
+    v = np.zeros((3, 8), np.uint32); f = v.view(np.float32)
+    f[0, 0:3] = (0, 0, -5); f[1, 0:3] = (4, 0, -5); f[2, 0:3] = (0, 4, -5); f[:, 4:7] = (0, 0, 1)
+    sd = S.SceneData(v, np.array([0, 1, 2], np.uint32), np.array([(0, 0, 0, 0), (0, 3, 0, 3)], np.uint32), np.stack([S.make_material(diffuse=(0, 1, 0))]),
+                     np.stack([S.Transform().to_3x4().reshape(12)] * 2), np.array([(0, 0, 0, 0), (1, 0, 0, 0)], np.uint32))
+    cam = S.Transform(position=np.array([1, 1, 2], np.float32)); cam.look_at(np.array([1, 1, -5], np.float32))
+    ubo2 = S.make_ubo(cam.to_mat4_colmajor(), S.proj_inverse(W, H))
+    rt2 = rgmod.Raytracer(W, H)
+    rt2.load_scene(sd)
+    rt2.render_frame(ubo2, rgmod.RG_DEBUG_IDS)
+    ref2 = O.OracleScene(sd).render(ubo2, W, H, 0)
+    inst2, prim2 = rt2.read_ids()
+    assert np.array_equal(inst2, ref2["inst"]) and np.array_equal(prim2, ref2["prim"]) and (inst2 == 1).sum() > 50
+    # invalid arguments are rejected with a message, not a crash
+    with pytest.raises(rgmod.RaygunError):
+        rt2.updateRenderTarget(S.make_ubo(np.zeros(16), np.zeros(16), num_samples=0))
+    with pytest.raises(rgmod.RaygunError):
+        rt2.setupTopLevelAS(np.array([[0] * 12 + [9, 0, 0, 0]], np.uint32))
+    with pytest.raises(rgmod.RaygunError):
+        rt2.set_region(10, 10, 5, 20)
+
+
+def test_strict_ieee_switch_only_changes_diffuse_materials(rgmod, O, S, example_scene, oracle_example):
+    """SURVEY hazard 8: with the 0/0 kept, NaN appears exactly where the oracle (strict) has it."""
+    W, H = 160, 90
+    ubo = S.example_ubo(W, H)
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(example_scene)
+    rt.render_frame(ubo, rgmod.RG_STRICT_IEEE)
+    g = O.f16_to_f32(rt.read_image(rgmod.IMG_ROUGH))
+    ref = oracle_example.trace(ubo, W, H, O.STRICT_IEEE)
+    r = O.f16_to_f32(ref["rough"])
+    assert np.isnan(r).any()
+    assert float((np.isnan(g) == np.isnan(r)).mean()) >= 0.9999
