@@ -18,7 +18,7 @@ import numpy as np
 from . import scene  # noqa: F401  (host-side scene data)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librgb200.so")
+LIB_PATH = os.environ.get("RGB200_LIB") or os.path.join(_HERE, "librgb200.so")   # RGB200_LIB: developer override (A/B builds)
 
 # rg_render flags (include/rgb200.h)
 RG_FXAA, RG_SRGB8, RG_STRICT_IEEE, RG_DEBUG_IDS, RG_COUNT_TRAVERSAL, RG_NO_GATHER = 1, 2, 4, 8, 16, 32

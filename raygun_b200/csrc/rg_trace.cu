@@ -307,8 +307,11 @@ enum { ST_SHADOW_RET = 0, ST_TRY_REFLECT = 1, ST_REFLECT_RET = 2, ST_TRY_REFRACT
 __device__ __forceinline__ uint32_t f2h(float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); }
 __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) { return make_uint2(f2h(x) | (f2h(y) << 16), f2h(z) | (f2h(w) << 16)); }
 
+#ifndef RG_TRACE_MIN_BLOCKS
+#define RG_TRACE_MIN_BLOCKS 4
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_trace(const TraceParams P) {
+__global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     __shared__ float s_ubo[48];
     if(threadIdx.x < 48) s_ubo[threadIdx.x] = P.ubo[threadIdx.x];
     __syncthreads();
