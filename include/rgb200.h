@@ -177,6 +177,8 @@ int rg_debug_tlas_sort(rg_ctx* ctx, uint32_t* keys_sorted, uint32_t* inst_order,
 /* Closest-hit queries straight into the traversal kernel (n rays: org xyz, dir xyz, tmin, tmax = 8 floats each);
  * out: t,u,v (3 floats) + inst, prim (2 u32) per ray; inst = 0xffffffff on miss. */
 int rg_debug_trace_rays(rg_ctx* ctx, const float* rays8, uint32_t n, float* tuv, uint32_t* inst_prim);
+/* Device time of the last rg_debug_trace_rays kernel (second of two identical launches), milliseconds. */
+float rg_debug_last_trace_rays_ms(const rg_ctx* ctx);
 /* Counts: wide nodes, triangles, bytes of the BLAS set and of the current TLAS. */
 int rg_debug_bvh_stats(rg_ctx* ctx, uint64_t* out8);
 

@@ -29,7 +29,7 @@ ABI_SYMBOLS = (
     "rg_refit_blas", "rg_set_instances", "rg_set_ubo", "rg_render", "rg_sync", "rg_read_rgba8", "rg_read_image", "rg_read_ids", "rg_get_timings",
     "rg_set_instances_device", "rg_set_ubo_device", "rg_framebuffer_device_ptr", "rg_set_gather_target", "rg_gather_buffer_export",
     "rg_gather_buffer_open", "rg_gather_buffer_close", "rg_read_gathered_rgba8", "rg_debug_blas_sort", "rg_debug_tlas_sort", "rg_debug_trace_rays",
-    "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2",
+    "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2", "rg_debug_last_trace_rays_ms",
 )
 
 
@@ -55,6 +55,7 @@ def load_library():
         lib.rg_last_error.restype = C.c_char_p
         lib.rg_launch_count.restype = C.c_uint64
         lib.rg_destroy.restype = None
+        lib.rg_debug_last_trace_rays_ms.restype = C.c_float
         _lib = lib
     return _lib
 

@@ -65,6 +65,7 @@ struct rg_ctx {
     bool haveFrame = false, haveAs = false, blasBuilt = false;
     uint32_t lastFlags = 0;
     void* flushBuf = nullptr;
+    float lastRaysMs = 0.0f;
 };
 
 namespace {
@@ -631,15 +632,21 @@ int rg_debug_trace_rays(rg_ctx* ctx, const float* rays8, uint32_t n, float* tuv,
     CK(cudaMalloc(&dR, 32 * (size_t)(n + 1))); CK(cudaMalloc(&dT, 12 * (size_t)(n + 1))); CK(cudaMalloc(&dI, 8 * (size_t)(n + 1)));
     CK(cudaMemcpyAsync(dR, rays8, 32 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     TraceParams tp; fillTraceParams(ctx, tp, 0);
+    launchTraceRays(tp, dR, n, dT, dI, ctx->stream);   // warm-up
+    CK(cudaEventRecord(ctx->ev[EV_USER0], ctx->stream));
     launchTraceRays(tp, dR, n, dT, dI, ctx->stream);
-    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[EV_USER1], ctx->stream));
+    ctx->launches += 2;
     CK(cudaMemcpyAsync(tuv, dT, 12 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(inst_prim, dI, 8 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(dR); cudaFree(dT); cudaFree(dI);
     CK(cudaGetLastError());
+    cudaEventElapsedTime(&ctx->lastRaysMs, ctx->ev[EV_USER0], ctx->ev[EV_USER1]);
     return 0;
 }
+
+float rg_debug_last_trace_rays_ms(const rg_ctx* ctx) { return ctx ? ctx->lastRaysMs : 0.0f; }
 
 int rg_debug_bvh_stats(rg_ctx* ctx, uint64_t* out8) {
     if(!ctx || !out8) return 1;

@@ -57,13 +57,15 @@ struct RayCtx {
 };
 
 __device__ __forceinline__ float sel3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
+__device__ __forceinline__ float __frcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 __device__ __forceinline__ void setupRay(RayCtx& r, float ox, float oy, float oz, float dx, float dy, float dz) {
     r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
     const float eps = 1e-30f;
-    r.ix = 1.0f / (fabsf(dx) > eps ? dx : copysignf(eps, dx));
-    r.iy = 1.0f / (fabsf(dy) > eps ? dy : copysignf(eps, dy));
-    r.iz = 1.0f / (fabsf(dz) > eps ? dz : copysignf(eps, dz));
+    // approximate reciprocal (1 ulp): only the conservative slab test uses it; the slack below covers it
+    r.ix = __frcp_approx(fabsf(dx) > eps ? dx : copysignf(eps, dx));
+    r.iy = __frcp_approx(fabsf(dy) > eps ? dy : copysignf(eps, dy));
+    r.iz = __frcp_approx(fabsf(dz) > eps ? dz : copysignf(eps, dz));
     r.octinv = (dx >= 0.0f ? 4u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 1u : 0u);
     const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
     const int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
@@ -82,20 +84,27 @@ __device__ __forceinline__ float byteF(uint32_t w) {  // byte J of w as float: P
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + J)) - 8388608.0f;
 }
 
+// One child of a node: slab test on the quantised planes, then OR the child's bits into the hit mask.  Branch-free:
+// bits4 / idx4 hold, per child byte, the bits to insert (0 for an empty slot) and where (see decodeMeta4).
 template <int J>
-__device__ __forceinline__ void childTest(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, uint32_t meta4, float anx,
-                                          float any_, float anz, float onx, float ony, float onz, float afx, float afy, float afz, float ofx, float ofy,
-                                          float ofz, float tmin, float tmax, uint32_t octinv, uint32_t& hitmask) {
-    const float tnx = fmaf(byteF<J>(nx), anx, onx), tny = fmaf(byteF<J>(ny), any_, ony), tnz = fmaf(byteF<J>(nz), anz, onz);
-    const float tfx = fmaf(byteF<J>(fx), afx, ofx), tfy = fmaf(byteF<J>(fy), afy, ofy), tfz = fmaf(byteF<J>(fz), afz, ofz);
+__device__ __forceinline__ void childTest(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, uint32_t bits4, uint32_t idx4,
+                                          float ax, float ay, float az, float onx, float ony, float onz, float ofx, float ofy, float ofz, float tmin,
+                                          float tmax, uint32_t& hitmask) {
+    const float tnx = fmaf(byteF<J>(nx), ax, onx), tny = fmaf(byteF<J>(ny), ay, ony), tnz = fmaf(byteF<J>(nz), az, onz);
+    const float tfx = fmaf(byteF<J>(fx), ax, ofx), tfy = fmaf(byteF<J>(fy), ay, ofy), tfz = fmaf(byteF<J>(fz), az, ofz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-    if(tn <= tf) {
-        const uint32_t m = (meta4 >> (8 * J)) & 0xffu;
-        const uint32_t inner = ((m & 0x18u) == 0x18u) ? 1u : 0u;
-        const uint32_t idx = inner ? (24u + ((m & 7u) ^ octinv)) : (m & 31u);
-        hitmask |= (m >> 5) << idx;
-    }
+    const uint32_t b = (bits4 >> (8 * J)) & 0xffu, i = (idx4 >> (8 * J)) & 0xffu;
+    hitmask |= (tn <= tf) ? (b << i) : 0u;
+}
+
+// Four meta bytes at once (after Ylitie et al. 2017): inner children (bits 3 and 4 set) get bit index 24 + (slot ^ octinv),
+// leaves keep their primitive offset; the bits to insert are meta >> 5 (1 for inner nodes, unary count for leaves).
+__device__ __forceinline__ void decodeMeta4(uint32_t meta4, uint32_t octinv4, uint32_t& bits4, uint32_t& idx4) {
+    const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
+    idx4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
+    bits4 = (meta4 >> 5) & 0x07070707u;
 }
 
 // Watertight ray / triangle test (Woop, Benthin, Wald 2013), no culling; operation order == oracle/orc_scene.cpp intersectTri.
@@ -163,29 +172,33 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
             // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
             // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.
             // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
-            const float anx = sx * r.ix, any_ = sy * r.iy, anz = sz * r.iz;
-            const float afx = anx, afy = any_, afz = anz;
+            const float ax = sx * r.ix, ay = sy * r.iy, az = sz * r.iz;
             const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
-            const float kSlack = 4.8e-7f;
+            const float kSlack = 7.2e-7f;
             const float onx = fmaf(-fabsf(bx), kSlack, bx), ony = fmaf(-fabsf(by), kSlack, by), onz = fmaf(-fabsf(bz), kSlack, bz);
             const float ofx = fmaf(fabsf(bx), kSlack, bx), ofy = fmaf(fabsf(by), kSlack, by), ofz = fmaf(fabsf(bz), kSlack, bz);
             const bool negx = r.dx < 0.0f, negy = r.dy < 0.0f, negz = r.dz < 0.0f;
+            const uint32_t octinv4 = r.octinv * 0x01010101u;
             uint32_t hitmask = 0;
             {   // slots 0..3
                 const uint32_t lx = n2.x, ly = n2.z, lz = n3.x, hx = n3.z, hy = n4.x, hz = n4.z;
                 const uint32_t nx = negx ? hx : lx, fx = negx ? lx : hx, ny = negy ? hy : ly, fy = negy ? ly : hy, nz = negz ? hz : lz, fz = negz ? lz : hz;
-                childTest<0>(nx, ny, nz, fx, fy, fz, n1.z, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
-                childTest<1>(nx, ny, nz, fx, fy, fz, n1.z, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
-                childTest<2>(nx, ny, nz, fx, fy, fz, n1.z, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
-                childTest<3>(nx, ny, nz, fx, fy, fz, n1.z, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+                uint32_t bits4, idx4;
+                decodeMeta4(n1.z, octinv4, bits4, idx4);
+                childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+                childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+                childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+                childTest<3>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
             }
             {   // slots 4..7
                 const uint32_t lx = n2.y, ly = n2.w, lz = n3.y, hx = n3.w, hy = n4.y, hz = n4.w;
                 const uint32_t nx = negx ? hx : lx, fx = negx ? lx : hx, ny = negy ? hy : ly, fy = negy ? ly : hy, nz = negz ? hz : lz, fz = negz ? lz : hz;
-                childTest<0>(nx, ny, nz, fx, fy, fz, n1.w, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
-                childTest<1>(nx, ny, nz, fx, fy, fz, n1.w, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
-                childTest<2>(nx, ny, nz, fx, fy, fz, n1.w, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
-                childTest<3>(nx, ny, nz, fx, fy, fz, n1.w, anx, any_, anz, onx, ony, onz, afx, afy, afz, ofx, ofy, ofz, tmin, hit.t, r.octinv, hitmask);
+                uint32_t bits4, idx4;
+                decodeMeta4(n1.w, octinv4, bits4, idx4);
+                childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+                childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+                childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+                childTest<3>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
             }
             ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
             tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
@@ -202,10 +215,14 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
                 const uint4 l3 = __ldg(lp + 3);
                 if(l3.x == kInvalid) continue;  // instance of an empty mesh
                 const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
-                if(sp + 3 <= kStackSize) {
+                if(sp + 6 <= kStackSize) {
                     if(tg.y) stack[sp++] = tg;
                     if(ng.y & 0xff000000u) stack[sp++] = ng;
-                    stack[sp++] = make_uint2(kInvalid, 0u);
+                    // the world-space slab / shear constants ride on the stack while the instance is traversed
+                    stack[sp++] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
+                    stack[sp++] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx));
+                    stack[sp++] = make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz));
+                    stack[sp++] = make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8));
                 } else continue;  // stack exhausted: skip (never with sane scenes)
                 if(COUNT) cnt[CNT_INST]++;
                 // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
@@ -217,7 +234,7 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
                 const float odx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
                 const float ody = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
                 const float odz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
-                if(odx == 0.0f && ody == 0.0f && odz == 0.0f) { sp -= 1; if(ng.y & 0xff000000u) sp -= 1; if(tg.y) sp -= 1; continue; }
+                if(odx == 0.0f && ody == 0.0f && odz == 0.0f) { sp -= 4; if(ng.y & 0xff000000u) sp -= 1; if(tg.y) sp -= 1; continue; }
                 setupRay(r, oox, ooy, ooz, odx, ody, odz);
                 curInst = l3.y;
                 inBlas = true;
@@ -246,7 +263,11 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
                 ng = stack[--sp];
                 if(ng.x == kInvalid) {  // leave the instance: back to the world-space ray
                     inBlas = false; nodes = P.tlasNodes;
-                    setupRay(r, ox, oy, oz, dx, dy, dz);
+                    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+                    r.octinv = ng.y & 7u; r.kx = (int)((ng.y >> 4) & 3u); r.ky = (int)((ng.y >> 6) & 3u); r.kz = (int)((ng.y >> 8) & 3u);
+                    const uint2 c2 = stack[--sp], c1 = stack[--sp], c0 = stack[--sp];
+                    r.ix = __uint_as_float(c0.x); r.iy = __uint_as_float(c0.y); r.iz = __uint_as_float(c1.x);
+                    r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
                     continue;
                 }
                 break;

@@ -20,3 +20,9 @@ for i in range(8):
     if i >= 3: ts.append((tm["rt_only_ms"], tm["postproc_ms"], tm["as_build_ms"]))
 t = np.median(np.array(ts), axis=0)
 print(f"{os.environ.get('RGB200_LIB','default'):40s} {wl}: trace {t[0]:.3f} ms  post {t[1]:.3f} ms  as {t[2]:.3f} ms  rays {tm['rays']}  {tm['rays']/t[0]/1e3:.0f} Mrays/s")
+
+rt.doRaytracing(rg.RG_FXAA | rg.RG_COUNT_TRAVERSAL)
+tc = rt.timings()
+r = max(tc["rays"], 1)
+print(f"   per ray: nodes {tc['nodes_visited']/r:.2f} tris {tc['tris_tested']/r:.2f} inst {tc['instances_entered']/r:.2f} generic_hits {tc['generic_hits']/r:.2f}"
+      f" | primary {tc['rays_primary']} shadow {tc['rays_shadow']} reflect {tc['rays_reflect']} refract {tc['rays_refract']} sky {tc['sky_lookups']}  bvh {rt.debug_bvh_stats()}")
