@@ -307,8 +307,8 @@ def main():
                         "sample": f"{n} full frames of the same workload ({dt:.1f} s), CPU restatement of the reference shaders, OpenMP over rows",
                         "ms_per_frame": dt / n * 1e3}
 
+    barrier()   # every rank: nobody may still be storing into rank 0's frame buffer
     if peer_ptr is not None:
-        barrier()
         rt.gather_buffer_close(peer_ptr)
     if rank == 0:
         ms_step = dev_ms / args.steps

@@ -349,13 +349,10 @@ __device__ void quantizeNode(Node8& nd, const float (*clo)[3], const float (*chi
 }
 
 template <class LeafSource>
-__global__ void k_collapse_level(const uint2* __restrict__ queueIn, const uint32_t* __restrict__ nInPtr, uint2* __restrict__ queueOut, uint32_t* nOutPtr,
-                                 uint32_t* nodeCounter, uint32_t* primCounter, const BNode* __restrict__ bnodes, const uint2* __restrict__ range,
-                                 const Aabb* __restrict__ primBox, const uint32_t* __restrict__ vals, Node8* __restrict__ nodes, uint32_t nodeOffset,
-                                 uint32_t primOffset, LeafSource leafSrc, uint32_t* __restrict__ wideRef) {
-    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-    if(item >= *nInPtr) return;
-    const uint2 it = queueIn[item];
+__device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint32_t* nOutPtr, uint32_t* nodeCounter, uint32_t* primCounter,
+                             const BNode* __restrict__ bnodes, const uint2* __restrict__ range, const Aabb* __restrict__ primBox,
+                             const uint32_t* __restrict__ vals, Node8* __restrict__ nodes, uint32_t nodeOffset, uint32_t primOffset, LeafSource leafSrc,
+                             uint32_t* __restrict__ wideRef) {
     const uint32_t bref = it.x, wide = it.y;
 
     uint32_t c[8];
@@ -450,6 +447,49 @@ __global__ void k_collapse_level(const uint2* __restrict__ queueIn, const uint32
     nd.childBase = nodeOffset + childBase;
     nd.primBase = primOffset + primBase;
     nodes[nodeOffset + wide] = nd;
+}
+
+// one launch per level (host reads the queue size in between): large builds
+template <class LeafSource>
+__global__ void k_collapse_level(const uint2* __restrict__ queueIn, const uint32_t* __restrict__ nInPtr, uint2* __restrict__ queueOut, uint32_t* nOutPtr,
+                                 uint32_t* nodeCounter, uint32_t* primCounter, const BNode* __restrict__ bnodes, const uint2* __restrict__ range,
+                                 const Aabb* __restrict__ primBox, const uint32_t* __restrict__ vals, Node8* __restrict__ nodes, uint32_t nodeOffset,
+                                 uint32_t primOffset, LeafSource leafSrc, uint32_t* __restrict__ wideRef) {
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    if(item >= *nInPtr) return;
+    collapseItem<LeafSource>(queueIn[item], queueOut, nOutPtr, nodeCounter, primCounter, bnodes, range, primBox, vals, nodes, nodeOffset, primOffset,
+                             leafSrc, wideRef);
+}
+
+// all levels in ONE block-wide loop (no host round trip): the per-frame TLAS.  counters: [0],[1] queue sizes, [2] nodes, [3] prims.
+template <class LeafSource>
+__global__ void __launch_bounds__(1024) k_collapse_all(uint2* queue0, uint2* queue1, uint32_t* counters, uint32_t n, const BNode* __restrict__ bnodes,
+                                                       const uint2* __restrict__ range, const Aabb* __restrict__ primBox,
+                                                       const uint32_t* __restrict__ vals, Node8* __restrict__ nodes, uint32_t nodeOffset,
+                                                       uint32_t primOffset, LeafSource leafSrc, uint32_t* __restrict__ wideRef) {
+    __shared__ uint32_t sCount;
+    if(threadIdx.x == 0) {
+        queue0[0] = make_uint2(n >= 2 ? 0u : kLeafBit, 0u);
+        counters[0] = 1; counters[1] = 0; counters[2] = 1; counters[3] = 0;
+    }
+    __syncthreads();
+    int in = 0;
+    while(true) {
+        if(threadIdx.x == 0) sCount = counters[in];
+        __syncthreads();
+        const uint32_t count = sCount;
+        if(count == 0) break;
+        uint2* qIn = in ? queue1 : queue0;
+        uint2* qOut = in ? queue0 : queue1;
+        for(uint32_t item = threadIdx.x; item < count; item += blockDim.x)
+            collapseItem<LeafSource>(qIn[item], qOut, &counters[in ^ 1], &counters[2], &counters[3], bnodes, range, primBox, vals, nodes, nodeOffset,
+                                     primOffset, leafSrc, wideRef);
+        __threadfence_block();
+        __syncthreads();
+        if(threadIdx.x == 0) counters[in] = 0;
+        in ^= 1;
+        __syncthreads();
+    }
 }
 
 __global__ void k_collapse_seed(uint2* queue, uint32_t* counters, uint32_t n) {
@@ -630,8 +670,14 @@ void buildTlas(LbvhScratch& s, const InstTrav* instTrav, const InstShade* instSh
     s.launches++;
     lbvhCommon(s, n, st);
     LeafSourceInst ls{instTrav, tlasLeavesOut};
-    uint32_t nNodes = 0, nPrims = 0;
-    collapseHostDriven(s, n, tlasNodes, 0, 0, ls, &nNodes, &nPrims, st);
+    if(n <= kTlasSingleBlockMax) {   // fully asynchronous: every level inside one block
+        k_collapse_all<LeafSourceInst><<<1, 1024, 0, st>>>(s.queue[0], s.queue[1], s.counters, n, s.bnodes, s.range, s.primBox, s.vals[s.sortedBuf],
+                                                          tlasNodes, 0, 0, ls, s.wideRef);
+        s.launches++;
+    } else {
+        uint32_t nNodes = 0, nPrims = 0;
+        collapseHostDriven(s, n, tlasNodes, 0, 0, ls, &nNodes, &nPrims, st);
+    }
 }
 
 }  // namespace rg

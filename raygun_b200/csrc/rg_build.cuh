@@ -27,6 +27,8 @@ struct LbvhScratch {
     void release();
 };
 
+constexpr uint32_t kTlasSingleBlockMax = 1u << 17;   // instances; above this the level loop goes back to the host
+
 struct TriSource { const void* vertices; const uint32_t* indices; uint32_t vtxOff, idxOff, nTri; };
 
 // Builds the BLAS of one mesh.  nodesOut / trisOut point at the first free slot of the shared arrays;
