@@ -11,8 +11,8 @@
 // transition image is R8_SNORM (raytracer.cpp:187); out-of-bounds imageLoad returns 0 and
 // out-of-bounds imageStore is dropped, so the 16x16 work-group padding (raytracer.cpp:108-109)
 // reduces to "loop over in-bounds pixels".  The FXAA sampler is linear / clamp-to-edge
-// (raygun/compute/compute_system.cpp:76-84); the nine taps taken exactly at texel centres
-// (textureGather / textureLodOffset at posM, fxaa.h:779-845) are modelled as exact texel reads.
+// (raygun/compute/compute_system.cpp:76-84) evaluated with float weights; the nine taps at the pixel centre
+// (textureLodOffset at posM, fxaa.h:804-845, non-gather path) go through the same bilinear arithmetic.
 #include <omp.h>
 
 #include <cmath>
@@ -31,12 +31,13 @@ struct Img {
         x = x < 0 ? 0 : (x >= W ? W - 1 : x); y = y < 0 ? 0 : (y >= H ? H - 1 : y);
         return unpack_half4(p[(size_t)y * W + x]);
     }
-    // textureLod(sampler2D, p, 0) with linear filter and clamp-to-edge
-    vec4 sample(float px, float py) const {
+    // textureLod / textureLodOffset(sampler2D, p, 0, o) with linear filter and clamp-to-edge: float weights, the texel
+    // offset is added after the floor (as llvmpipe's float path does for rgba16f)
+    vec4 sample(float px, float py, int ox = 0, int oy = 0) const {
         const float u = px * (float)W - 0.5f, v = py * (float)H - 0.5f;
         const float fu = std::floor(u), fv = std::floor(v);
         const float ax = u - fu, ay = v - fv;
-        const int x0 = (int)fu, y0 = (int)fv;
+        const int x0 = (int)fu + ox, y0 = (int)fv + oy;
         const vec4 c00 = texel(x0, y0), c10 = texel(x0 + 1, y0), c01 = texel(x0, y0 + 1), c11 = texel(x0 + 1, y0 + 1);
         const vec4 top = c00 * (1.0f - ax) + c10 * ax, bot = c01 * (1.0f - ax) + c11 * ax;
         return top * (1.0f - ay) + bot * ay;
@@ -62,10 +63,12 @@ vec4 fxaaPixel(const Img& tex, int gx, int gy) {
     const float subpix = 1.0f, edgeThreshold = 0.063f, edgeThresholdMin = 0.0312f;          // fxaa.comp:34
     static const float P[12] = {1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.5f, 2.0f, 2.0f, 2.0f, 2.0f, 4.0f, 8.0f};  // fxaa.h:487-500
 
-    const vec4 rgbyM = tex.texel(gx, gy);
+    // fxaa.h:804-814 (FXAA_GATHER4_ALPHA == 0): FxaaTexTop / FxaaTexOff are sampler reads AT posM; (gx + 0.5) / W * W - 0.5 is
+    // not always exactly gx in binary32, so these go through the bilinear arithmetic like every other tap
+    const vec4 rgbyM = tex.sample(posMx, posMy);
     const float lumaM = rgbyM.y;
-    float lumaS = tex.texel(gx, gy + 1).y, lumaE = tex.texel(gx + 1, gy).y;
-    float lumaN = tex.texel(gx, gy - 1).y, lumaW = tex.texel(gx - 1, gy).y;
+    float lumaS = tex.sample(posMx, posMy, 0, 1).y, lumaE = tex.sample(posMx, posMy, 1, 0).y;
+    float lumaN = tex.sample(posMx, posMy, 0, -1).y, lumaW = tex.sample(posMx, posMy, -1, 0).y;
 
     const float maxSM = fmax_glsl(lumaS, lumaM), minSM = fmin_glsl(lumaS, lumaM);
     const float maxESM = fmax_glsl(lumaE, maxSM), minESM = fmin_glsl(lumaE, minSM);
@@ -76,8 +79,8 @@ vec4 fxaaPixel(const Img& tex, int gx, int gy) {
     const float rangeMaxClamped = fmax_glsl(edgeThresholdMin, rangeMaxScaled);
     if(range < rangeMaxClamped) return rgbyM;
 
-    const float lumaNW = tex.texel(gx - 1, gy - 1).y, lumaSE = tex.texel(gx + 1, gy + 1).y;
-    const float lumaNE = tex.texel(gx + 1, gy - 1).y, lumaSW = tex.texel(gx - 1, gy + 1).y;
+    const float lumaNW = tex.sample(posMx, posMy, -1, -1).y, lumaSE = tex.sample(posMx, posMy, 1, 1).y;   // fxaa.h:837-845
+    const float lumaNE = tex.sample(posMx, posMy, 1, -1).y, lumaSW = tex.sample(posMx, posMy, -1, 1).y;
 
     const float lumaNS = lumaN + lumaS, lumaWE = lumaW + lumaE;
     const float subpixRcpRange = 1.0f / range;

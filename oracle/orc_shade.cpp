@@ -49,10 +49,10 @@ const float kAAOffsets[9][8][2] = {
     {{0.0625f, -0.1875f}, {-0.0625f, 0.1875f}, {0.3125f, 0.0625f}, {-0.1875f, -0.3125f}, {-0.3125f, 0.3125f}, {-0.4375f, -0.0625f}, {0.1875f, 0.4375f}, {0.4375f, -0.4375f}},
 };
 
-// miss.rmiss:38-74.  normalize(0) would be NaN (hazard 7): a zero direction is kept as 0.
+// miss.rmiss:38-74.  normalize(0) would be NaN (hazard 7): a zero direction is kept as 0 (ORC_STRICT_IEEE: literal NaN).
 vec3 skyMix(const Ctx& c, vec3 worldRayDir, vec3 sunTone, vec3 skyTone, vec3 scatterTone, float scatterFactor, float powFactor) {
     const bool zero = worldRayDir.x == 0.0f && worldRayDir.y == 0.0f && worldRayDir.z == 0.0f;
-    const vec3 rayDir = zero ? vec3(0.0f) : normalize(worldRayDir);
+    const vec3 rayDir = (zero && !(c.flags & ORC_STRICT_IEEE)) ? vec3(0.0f) : normalize(worldRayDir);
     const float y = std::fabs(worldRayDir.y + 1.5f) / 3.0f;
 
     float sun = 1.0f - distance(rayDir, normalize(-c.lightDir));

@@ -116,25 +116,37 @@ __device__ F4 fxaaPixel(const uint2* __restrict__ tex, int gx, int gy, int LW, i
     const float P[12] = {1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.5f, 2.0f, 2.0f, 2.0f, 2.0f, 4.0f, 8.0f};
     // global texture coordinate of the pixel centre; local sampling subtracts the rectangle origin in texel space
     float posMx = ((float)(gx + ox) + 0.5f) / (float)fw, posMy = ((float)(gy + oy) + 0.5f) / (float)fh;
-    auto sG = [&](float px, float py) {
+    // textureLod / textureLodOffset(tex, p, 0, o): linear filter with float weights, clamp-to-edge of the FULL frame, texel offset
+    // added after the floor; then into the local rectangle's coordinates
+    auto sG = [&](float px, float py, int dx, int dy) {
         const float u = px * (float)fw - 0.5f, v = py * (float)fh - 0.5f;
         const float fu = floorf(u), fv = floorf(v);
         const float ax = u - fu, ay = v - fv;
-        // clamp-to-edge of the FULL frame, then into local coordinates
-        const int X0 = min(max((int)fu, 0), fw - 1) - ox, X1 = min(max((int)fu + 1, 0), fw - 1) - ox;
-        const int Y0 = min(max((int)fv, 0), fh - 1) - oy, Y1 = min(max((int)fv + 1, 0), fh - 1) - oy;
+        const int X0 = min(max((int)fu + dx, 0), fw - 1) - ox, X1 = min(max((int)fu + dx + 1, 0), fw - 1) - ox;
+        const int Y0 = min(max((int)fv + dy, 0), fh - 1) - oy, Y1 = min(max((int)fv + dy + 1, 0), fh - 1) - oy;
         const float c00 = texelG(tex, X0, Y0, LW, LH), c10 = texelG(tex, X1, Y0, LW, LH), c01 = texelG(tex, X0, Y1, LW, LH), c11 = texelG(tex, X1, Y1, LW, LH);
         const float top = c00 * (1.0f - ax) + c10 * ax, bot = c01 * (1.0f - ax) + c11 * ax;
         return top * (1.0f - ay) + bot * ay;
     };
-    auto tG = [&](int dx, int dy) {  // exact texel read at the pixel centre + offset, clamp-to-edge of the full frame
-        const int X = min(max(gx + ox + dx, 0), fw - 1) - ox, Y = min(max(gy + oy + dy, 0), fh - 1) - oy;
-        return texelG(tex, X, Y, LW, LH);
+    auto s4 = [&](float px, float py) {
+        const float u = px * (float)fw - 0.5f, v = py * (float)fh - 0.5f;
+        const float fu = floorf(u), fv = floorf(v);
+        const float ax = u - fu, ay = v - fv;
+        const int X0 = min(max((int)fu, 0), fw - 1) - ox, X1 = min(max((int)fu + 1, 0), fw - 1) - ox;
+        const int Y0 = min(max((int)fv, 0), fh - 1) - oy, Y1 = min(max((int)fv + 1, 0), fh - 1) - oy;
+        const F4 c00 = texel(tex, X0, Y0, LW, LH), c10 = texel(tex, X1, Y0, LW, LH), c01 = texel(tex, X0, Y1, LW, LH), c11 = texel(tex, X1, Y1, LW, LH);
+        F4 o;
+        o.x = (c00.x * (1.0f - ax) + c10.x * ax) * (1.0f - ay) + (c01.x * (1.0f - ax) + c11.x * ax) * ay;
+        o.y = (c00.y * (1.0f - ax) + c10.y * ax) * (1.0f - ay) + (c01.y * (1.0f - ax) + c11.y * ax) * ay;
+        o.z = (c00.z * (1.0f - ax) + c10.z * ax) * (1.0f - ay) + (c01.z * (1.0f - ax) + c11.z * ax) * ay;
+        o.w = (c00.w * (1.0f - ax) + c10.w * ax) * (1.0f - ay) + (c01.w * (1.0f - ax) + c11.w * ax) * ay;
+        return o;
     };
 
-    const F4 rgbyM = texel(tex, gx, gy, LW, LH);
+    // fxaa.h:804-814 (non-gather path): the taps at the pixel centre are sampler reads too
+    const F4 rgbyM = s4(posMx, posMy);
     const float lumaM = rgbyM.y;
-    float lumaS = tG(0, 1), lumaE = tG(1, 0), lumaN = tG(0, -1), lumaW = tG(-1, 0);
+    float lumaS = sG(posMx, posMy, 0, 1), lumaE = sG(posMx, posMy, 1, 0), lumaN = sG(posMx, posMy, 0, -1), lumaW = sG(posMx, posMy, -1, 0);
     const float maxSM = fmaxf(lumaS, lumaM), minSM = fminf(lumaS, lumaM);
     const float maxESM = fmaxf(lumaE, maxSM), minESM = fminf(lumaE, minSM);
     const float maxWN = fmaxf(lumaN, lumaW), minWN = fminf(lumaN, lumaW);
@@ -144,7 +156,7 @@ __device__ F4 fxaaPixel(const uint2* __restrict__ tex, int gx, int gy, int LW, i
     const float rangeMaxClamped = fmaxf(0.0312f, rangeMaxScaled);
     if(range < rangeMaxClamped) return rgbyM;
 
-    const float lumaNW = tG(-1, -1), lumaSE = tG(1, 1), lumaNE = tG(1, -1), lumaSW = tG(-1, 1);
+    const float lumaNW = sG(posMx, posMy, -1, -1), lumaSE = sG(posMx, posMy, 1, 1), lumaNE = sG(posMx, posMy, 1, -1), lumaSW = sG(posMx, posMy, -1, 1);
     const float lumaNS = lumaN + lumaS, lumaWE = lumaW + lumaE;
     const float subpixRcpRange = 1.0f / range;
     const float subpixNSWE = lumaNS + lumaWE;
@@ -177,9 +189,9 @@ __device__ F4 fxaaPixel(const uint2* __restrict__ tex, int gx, int gy, int LW, i
     float posNx = posBx - offNPx * P[0], posNy = posBy - offNPy * P[0];
     float posPx = posBx + offNPx * P[0], posPy = posBy + offNPy * P[0];
     const float subpixD = ((-2.0f) * subpixC) + 3.0f;
-    float lumaEndN = sG(posNx, posNy);
+    float lumaEndN = sG(posNx, posNy, 0, 0);
     const float subpixE = subpixC * subpixC;
-    float lumaEndP = sG(posPx, posPy);
+    float lumaEndP = sG(posPx, posPy, 0, 0);
     if(!pairN) lumaNN = lumaSS;
     const float gradientScaled = gradient * 1.0f / 4.0f;
     const float lumaMM = lumaM - lumaNN * 0.5f;
@@ -193,8 +205,8 @@ __device__ F4 fxaaPixel(const uint2* __restrict__ tex, int gx, int gy, int LW, i
     if(!doneP) { posPx += offNPx * P[1]; posPy += offNPy * P[1]; }
 #pragma unroll 1
     for(int k = 2; k < 12 && doneNP; ++k) {
-        if(!doneN) lumaEndN = sG(posNx, posNy);
-        if(!doneP) lumaEndP = sG(posPx, posPy);
+        if(!doneN) lumaEndN = sG(posNx, posNy, 0, 0);
+        if(!doneP) lumaEndP = sG(posPx, posPy, 0, 0);
         if(!doneN) lumaEndN = lumaEndN - lumaNN * 0.5f;
         if(!doneP) lumaEndP = lumaEndP - lumaNN * 0.5f;
         doneN = fabsf(lumaEndN) >= gradientScaled;
@@ -220,18 +232,7 @@ __device__ F4 fxaaPixel(const uint2* __restrict__ tex, int gx, int gy, int LW, i
     const float pixelOffsetSubpix = fmaxf(pixelOffsetGood, subpixH);
     if(!horzSpan) posMx += pixelOffsetSubpix * lengthSign;
     if(horzSpan) posMy += pixelOffsetSubpix * lengthSign;
-    F4 s;
-    {
-        const float u = posMx * (float)fw - 0.5f, v = posMy * (float)fh - 0.5f;
-        const float fu = floorf(u), fv = floorf(v);
-        const float ax = u - fu, ay = v - fv;
-        const int X0 = min(max((int)fu, 0), fw - 1) - ox, X1 = min(max((int)fu + 1, 0), fw - 1) - ox;
-        const int Y0 = min(max((int)fv, 0), fh - 1) - oy, Y1 = min(max((int)fv + 1, 0), fh - 1) - oy;
-        const F4 c00 = texel(tex, X0, Y0, LW, LH), c10 = texel(tex, X1, Y0, LW, LH), c01 = texel(tex, X0, Y1, LW, LH), c11 = texel(tex, X1, Y1, LW, LH);
-        s.x = (c00.x * (1.0f - ax) + c10.x * ax) * (1.0f - ay) + (c01.x * (1.0f - ax) + c11.x * ax) * ay;
-        s.y = (c00.y * (1.0f - ax) + c10.y * ax) * (1.0f - ay) + (c01.y * (1.0f - ax) + c11.y * ax) * ay;
-        s.z = (c00.z * (1.0f - ax) + c10.z * ax) * (1.0f - ay) + (c01.z * (1.0f - ax) + c11.z * ax) * ay;
-    }
+    F4 s = s4(posMx, posMy);
     s.w = lumaM;
     return s;
 }

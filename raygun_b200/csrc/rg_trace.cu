@@ -291,9 +291,9 @@ __device__ __forceinline__ float2 aaOffset(int numSamples, int i) {
 }
 
 // miss.rmiss:38-74 with the constants of :78; normalize(0) is kept 0 (SURVEY hazard 7)
-__device__ V3 skyColor(V3 d, V3 lightDir) {
+__device__ V3 skyColor(V3 d, V3 lightDir, bool strict) {
     const bool zero = d.x == 0.0f && d.y == 0.0f && d.z == 0.0f;
-    const V3 rayDir = zero ? v3(0, 0, 0) : normalize(d);
+    const V3 rayDir = (zero && !strict) ? v3(0, 0, 0) : normalize(d);
     const float y = fabsf(d.y + 1.5f) / 3.0f;
     const V3 sd = normalize(-lightDir) - rayDir;
     float sun = 1.0f - sqrtf(dot(sd, sd));
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
             }
         } else {
             if(missIndex == 0) {  // miss.rmiss:76-83
-                const V3 sky = skyColor(rd, L);
+                const V3 sky = skyColor(rd, L, strictIeee);
                 hv = sky; depth = 10000.0f;
                 if(sp == 0 && recDepth == 0) { pRough = sky; pRoughA = 0.0f; }   // roughValue is only observable for a primary miss
             } else {              // shadowMiss.rmiss:33
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                     const float dp2 = dp * dp;
                     shadowCol = shadowCol * (dp2 * dp2 * dp + 0.75f);   // pow(x, 5)
                     cnt[CNT_SKY]++;   // T4: cull mask 0 -> always miss 0
-                    const V3 sky = skyColor(-dir, L);
+                    const V3 sky = skyColor(-dir, L, strictIeee);
                     depth = 10000.0f;
                     hv = shadowCol + sky * 0.1f;
                 }
