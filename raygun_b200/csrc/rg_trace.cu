@@ -37,7 +37,10 @@ __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y 
 __device__ __forceinline__ V3 normalize(V3 a) { const float r = 1.0f / sqrtf(dot(a, a)); return a * r; }
 __device__ __forceinline__ V3 mix3(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// GLSL min / max / clamp as GLM evaluates them ((y < x) ? y : x ...): NaN propagates exactly as in the oracle (RG_STRICT_IEEE)
+__device__ __forceinline__ float glmin(float x, float y) { return (y < x) ? y : x; }
+__device__ __forceinline__ float glmax(float x, float y) { return (x < y) ? y : x; }
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return glmin(glmax(x, lo), hi); }
 __device__ __forceinline__ float glmod(float x, float y) { return x - y * floorf(x / y); }
 __device__ __forceinline__ V3 reflect3(V3 I, V3 N) { return I - N * (dot(N, I) * 2.0f); }
 __device__ __forceinline__ V3 refract3(V3 I, V3 N, float eta) {
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
             if(effectId == 1u) {  // gridEffect, :74-91
                 const float aa = (refDepth + hit.t + 8.0f) / 30.0f;
                 const float aa2 = aa / 2.0f;
-                float minmod = fminf(fabsf(glmod((origin.x + 1000.0f) * 10.0f + aa2, 20.0f) - aa2), fabsf(glmod((origin.z + 1000.0f) * 10.0f + aa2, 20.0f) - aa2));
+                float minmod = glmin(fabsf(glmod((origin.x + 1000.0f) * 10.0f + aa2, 20.0f) - aa2), fabsf(glmod((origin.z + 1000.0f) * 10.0f + aa2, 20.0f) - aa2));
                 if(minmod < aa2) {
                     minmod -= aa2 - (aa * aa) / 3.0f;
                     minmod *= 3.0f / (aa * aa);
@@ -491,7 +494,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                 const bool frontFacing = dot(-rd, n) > 0.0f;
                 if(!frontFacing) n = normalize(-n);
                 const float ndl = dot(-L, n);
-                V3 baseColor = diffuse * fmaxf(ndl, 0.2f);
+                V3 baseColor = diffuse * glmax(ndl, 0.2f);
                 float* f = fr[sp++];
                 f[F_ORG] = origin.x; f[F_ORG + 1] = origin.y; f[F_ORG + 2] = origin.z;
                 f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
@@ -621,7 +624,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                 const V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]);
                 const V3 reflectColor = v3(f[F_RCOL], f[F_RCOL + 1], f[F_RCOL + 2]);
                 const float transparency = f[F_TRANSP], reflectivity = f[F_REFL], roughness = f[F_ROUGH];
-                const float totalContrib = fmaxf(transparency, reflectivity);
+                const float totalContrib = glmax(transparency, reflectivity);
                 float weight = reflectivity / (transparency + reflectivity);
                 if(!strictIeee && (transparency + reflectivity) == 0.0f) weight = 0.0f;   // SURVEY hazard 8
                 const V3 roughCol = mix3(refractColor, reflectColor, weight);
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                 if(recDepth == 0) {
                     hv = base;
                     pNormal = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                    pRough = roughCol; pRoughA = fminf((f[F_RDEPTH] / 50.0f) * roughness, roughness / 2.1f);
+                    pRough = roughCol; pRoughA = glmin((f[F_RDEPTH] / 50.0f) * roughness, roughness / 2.1f);
                     pContrib = totalContrib;
                 }
                 depth = f[F_T];
