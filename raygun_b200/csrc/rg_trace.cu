@@ -18,6 +18,10 @@
 
 #include "../../include/rgb200.h"
 
+#ifndef RG_POSTPONE_THRESHOLD
+#define RG_POSTPONE_THRESHOLD 12
+#endif
+
 namespace rg {
 
 namespace {
@@ -83,8 +87,8 @@ __device__ __forceinline__ void setupRay(RayCtx& r, float ox, float oy, float oz
 }
 
 template <int J>
-__device__ __forceinline__ float byteF(uint32_t w) {  // byte J of w as float: PRMT into the mantissa of 2^23, one FADD
-    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + J)) - 8388608.0f;
+__device__ __forceinline__ float byteF(uint32_t w) {  // 1 + b / 32768 for byte J of w: ONE PRMT puts b into mantissa bits 15..8 of 1.0f;
+    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u + (J << 4)));   // the affine map back to b is folded into the FFMA constants
 }
 
 // One child of a node: slab test on the quantised planes, then OR the child's bits into the hit mask.  Branch-free:
@@ -175,11 +179,14 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
             // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
             // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.
             // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
-            const float ax = sx * r.ix, ay = sy * r.iy, az = sz * r.iz;
+            // byteF gives v = 1 + q / 32768, so t = v * A + (b - A) with A = 32768 * 2^e / d.  Rounding: ulp(A) = 1/256 of one
+            // quantisation step in t, plus the error of b = (p - o) / d; both are covered by the slack (relative to |b| and to a step).
+            const float ax = sx * r.ix * 32768.0f, ay = sy * r.iy * 32768.0f, az = sz * r.iz * 32768.0f;
             const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
-            const float kSlack = 7.2e-7f;
-            const float onx = fmaf(-fabsf(bx), kSlack, bx), ony = fmaf(-fabsf(by), kSlack, by), onz = fmaf(-fabsf(bz), kSlack, bz);
-            const float ofx = fmaf(fabsf(bx), kSlack, bx), ofy = fmaf(fabsf(by), kSlack, by), ofz = fmaf(fabsf(bz), kSlack, bz);
+            const float kSlack = 7.2e-7f, kStep = 1.0f / (32768.0f * 64.0f);   // 1/64 of a quantisation step
+            const float wx = fmaf(fabsf(bx), kSlack, fabsf(ax) * kStep), wy = fmaf(fabsf(by), kSlack, fabsf(ay) * kStep), wz = fmaf(fabsf(bz), kSlack, fabsf(az) * kStep);
+            const float onx = (bx - ax) - wx, ony = (by - ay) - wy, onz = (bz - az) - wz;
+            const float ofx = (bx - ax) + wx, ofy = (by - ay) + wy, ofz = (bz - az) + wz;
             const bool negx = r.dx < 0.0f, negy = r.dy < 0.0f, negz = r.dz < 0.0f;
             const uint32_t octinv4 = r.octinv * 0x01010101u;
             uint32_t hitmask = 0;
@@ -246,6 +253,16 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
                 tg = make_uint2(0u, 0u);
                 break;
             } else {
+#if RG_POSTPONE_THRESHOLD > 0
+                // too few lanes of this warp are in the triangle loop and this lane still has child nodes to visit: put the
+                // triangle group back (it goes to the stack) and test it later together with more lanes (after Ylitie et al. 2017)
+                if((ng.y & 0xff000000u) && sp < kStackSize && __popc(__activemask()) < RG_POSTPONE_THRESHOLD) {
+                    tg.y |= 1u << bit;
+                    stack[sp++] = tg;
+                    tg.y = 0u;
+                    break;
+                }
+#endif
                 const float4* tp = reinterpret_cast<const float4*>(P.tris + (tg.x + bit));
                 const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
                 if(COUNT) cnt[CNT_TRIS]++;
@@ -294,7 +311,7 @@ __device__ __forceinline__ float2 aaOffset(int numSamples, int i) {
 }
 
 // miss.rmiss:38-74 with the constants of :78; normalize(0) is kept 0 (SURVEY hazard 7)
-__device__ V3 skyColor(V3 d, V3 lightDir, bool strict) {
+__device__ __noinline__ V3 skyColor(V3 d, V3 lightDir, bool strict) {
     const bool zero = d.x == 0.0f && d.y == 0.0f && d.z == 0.0f;
     const V3 rayDir = (zero && !strict) ? v3(0, 0, 0) : normalize(d);
     const float y = fabsf(d.y + 1.5f) / 3.0f;
@@ -331,6 +348,9 @@ enum { ST_SHADOW_RET = 0, ST_TRY_REFLECT = 1, ST_REFLECT_RET = 2, ST_TRY_REFRACT
 __device__ __forceinline__ uint32_t f2h(float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); }
 __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) { return make_uint2(f2h(x) | (f2h(y) << 16), f2h(z) | (f2h(w) << 16)); }
 
+#ifndef RG_POSTPONE_THRESHOLD
+#define RG_POSTPONE_THRESHOLD 12
+#endif
 #ifndef RG_TRACE_MIN_BLOCKS
 #define RG_TRACE_MIN_BLOCKS 4
 #endif
