@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--split", default="columns", choices=["columns", "rows"])
+    ap.add_argument("--mgpu", default="partition", choices=["partition", "overdraw"],
+                    help="N > 1: 'partition' = tiles traced round-robin, G-buffer pixels stored to their owners over NVLink; 'overdraw' = every band re-traces its halo")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -161,7 +163,7 @@ def main():
 
     import torch
     import raygun_b200 as rg
-    from raygun_b200.parallel import band_region, share_gather_handle, overdraw
+    from raygun_b200.parallel import band_region, share_gather_handle, overdraw, attach_partition
 
     dist = None
     if world > 1:
@@ -180,6 +182,9 @@ def main():
     inst_raw = rt.pack_instances(sd.inst_xform, sd.inst_meta)
     rt.setupTopLevelAS(inst_raw)
     rt.updateRenderTarget(ubo)
+
+    if world > 1 and args.mgpu == "partition":
+        attach_partition(dist, rt, rank, world)
 
     # gather target: rank 0's full-frame buffer, mapped into every other rank through CUDA IPC (NVLink peer stores)
     peer_ptr = None
@@ -270,11 +275,13 @@ def main():
 
     # ---------------- roofline of the dominant kernel (k_trace) from one instrumented, untimed frame (rank 0, N = 1 only)
     roofline = None
+    # (every rank renders it: in partitioned mode a frame is a collective operation)
+    rt.set_instances_device(d_inst.data_ptr(), len(inst_raw))
+    rt.doRaytracing(flags | rg.RG_COUNT_TRAVERSAL)
+    tmc = rt.timings()
+    barrier()
     if rank == 0:
         peak, peak_src = load_peaks()
-        rt.set_instances_device(d_inst.data_ptr(), len(inst_raw))
-        rt.doRaytracing(flags | rg.RG_COUNT_TRAVERSAL)
-        tmc = rt.timings()
         px = rt.region_size[0] * rt.region_size[1]
         alg_bytes = trace_algorithmic_bytes(tmc, px)
         trace_ms = sections["rt_only_ms"] / args.steps
@@ -308,14 +315,20 @@ def main():
                         "ms_per_frame": dt / n * 1e3}
 
     barrier()   # every rank: nobody may still be storing into rank 0's frame buffer
+    sync_err = rt.sync_error()
     if peer_ptr is not None:
         rt.gather_buffer_close(peer_ptr)
+    if world > 1 and args.mgpu == "partition":
+        rt.peer_detach_all()
+    if sync_err:
+        raise RuntimeError(f"rank {rank}: cross-GPU barrier timed out waiting for rank {sync_err - 1}")
     if rank == 0:
         ms_step = dev_ms / args.steps
         line = {"metric": "Mrays/s", "value": rays_total / (dev_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": desc, "width": W, "height": H, "split": f"{world} {args.split} bands, 40 px halo, overdraw x{overdraw(W, H, world, args.split):.3f}" if world > 1 else "none",
+                "config": {"workload": desc, "width": W, "height": H, "split": (f"{world} {args.split} bands for the post chain; trace: 8x4 tiles dealt round-robin in chunks of 16, G-buffer pixels stored to their owners over NVLink"
+                                     if args.mgpu == "partition" else f"{world} {args.split} bands, 40 px halo re-traced, overdraw x{overdraw(W, H, world, args.split):.3f}") if world > 1 else "none",
                            "l2": "flushed before every timed frame (256 MiB memset)", "tlas": "rebuilt every frame"},
                 "fps": 1e3 / ms_step, "rays_per_frame": rays_total / args.steps,
                 "sections_ms": {k: v / args.steps for k, v in sections.items()}, "wall_ms_per_step_incl_flush": wall_ms / args.steps,

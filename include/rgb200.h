@@ -158,6 +158,25 @@ int rg_set_ubo_device(rg_ctx* ctx, const rg_ubo* d_ubo);
 /* Device address of the RGBA8 frame buffer (region-sized, row pitch = region width * 4). */
 int rg_framebuffer_device_ptr(rg_ctx* ctx, void** d_ptr);
 
+/* Partitioned multi-GPU mode (preferred over plain regions: no halo is traced twice and the load is balanced).
+ * Every rank keeps its region (rg_set_region) for the post chain, but TRACES every world-th chunk of 8x4-pixel tiles of the
+ * whole frame; the trace kernel stores each finished pixel's G-buffer straight into the images of every rank whose
+ * region + halo contains it (own memory or peer memory over NVLink).  Two device-side flag barriers per frame (after the
+ * trace, after the post chain) keep the ranks in step without host round trips; a wait gives up after 4 s (rg_sync_error).
+ * Order of calls: rg_set_region, rg_set_partition, then on every rank rg_peer_export -> exchange the descriptors ->
+ * rg_peer_attach for every other rank (open_ipc = 1 across processes, 0 for contexts of one process). */
+typedef struct rg_peer_desc {
+    void* base; void* normal; void* rough;          /* G-buffer images of the exporting rank (device pointers in ITS address space) */
+    void* arrive_trace; void* arrive_post;          /* its two flag arrays */
+    int32_t x0, y0, w, h;                           /* its rectangle (region + halo) in frame coordinates */
+    uint8_t ipc[5][64];                             /* cudaIpcMemHandle_t of the five allocations above */
+} rg_peer_desc;
+int rg_set_partition(rg_ctx* ctx, uint32_t rank, uint32_t world);
+int rg_peer_export(rg_ctx* ctx, rg_peer_desc* out);
+int rg_peer_attach(rg_ctx* ctx, uint32_t peer_rank, const rg_peer_desc* desc, int open_ipc);
+int rg_peer_detach_all(rg_ctx* ctx);
+int rg_sync_error(rg_ctx* ctx);
+
 /* Tile gather over NVLink: the final kernel (FXAA + 8-bit convert) stores this context's region
  * straight into `d_target` (a width x height RGBA8 frame that may live on a PEER GPU: either a
  * pointer in the same process with peer access enabled, or one opened from a CUDA IPC handle). */

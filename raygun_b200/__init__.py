@@ -30,6 +30,7 @@ ABI_SYMBOLS = (
     "rg_set_instances_device", "rg_set_ubo_device", "rg_framebuffer_device_ptr", "rg_set_gather_target", "rg_gather_buffer_export",
     "rg_gather_buffer_open", "rg_gather_buffer_close", "rg_read_gathered_rgba8", "rg_debug_blas_sort", "rg_debug_tlas_sort", "rg_debug_trace_rays",
     "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2", "rg_debug_last_trace_rays_ms",
+    "rg_set_partition", "rg_peer_export", "rg_peer_attach", "rg_peer_detach_all", "rg_sync_error",
 )
 
 
@@ -39,6 +40,12 @@ class RgTimings(C.Structure):
                 ("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_refract", C.c_uint64),
                 ("sky_lookups", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("instances_entered", C.c_uint64),
                 ("generic_hits", C.c_uint64)]
+
+
+class RgPeerDesc(C.Structure):
+    """rg_peer_desc (include/rgb200.h): one rank's G-buffer images, barrier flags, rectangle and CUDA IPC handles."""
+    _fields_ = [("base", C.c_void_p), ("normal", C.c_void_p), ("rough", C.c_void_p), ("arrive_trace", C.c_void_p), ("arrive_post", C.c_void_p),
+                ("x0", C.c_int32), ("y0", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("ipc", (C.c_ubyte * 64) * 5)]
 
 
 _lib = None
@@ -219,6 +226,25 @@ class Raytracer:
 
     def gather_buffer_close(self, dptr: int):
         self._ck(self.lib.rg_gather_buffer_close(self.h, C.c_void_p(dptr)))
+
+    # partitioned multi-GPU mode (trace shares dealt round-robin, G-buffer pixels stored into the owners' memory)
+    def set_partition(self, rank: int, world: int):
+        self._ck(self.lib.rg_set_partition(self.h, C.c_uint32(rank), C.c_uint32(world)))
+
+    def peer_export(self) -> bytes:
+        d = RgPeerDesc()
+        self._ck(self.lib.rg_peer_export(self.h, C.byref(d)))
+        return bytes(d)
+
+    def peer_attach(self, peer_rank: int, desc: bytes, open_ipc: bool):
+        d = RgPeerDesc.from_buffer_copy(desc)
+        self._ck(self.lib.rg_peer_attach(self.h, C.c_uint32(peer_rank), C.byref(d), C.c_int(1 if open_ipc else 0)))
+
+    def peer_detach_all(self):
+        self._ck(self.lib.rg_peer_detach_all(self.h))
+
+    def sync_error(self) -> int:
+        return int(self.lib.rg_sync_error(self.h))
 
     def set_gather_target(self, dptr):
         self._ck(self.lib.rg_set_gather_target(self.h, C.c_void_p(dptr or 0)))

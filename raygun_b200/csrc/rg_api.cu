@@ -43,6 +43,16 @@ struct rg_ctx {
     uint2 *base = nullptr, *normal = nullptr, *rough = nullptr, *final_ = nullptr, *roughA = nullptr, *roughB = nullptr;
     signed char* trans = nullptr;
     uint32_t *rgba8 = nullptr, *idInst = nullptr, *idPrim = nullptr;
+    uint2* fxaaOut = nullptr;          // FXAA target (the reference writes baseImage and swaps; pointers stay put here so peers can keep them)
+    bool lastFxaa = false;
+    // partitioned multi-GPU mode: who traces what, where finished pixels go, and the two cross-GPU barriers per frame
+    uint32_t rank = 0, world = 1, frameId = 0;
+    TraceParams::Target peers[kMaxPeers]{};
+    uint32_t* peerArriveTrace[kMaxPeers]{}; uint32_t* peerArrivePost[kMaxPeers]{};
+    void* peerIpcOpened[kMaxPeers][5]{};
+    bool peerAttached[kMaxPeers]{};
+    uint32_t *arriveTrace = nullptr, *arrivePost = nullptr, *dSyncErr = nullptr;   // [kMaxPeers] each, in this GPU's memory
+    uint32_t **dPeerTraceFlags = nullptr, **dPeerPostFlags = nullptr;             // device copies of the peers' flag-array pointers
     uint32_t* gatherOwn = nullptr;     // full-frame buffer owned by this context (GPU 0 role)
     uint32_t* gatherTarget = nullptr;  // where the final kernel stores the region (may be peer memory)
 
@@ -81,6 +91,7 @@ int fail(rg_ctx* c, const char* fmt, ...) {
 
 void freeImages(rg_ctx* c) {
     cudaFree(c->base); cudaFree(c->normal); cudaFree(c->rough); cudaFree(c->final_); cudaFree(c->roughA); cudaFree(c->roughB); cudaFree(c->trans);
+    cudaFree(c->fxaaOut); c->fxaaOut = nullptr;
     cudaFree(c->rgba8); cudaFree(c->idInst); cudaFree(c->idPrim);
     c->base = c->normal = c->rough = c->final_ = c->roughA = c->roughB = nullptr; c->trans = nullptr; c->rgba8 = c->idInst = c->idPrim = nullptr;
 }
@@ -93,15 +104,40 @@ int allocImages(rg_ctx* ctx) {
     const int ry1 = ctx->iy1 + kHalo > (int)ctx->H ? (int)ctx->H : ctx->iy1 + kHalo;
     ctx->rw = rx1 - ctx->rx0; ctx->rh = ry1 - ctx->ry0;
     const size_t n = (size_t)ctx->rw * ctx->rh;
-    uint2** imgs[6] = {&ctx->base, &ctx->normal, &ctx->rough, &ctx->final_, &ctx->roughA, &ctx->roughB};
+    uint2** imgs[7] = {&ctx->base, &ctx->normal, &ctx->rough, &ctx->final_, &ctx->roughA, &ctx->roughB, &ctx->fxaaOut};
     for(auto p: imgs) { CK(cudaMalloc(p, n * sizeof(uint2))); CK(cudaMemsetAsync(*p, 0, n * sizeof(uint2), ctx->stream)); }
     CK(cudaMalloc(&ctx->trans, n)); CK(cudaMemsetAsync(ctx->trans, 0, n, ctx->stream));
     CK(cudaMalloc(&ctx->idInst, n * 4)); CK(cudaMalloc(&ctx->idPrim, n * 4));
     CK(cudaMemsetAsync(ctx->idInst, 0xff, n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->idPrim, 0xff, n * 4, ctx->stream));
     const size_t ni = (size_t)(ctx->ix1 - ctx->ix0) * (ctx->iy1 - ctx->iy0);
     CK(cudaMalloc(&ctx->rgba8, ni * 4)); CK(cudaMemsetAsync(ctx->rgba8, 0, ni * 4, ctx->stream));
-    ctx->haveFrame = false;
+    ctx->haveFrame = false; ctx->lastFxaa = false;
+    for(auto& a: ctx->peerAttached) a = false;   // peers must re-attach after a re-allocation
     return 0;
+}
+
+// Cross-GPU barrier flags: rank r publishes "frame f reached" by storing f into slot r of every peer's flag array (peer store,
+// system-scope fence first so the G-buffer / frame stores of the preceding kernel are visible), and waits on its own array.
+__global__ void k_signal(uint32_t* const* peerFlags, uint32_t nPeers, uint32_t myRank, uint32_t frame) {
+    __threadfence_system();
+    if(threadIdx.x < nPeers && peerFlags[threadIdx.x]) {
+        volatile uint32_t* f = peerFlags[threadIdx.x] + myRank;
+        *f = frame;
+    }
+    __threadfence_system();
+}
+__global__ void k_wait(const uint32_t* myFlags, uint32_t nPeers, uint32_t frame, uint32_t* err) {
+    if(threadIdx.x < nPeers) {
+        const volatile uint32_t* f = myFlags + threadIdx.x;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while((int)(*f - frame) < 0) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if(t1 - t0 > 4000000000ull) { atomicExch(err, 1u + threadIdx.x); break; }   // 4 s: a peer is gone; never hang the GPU
+        }
+    }
+    __threadfence_system();
 }
 
 // world->object from the 3x4 (binary64, explicitly rounded operations; same formula as oracle/orc_scene.cpp invert3x4)
@@ -174,15 +210,26 @@ int buildTlasFromRaw(rg_ctx* ctx, uint32_t n) {
 void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
     p.tlasNodes = c->tlasNodes; p.tlasLeaves = c->tlasLeaves; p.blasNodes = c->blasNodes; p.tris = c->tris; p.instShade = c->dInstShade;
     p.vertices = (const float4*)c->dVertices; p.indices = c->dIndices; p.materials = (const float4*)c->dMaterials; p.ubo = c->dUbo;
-    p.nInst = c->nInst; p.W = c->W; p.H = c->H; p.rx0 = (uint32_t)c->rx0; p.ry0 = (uint32_t)c->ry0; p.rw = (uint32_t)c->rw; p.rh = (uint32_t)c->rh;
-    p.base = c->base; p.normal = c->normal; p.rough = c->rough;
+    p.nInst = c->nInst; p.W = c->W; p.H = c->H;
+    p.rank = c->rank; p.world = c->world;
+    const TraceParams::Target self{c->base, c->normal, c->rough, c->rx0, c->ry0, c->rw, c->rh};
+    p.sx0 = c->rx0; p.sy0 = c->ry0; p.sw = c->rw; p.sh = c->rh;
+    if(c->world > 1) {   // partitioned: the whole frame is the domain, every rank's rectangle is a store target
+        p.dx0 = 0; p.dy0 = 0; p.dw = c->W; p.dh = c->H;
+        for(uint32_t q = 0; q < c->world; ++q) p.targets[q] = (q == c->rank) ? self : c->peers[q];
+        p.nTargets = c->world; p.self = c->rank;
+    } else {             // single GPU, or overdraw mode: trace exactly the own rectangle
+        p.dx0 = (uint32_t)c->rx0; p.dy0 = (uint32_t)c->ry0; p.dw = (uint32_t)c->rw; p.dh = (uint32_t)c->rh;
+        p.targets[0] = self; p.nTargets = 1; p.self = 0;
+    }
     p.idInst = (flags & RG_DEBUG_IDS) ? c->idInst : nullptr; p.idPrim = (flags & RG_DEBUG_IDS) ? c->idPrim : nullptr;
     p.workCounter = c->dWork; p.counters = c->dCounters; p.flags = flags;
 }
 
 void fillPostParams(rg_ctx* c, PostParams& p, uint32_t flags) {
     p.base = c->base; p.normal = c->normal; p.rough = c->rough; p.final_ = c->final_; p.roughA = c->roughA; p.roughB = c->roughB;
-    p.fxaaOut = c->base;  // fxaa.comp:35 writes baseImage; the host then swaps base <-> final (raytracer.cpp:138-140)
+    p.fxaaOut = c->fxaaOut;  // fxaa.comp:35 writes baseImage and the host swaps base <-> final (raytracer.cpp:138-140); here the FXAA
+                             // result has its own buffer and rg_read_image maps the selectors, so image pointers never move
     p.trans = c->trans; p.rgba8 = c->rgba8; p.gather = (flags & RG_NO_GATHER) ? nullptr : c->gatherTarget;
     p.W = (int)c->W; p.H = (int)c->H; p.rx0 = c->rx0; p.ry0 = c->ry0; p.rw = c->rw; p.rh = c->rh;
     p.ix0 = c->ix0; p.iy0 = c->iy0; p.ix1 = c->ix1; p.iy1 = c->iy1;
@@ -200,7 +247,7 @@ int runPost(rg_ctx* ctx, uint32_t flags) {
     launchPostprocess(pp, ctx->stream);
     launchFxaaBlit(pp, ctx->stream);
     ctx->launches += 1 + 20 + 1 + 1;
-    if(flags & RG_FXAA) { uint2* t = ctx->base; ctx->base = ctx->final_; ctx->final_ = t; }
+    ctx->lastFxaa = (flags & RG_FXAA) != 0;
     CK(cudaEventRecord(ctx->ev[EV_POST1], ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_GATHER1], ctx->stream));
     CK(cudaGetLastError());
@@ -239,6 +286,10 @@ int rg_create(rg_ctx** out, int cuda_device, uint32_t width, uint32_t height) {
     cudaMalloc(&ctx->dUbo, 192); cudaMemset(ctx->dUbo, 0, 192);
     cudaMalloc(&ctx->dWork, 4); cudaMalloc(&ctx->dCounters, 16 * 8); cudaMemset(ctx->dCounters, 0, 128);
     cudaMallocHost(&ctx->hUboPinned, sizeof(rg_ubo));
+    cudaMalloc(&ctx->arriveTrace, 4 * kMaxPeers); cudaMalloc(&ctx->arrivePost, 4 * kMaxPeers); cudaMalloc(&ctx->dSyncErr, 4);
+    cudaMemset(ctx->arriveTrace, 0, 4 * kMaxPeers); cudaMemset(ctx->arrivePost, 0, 4 * kMaxPeers); cudaMemset(ctx->dSyncErr, 0, 4);
+    cudaMalloc(&ctx->dPeerTraceFlags, sizeof(void*) * kMaxPeers); cudaMalloc(&ctx->dPeerPostFlags, sizeof(void*) * kMaxPeers);
+    cudaMemset(ctx->dPeerTraceFlags, 0, sizeof(void*) * kMaxPeers); cudaMemset(ctx->dPeerPostFlags, 0, sizeof(void*) * kMaxPeers);
     ctx->W = width; ctx->H = height; ctx->ix0 = 0; ctx->iy0 = 0; ctx->ix1 = (int)width; ctx->iy1 = (int)height;
     if(allocImages(ctx)) { fprintf(stderr, "rgb200: %s\n", ctx->err.c_str()); rg_destroy(ctx); return 6; }
     *out = ctx;
@@ -250,6 +301,8 @@ void rg_destroy(rg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     freeImages(ctx);
+    for(auto& pr: ctx->peerIpcOpened) for(void* ptr: pr) if(ptr) cudaIpcCloseMemHandle(ptr);
+    cudaFree(ctx->arriveTrace); cudaFree(ctx->arrivePost); cudaFree(ctx->dSyncErr); cudaFree(ctx->dPeerTraceFlags); cudaFree(ctx->dPeerPostFlags);
     cudaFree(ctx->gatherOwn); cudaFree(ctx->flushBuf);
     cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes);
     cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->dMeshRoots); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
@@ -441,14 +494,32 @@ int rg_render(rg_ctx* ctx, uint32_t flags) {
     if(!ctx) return 1;
     if(!ctx->haveAs) return fail(ctx, "rg_render: no acceleration structure (rg_build_blas + rg_set_instances first)");
     USE_DEVICE();
+    const bool partitioned = ctx->world > 1;
+    if(partitioned) {
+        for(uint32_t q = 0; q < ctx->world; ++q)
+            if(q != ctx->rank && !ctx->peerAttached[q]) return fail(ctx, "rg_render: partitioned mode but peer %u is not attached (rg_peer_attach)", q);
+        ctx->frameId++;
+        // nobody may still be reading last frame's G-buffer when new pixels start to land in it
+        k_wait<<<1, 32, 0, ctx->stream>>>(ctx->arrivePost, ctx->world, ctx->frameId - 1, ctx->dSyncErr);
+        ctx->launches++;
+    }
     CK(cudaMemsetAsync(ctx->dWork, 0, 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->dCounters, 0, 128, ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_RT0], ctx->stream));
     TraceParams tp; fillTraceParams(ctx, tp, flags);
     launchTrace(tp, ctx->numSms, ctx->stream);
     ctx->launches++;
+    if(partitioned) {   // every rank's share of this rectangle has landed once all ranks signalled
+        k_signal<<<1, 32, 0, ctx->stream>>>(ctx->dPeerTraceFlags, ctx->world, ctx->rank, ctx->frameId);
+        k_wait<<<1, 32, 0, ctx->stream>>>(ctx->arriveTrace, ctx->world, ctx->frameId, ctx->dSyncErr);
+        ctx->launches += 2;
+    }
     CK(cudaEventRecord(ctx->ev[EV_RTONLY1], ctx->stream));
     if(runPost(ctx, flags)) return 1;
+    if(partitioned) {
+        k_signal<<<1, 32, 0, ctx->stream>>>(ctx->dPeerPostFlags, ctx->world, ctx->rank, ctx->frameId);
+        ctx->launches++;
+    }
     ctx->haveFrame = true; ctx->lastFlags = flags;
     return 0;
 }
@@ -474,8 +545,9 @@ int rg_read_image(rg_ctx* ctx, int which, void* dst) {
     if(!ctx || !dst) return fail(ctx, "rg_read_image: null");
     USE_DEVICE();
     switch(which) {
-    case RG_IMG_FINAL: return readRegion(ctx, ctx->final_, 8, dst);
-    case RG_IMG_BASE: return readRegion(ctx, ctx->base, 8, dst);
+    // after an FXAA frame the reference has swapped the images: "final" is the FXAA output, "base" the postprocess output
+    case RG_IMG_FINAL: return readRegion(ctx, ctx->lastFxaa ? ctx->fxaaOut : ctx->final_, 8, dst);
+    case RG_IMG_BASE: return readRegion(ctx, ctx->lastFxaa ? ctx->final_ : ctx->base, 8, dst);
     case RG_IMG_NORMAL: return readRegion(ctx, ctx->normal, 8, dst);
     case RG_IMG_ROUGH: return readRegion(ctx, ctx->rough, 8, dst);
     case RG_IMG_TRANSITIONS: return readRegion(ctx, ctx->trans, 1, dst);
@@ -569,6 +641,84 @@ int rg_read_gathered_rgba8(rg_ctx* ctx, void* dst) {
     CK(cudaMemcpyAsync(dst, ctx->gatherOwn, (size_t)ctx->W * ctx->H * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+
+int rg_set_partition(rg_ctx* ctx, uint32_t rank, uint32_t world) {
+    if(!ctx) return 1;
+    if(world < 1 || world > (uint32_t)kMaxPeers || rank >= world) return fail(ctx, "rg_set_partition: rank %u of %u (max %d)", rank, world, kMaxPeers);
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->rank = rank; ctx->world = world; ctx->frameId = 0;
+    for(auto& a: ctx->peerAttached) a = false;
+    CK(cudaMemset(ctx->arriveTrace, 0, 4 * kMaxPeers)); CK(cudaMemset(ctx->arrivePost, 0, 4 * kMaxPeers)); CK(cudaMemset(ctx->dSyncErr, 0, 4));
+    // own slots: a rank also signals itself, so the flag-pointer tables contain the local arrays at [rank]
+    uint32_t* tr[kMaxPeers]{}; uint32_t* po[kMaxPeers]{};
+    tr[rank] = ctx->arriveTrace; po[rank] = ctx->arrivePost;
+    for(auto& x: ctx->peerArriveTrace) x = nullptr;
+    for(auto& x: ctx->peerArrivePost) x = nullptr;
+    ctx->peerArriveTrace[rank] = ctx->arriveTrace; ctx->peerArrivePost[rank] = ctx->arrivePost;
+    CK(cudaMemcpy(ctx->dPeerTraceFlags, tr, sizeof tr, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->dPeerPostFlags, po, sizeof po, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int rg_peer_export(rg_ctx* ctx, rg_peer_desc* out) {
+    if(!ctx || !out) return 1;
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    memset(out, 0, sizeof(*out));
+    out->base = ctx->base; out->normal = ctx->normal; out->rough = ctx->rough; out->arrive_trace = ctx->arriveTrace; out->arrive_post = ctx->arrivePost;
+    out->x0 = ctx->rx0; out->y0 = ctx->ry0; out->w = ctx->rw; out->h = ctx->rh;
+    void* ptrs[5] = {ctx->base, ctx->normal, ctx->rough, ctx->arriveTrace, ctx->arrivePost};
+    for(int k = 0; k < 5; ++k) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ptrs[k]));
+        memcpy(out->ipc[k], &h, 64);
+    }
+    return 0;
+}
+
+int rg_peer_attach(rg_ctx* ctx, uint32_t peer_rank, const rg_peer_desc* desc, int open_ipc) {
+    if(!ctx || !desc) return 1;
+    if(peer_rank >= ctx->world || peer_rank == ctx->rank) return fail(ctx, "rg_peer_attach: bad peer rank %u", peer_rank);
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    void* ptrs[5] = {desc->base, desc->normal, desc->rough, desc->arrive_trace, desc->arrive_post};
+    if(open_ipc) {
+        for(int k = 0; k < 5; ++k) {
+            if(ctx->peerIpcOpened[peer_rank][k]) { cudaIpcCloseMemHandle(ctx->peerIpcOpened[peer_rank][k]); ctx->peerIpcOpened[peer_rank][k] = nullptr; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, desc->ipc[k], 64);
+            CK(cudaIpcOpenMemHandle(&ptrs[k], h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->peerIpcOpened[peer_rank][k] = ptrs[k];
+        }
+    }
+    ctx->peers[peer_rank] = TraceParams::Target{(uint2*)ptrs[0], (uint2*)ptrs[1], (uint2*)ptrs[2], desc->x0, desc->y0, desc->w, desc->h};
+    ctx->peerArriveTrace[peer_rank] = (uint32_t*)ptrs[3]; ctx->peerArrivePost[peer_rank] = (uint32_t*)ptrs[4];
+    CK(cudaMemcpy(ctx->dPeerTraceFlags, ctx->peerArriveTrace, sizeof(void*) * kMaxPeers, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->dPeerPostFlags, ctx->peerArrivePost, sizeof(void*) * kMaxPeers, cudaMemcpyHostToDevice));
+    ctx->peerAttached[peer_rank] = true;
+    return 0;
+}
+
+int rg_peer_detach_all(rg_ctx* ctx) {
+    if(!ctx) return 1;
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    for(uint32_t q = 0; q < (uint32_t)kMaxPeers; ++q) {
+        for(int k = 0; k < 5; ++k) if(ctx->peerIpcOpened[q][k]) { cudaIpcCloseMemHandle(ctx->peerIpcOpened[q][k]); ctx->peerIpcOpened[q][k] = nullptr; }
+        ctx->peerAttached[q] = false;
+    }
+    return 0;
+}
+
+int rg_sync_error(rg_ctx* ctx) {   // non-zero if a cross-GPU wait timed out (1 + rank that never arrived)
+    if(!ctx) return -1;
+    uint32_t e = 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(&e, ctx->dSyncErr, 4, cudaMemcpyDeviceToHost);
+    return (int)e;
 }
 
 int rg_timer_begin(rg_ctx* ctx) {

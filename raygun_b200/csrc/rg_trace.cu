@@ -354,7 +354,7 @@ __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) {
 #ifndef RG_TRACE_MIN_BLOCKS
 #define RG_TRACE_MIN_BLOCKS 4
 #endif
-template <bool COUNT>
+template <bool COUNT, bool MULTI>
 __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     __shared__ float s_ubo[48];
     if(threadIdx.x < 48) s_ubo[threadIdx.x] = P.ubo[threadIdx.x];
@@ -368,8 +368,12 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
     const bool strictIeee = (P.flags & RG_STRICT_IEEE) != 0;
 
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t tilesX = (P.rw + 7) / 8, tilesY = (P.rh + 3) / 4;
-    const uint32_t total = tilesX * tilesY * 32u;
+    const uint32_t tilesX = (P.dw + 7) / 8, tilesY = (P.dh + 3) / 4;
+    const uint32_t nTiles = tilesX * tilesY;
+    // this rank's share: chunks of kChunkTiles tiles dealt round-robin (world == 1: everything)
+    const uint32_t nChunks = (nTiles + kChunkTiles - 1) / kChunkTiles;
+    const uint32_t myChunks = nChunks > P.rank ? (nChunks - P.rank + P.world - 1) / P.world : 0u;
+    const uint32_t total = myChunks * kChunkTiles * 32u;
 
     float fr[kMaxFrames][F_WORDS];
     uint32_t cnt[CNT_N];
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
 
     // per-pixel state
     bool active = false, exhausted = false;
-    uint32_t pix = 0, lx = 0, ly = 0;
+    uint32_t lx = 0, ly = 0;   // frame coordinates of the lane's pixel
     int sample = 0;
     V3 accColor = v3(0, 0, 0), accNormal = v3(0, 0, 0), accRough = v3(0, 0, 0);
     float accRoughA = 0, accContrib = 0, accDepth = 0;
@@ -397,7 +401,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
 
     auto primaryRay = [&](int i) {
         const float2 off = aaOffset(numSamples, i);
-        const float pcx = (float)(P.rx0 + lx) + 0.5f + off.x, pcy = (float)(P.ry0 + ly) + 0.5f + off.y;
+        const float pcx = (float)lx + 0.5f + off.x, pcy = (float)ly + 0.5f + off.y;
         const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
         // target = projInverse * (d.x, d.y, 1, 1); direction = viewInverse * (normalize(target.xyz), 0)
         const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
@@ -422,10 +426,11 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                 if(!active) {
                     const uint32_t w = basew + __popc(idle & ((1u << lane) - 1u));
                     if(w < total) {
-                        const uint32_t tile = w >> 5, l = w & 31u;
-                        lx = (tile % tilesX) * 8u + (l & 7u); ly = (tile / tilesX) * 4u + (l >> 3);
-                        if(lx < P.rw && ly < P.rh) {
-                            active = true; pix = ly * P.rw + lx; sample = 0;
+                        const uint32_t j = w >> 5, l = w & 31u;
+                        const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
+                        lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u); ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
+                        if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
+                            active = true; sample = 0;
                             accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
                             primaryRay(0);
                         }
@@ -443,7 +448,10 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
         cnt[rayKind]++;
         traverse<COUNT>(P, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmin, rtmax, hit, cnt);
         const bool found = hit.inst != kInvalid;
-        if(rayKind == CNT_PRIMARY && sample == 0 && P.idInst) { P.idInst[pix] = hit.inst; P.idPrim[pix] = hit.prim; }
+        if(rayKind == CNT_PRIMARY && sample == 0 && P.idInst) {
+            const int qx = (int)lx - P.sx0, qy = (int)ly - P.sy0;
+            if(qx >= 0 && qy >= 0 && qx < P.sw && qy < P.sh) { P.idInst[qy * P.sw + qx] = hit.inst; P.idPrim[qy * P.sw + qx] = hit.prim; }
+        }
 
         // ---- shade: closest hit or miss, then resume suspended frames until a new ray is issued
         bool issue = false;   // a new ray is pending
@@ -562,9 +570,20 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                 if(++sample < numSamples) { primaryRay(sample); issue = true; }
                 else {      // raygen.h:114 + raygen.rgen:35-38
                     const float inv = (float)numSamples;
-                    P.base[pix] = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
-                    P.normal[pix] = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
-                    P.rough[pix] = packHalf4(accRough.x / inv, accRough.y / inv, accRough.z / inv, accRoughA / inv);
+                    const uint2 ob = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
+                    const uint2 on = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
+                    const uint2 orr = packHalf4(accRough.x / inv, accRough.y / inv, accRough.z / inv, accRoughA / inv);
+                    // the pixel goes to every GPU whose post-chain rectangle contains it (own images or peer memory over NVLink)
+#pragma unroll
+                    for(int q = 0; q < (MULTI ? kMaxPeers : 1); ++q) {   // static indices: the targets stay in the constant bank
+                        if((uint32_t)q < P.nTargets) {
+                            const int qx = (int)lx - P.targets[q].x0, qy = (int)ly - P.targets[q].y0;
+                            if(qx >= 0 && qy >= 0 && qx < P.targets[q].w && qy < P.targets[q].h) {
+                                const size_t o = (size_t)qy * P.targets[q].w + qx;
+                                P.targets[q].base[o] = ob; P.targets[q].normal[o] = on; P.targets[q].rough[o] = orr;
+                            }
+                        }
+                    }
                     active = false;
                     break;
                 }
@@ -689,13 +708,17 @@ void launchTrace(const TraceParams& p, int numSms, cudaStream_t stream) {
     // persistent grid: a multiple of the SM count; resident CTAs per SM limited by registers / local memory
     int perSm = 0;
     if(p.flags & RG_COUNT_TRAVERSAL) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<true>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<true, true>, 128, 0);
         if(perSm < 1) perSm = 1;
-        k_trace<true><<<numSms * perSm, 128, 0, stream>>>(p);
+        k_trace<true, true><<<numSms * perSm, 128, 0, stream>>>(p);
+    } else if(p.nTargets > 1) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false, true>, 128, 0);
+        if(perSm < 1) perSm = 1;
+        k_trace<false, true><<<numSms * perSm, 128, 0, stream>>>(p);
     } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false, false>, 128, 0);
         if(perSm < 1) perSm = 1;
-        k_trace<false><<<numSms * perSm, 128, 0, stream>>>(p);
+        k_trace<false, false><<<numSms * perSm, 128, 0, stream>>>(p);
     }
 }
 

@@ -6,7 +6,9 @@ namespace rg {
 
 constexpr int kMaxRecursions = 8;   // BASELINE config 3 uses 8; the reference UI allows 0..7 (render_system.cpp:264)
 constexpr int kMaxFrames = kMaxRecursions + 1;  // a generic hit entered at recDepth >= max still gets a frame
-constexpr int kStackSize = 40;      // traversal stack entries (uint2) per ray: TLAS + BLAS
+constexpr int kStackSize = 40;
+constexpr int kMaxPeers = 8;        // GPUs of one node
+constexpr uint32_t kChunkTiles = 16; // tiles per round-robin chunk in partitioned mode      // traversal stack entries (uint2) per ray: TLAS + BLAS
 
 struct TraceParams {
     const Node8* tlasNodes;
@@ -20,9 +22,17 @@ struct TraceParams {
     const float* ubo;         // 48 words (device)
     uint32_t nInst;
     uint32_t W, H;            // full frame (launch size for ray generation)
-    uint32_t rx0, ry0, rw, rh;  // rectangle rendered by this context (region + halo, clipped), pitch = rw
-    uint2* base; uint2* normal; uint2* rough;  // rgba16f images (4 halves = uint2)
-    uint32_t* idInst; uint32_t* idPrim;        // optional primary ids (same pitch)
+    // trace domain: the pixels this launch is responsible for.  Single GPU / overdraw mode: the context's own rectangle.
+    // Partitioned mode (world > 1): the full frame, of which this rank takes every world-th chunk of kChunkTiles 8x4 tiles.
+    uint32_t dx0, dy0, dw, dh;
+    uint32_t rank, world;
+    // where a finished pixel is stored: every target whose rectangle (region + halo) contains it.  Target `self` is this
+    // context's own images; the others are peer GPUs' images, written over NVLink (peer pointers, same process or CUDA IPC).
+    struct Target { uint2* base; uint2* normal; uint2* rough; int32_t x0, y0, w, h; };
+    Target targets[kMaxPeers];
+    uint32_t nTargets, self;
+    int32_t sx0, sy0, sw, sh;   // own rectangle (for the id images)
+    uint32_t* idInst; uint32_t* idPrim;        // optional primary ids, own rectangle only
     uint32_t* workCounter;
     unsigned long long* counters;  // 5 ray kinds + nodes, tris, instances
     uint32_t flags;

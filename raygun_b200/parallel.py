@@ -47,3 +47,27 @@ def share_gather_handle(dist, rank: int, handle: bytes | None) -> bytes:
     if not isinstance(obj[0], (bytes, bytearray)) or len(obj[0]) != 64:
         raise RuntimeError("gather handle exchange failed")
     return bytes(obj[0])
+
+
+def attach_partition(dist, rt, rank: int, world: int):
+    """Partitioned mode over processes: every rank exports its G-buffer descriptor (CUDA IPC handles), all ranks gather
+    the descriptors and attach each other.  `rt` must already have its region (rt.set_region)."""
+    rt.set_partition(rank, world)
+    descs = [None] * world
+    dist.all_gather_object(descs, rt.peer_export())
+    for q in range(world):
+        if q != rank:
+            rt.peer_attach(q, descs[q], open_ipc=True)
+    dist.barrier()
+
+
+def attach_partition_in_process(rts):
+    """Same for several contexts of ONE process (tests, single-process multi-GPU hosts): raw device pointers, no IPC."""
+    world = len(rts)
+    for r, rt in enumerate(rts):
+        rt.set_partition(r, world)
+    descs = [rt.peer_export() for rt in rts]
+    for r, rt in enumerate(rts):
+        for q in range(world):
+            if q != r:
+                rt.peer_attach(q, descs[q], open_ipc=False)
