@@ -222,7 +222,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = rt.launch_count()
-    dev_ms, sections = 0.0, {"as_build_ms": 0.0, "rt_only_ms": 0.0, "rough_ms": 0.0, "postproc_ms": 0.0}
+    dev_ms, sections = 0.0, {"as_build_ms": 0.0, "rt_only_ms": 0.0, "trace_kernel_ms": 0.0, "rough_ms": 0.0, "postproc_ms": 0.0}
     rays_local = 0
     barrier()
     t_wall0 = time.perf_counter()
@@ -284,7 +284,7 @@ def main():
         peak, peak_src = load_peaks()
         px = rt.region_size[0] * rt.region_size[1]
         alg_bytes = trace_algorithmic_bytes(tmc, px)
-        trace_ms = sections["rt_only_ms"] / args.steps
+        trace_ms = sections["trace_kernel_ms"] / args.steps
         achieved = alg_bytes / (trace_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")

@@ -94,6 +94,8 @@ typedef struct rg_timings {
     float gather_ms;    /* tile gather to the target GPU (no reference counterpart) */
     uint64_t rays_primary, rays_shadow, rays_reflect, rays_refract, sky_lookups;
     uint64_t nodes_visited, tris_tested, instances_entered, generic_hits; /* only with RG_COUNT_TRAVERSAL */
+    float trace_kernel_ms; /* the trace kernel alone (rt_only_ms additionally holds the cross-GPU barrier in partitioned mode) */
+    float pad_;
 } rg_timings;
 
 /* rg_render flags */

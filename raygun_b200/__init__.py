@@ -39,7 +39,7 @@ class RgTimings(C.Structure):
                 ("postproc_ms", C.c_float), ("gather_ms", C.c_float),
                 ("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_refract", C.c_uint64),
                 ("sky_lookups", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("instances_entered", C.c_uint64),
-                ("generic_hits", C.c_uint64)]
+                ("generic_hits", C.c_uint64), ("trace_kernel_ms", C.c_float), ("pad_", C.c_float)]
 
 
 class RgPeerDesc(C.Structure):

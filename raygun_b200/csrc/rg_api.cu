@@ -27,7 +27,7 @@ struct MeshBlas {
     bool built = false;
 };
 
-enum { EV_AS0, EV_AS1, EV_RT0, EV_RTONLY1, EV_ROUGH0, EV_ROUGH1, EV_POST1, EV_GATHER1, EV_USER0, EV_USER1, EV_N };
+enum { EV_AS0, EV_AS1, EV_RT0, EV_RTONLY1, EV_ROUGH0, EV_ROUGH1, EV_POST1, EV_GATHER1, EV_USER0, EV_USER1, EV_TRACE1, EV_N };
 
 }  // namespace
 
@@ -53,6 +53,9 @@ struct rg_ctx {
     bool peerAttached[kMaxPeers]{};
     uint32_t *arriveTrace = nullptr, *arrivePost = nullptr, *dSyncErr = nullptr;   // [kMaxPeers] each, in this GPU's memory
     uint32_t **dPeerTraceFlags = nullptr, **dPeerPostFlags = nullptr;             // device copies of the peers' flag-array pointers
+    // trace scheduling state (see TraceParams): per-sample scratch + per-tile cost history
+    float4* sampleScratch = nullptr; uint32_t* sampleDone = nullptr; uint32_t* tileOrder = nullptr; uint32_t* tileCost = nullptr;
+    uint32_t schedSlots = 0, schedSamples = 0; uint64_t schedKey = 0; bool haveTileHistory = false;
     uint32_t* gatherOwn = nullptr;     // full-frame buffer owned by this context (GPU 0 role)
     uint32_t* gatherTarget = nullptr;  // where the final kernel stores the region (may be peer memory)
 
@@ -76,6 +79,7 @@ struct rg_ctx {
     uint32_t lastFlags = 0;
     void* flushBuf = nullptr;
     float lastRaysMs = 0.0f;
+    bool debugPostOnly = false, frameCostsValid = false;
 };
 
 namespace {
@@ -207,6 +211,34 @@ int buildTlasFromRaw(rg_ctx* ctx, uint32_t n) {
     return 0;
 }
 
+// (Re)allocate the scheduling buffers when the trace share or the sample count changed; returns non-zero on failure.
+int ensureSchedule(rg_ctx* ctx) {
+    const bool part = ctx->world > 1;
+    const uint32_t dw = part ? ctx->W : (uint32_t)ctx->rw, dh = part ? ctx->H : (uint32_t)ctx->rh;
+    const uint32_t slots = traceShareTiles(dw, dh, ctx->rank, ctx->world);
+    const uint32_t S = (uint32_t)ctx->hUbo.num_samples;
+    const uint64_t key = ((uint64_t)dw << 40) ^ ((uint64_t)dh << 20) ^ ((uint64_t)ctx->rank << 8) ^ ctx->world ^ ((uint64_t)ctx->rx0 << 50) ^ ((uint64_t)ctx->ry0 << 12);
+    if(slots != ctx->schedSlots || key != ctx->schedKey) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->sampleDone); cudaFree(ctx->tileOrder); cudaFree(ctx->tileCost);
+        ctx->sampleDone = ctx->tileOrder = ctx->tileCost = nullptr;
+        CK(cudaMalloc(&ctx->sampleDone, 4 * (size_t)(slots ? slots : 1) * 32));
+        CK(cudaMalloc(&ctx->tileOrder, 4 * (size_t)(slots ? slots : 1)));
+        CK(cudaMalloc(&ctx->tileCost, 4 * (size_t)(slots ? slots : 1)));
+        CK(cudaMemsetAsync(ctx->sampleDone, 0, 4 * (size_t)(slots ? slots : 1) * 32, ctx->stream));
+        CK(cudaMemsetAsync(ctx->tileCost, 0, 4 * (size_t)(slots ? slots : 1), ctx->stream));
+        ctx->schedSlots = slots; ctx->schedKey = key; ctx->haveTileHistory = false; ctx->frameCostsValid = false; ctx->schedSamples = 0;
+        cudaFree(ctx->sampleScratch); ctx->sampleScratch = nullptr;
+    }
+    if(S > 1 && S > ctx->schedSamples) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->sampleScratch); ctx->sampleScratch = nullptr;
+        CK(cudaMalloc(&ctx->sampleScratch, sizeof(float4) * 3 * (size_t)(slots ? slots : 1) * 32 * S));
+        ctx->schedSamples = S;
+    }
+    return 0;
+}
+
 void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
     p.tlasNodes = c->tlasNodes; p.tlasLeaves = c->tlasLeaves; p.blasNodes = c->blasNodes; p.tris = c->tris; p.instShade = c->dInstShade;
     p.vertices = (const float4*)c->dVertices; p.indices = c->dIndices; p.materials = (const float4*)c->dMaterials; p.ubo = c->dUbo;
@@ -224,6 +256,8 @@ void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
     }
     p.idInst = (flags & RG_DEBUG_IDS) ? c->idInst : nullptr; p.idPrim = (flags & RG_DEBUG_IDS) ? c->idPrim : nullptr;
     p.workCounter = c->dWork; p.counters = c->dCounters; p.flags = flags;
+    p.sampleScratch = c->sampleScratch; p.sampleDone = c->sampleDone;
+    p.tileOrder = c->haveTileHistory ? c->tileOrder : nullptr; p.tileCost = c->tileCost;
 }
 
 void fillPostParams(rg_ctx* c, PostParams& p, uint32_t flags) {
@@ -303,6 +337,7 @@ void rg_destroy(rg_ctx* ctx) {
     freeImages(ctx);
     for(auto& pr: ctx->peerIpcOpened) for(void* ptr: pr) if(ptr) cudaIpcCloseMemHandle(ptr);
     cudaFree(ctx->arriveTrace); cudaFree(ctx->arrivePost); cudaFree(ctx->dSyncErr); cudaFree(ctx->dPeerTraceFlags); cudaFree(ctx->dPeerPostFlags);
+    cudaFree(ctx->sampleScratch); cudaFree(ctx->sampleDone); cudaFree(ctx->tileOrder); cudaFree(ctx->tileCost);
     cudaFree(ctx->gatherOwn); cudaFree(ctx->flushBuf);
     cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes);
     cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->dMeshRoots); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
@@ -503,18 +538,27 @@ int rg_render(rg_ctx* ctx, uint32_t flags) {
         k_wait<<<1, 32, 0, ctx->stream>>>(ctx->arrivePost, ctx->world, ctx->frameId - 1, ctx->dSyncErr);
         ctx->launches++;
     }
+    if(ensureSchedule(ctx)) return 1;
     CK(cudaMemsetAsync(ctx->dWork, 0, 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->dCounters, 0, 128, ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_RT0], ctx->stream));
+    if(ctx->frameCostsValid) {   // heavy-first order from the previous frame's per-tile ray counts
+        launchOrderTiles(ctx->tileCost, ctx->schedSlots, ctx->tileOrder, ctx->stream);
+        ctx->launches++;
+        ctx->haveTileHistory = true;
+    }
     TraceParams tp; fillTraceParams(ctx, tp, flags);
     launchTrace(tp, ctx->numSms, ctx->stream);
     ctx->launches++;
+    ctx->frameCostsValid = true;
+    CK(cudaEventRecord(ctx->ev[EV_TRACE1], ctx->stream));
     if(partitioned) {   // every rank's share of this rectangle has landed once all ranks signalled
         k_signal<<<1, 32, 0, ctx->stream>>>(ctx->dPeerTraceFlags, ctx->world, ctx->rank, ctx->frameId);
         k_wait<<<1, 32, 0, ctx->stream>>>(ctx->arriveTrace, ctx->world, ctx->frameId, ctx->dSyncErr);
         ctx->launches += 2;
     }
     CK(cudaEventRecord(ctx->ev[EV_RTONLY1], ctx->stream));
+    ctx->debugPostOnly = false;
     if(runPost(ctx, flags)) return 1;
     if(partitioned) {
         k_signal<<<1, 32, 0, ctx->stream>>>(ctx->dPeerPostFlags, ctx->world, ctx->rank, ctx->frameId);
@@ -577,6 +621,7 @@ int rg_get_timings(rg_ctx* ctx, rg_timings* out) {
         cudaEventElapsedTime(&out->rough_ms, ctx->ev[EV_ROUGH0], ctx->ev[EV_ROUGH1]);
         cudaEventElapsedTime(&out->postproc_ms, ctx->ev[EV_RTONLY1], ctx->ev[EV_POST1]);
         cudaEventElapsedTime(&out->gather_ms, ctx->ev[EV_POST1], ctx->ev[EV_GATHER1]);
+        if(!ctx->debugPostOnly) cudaEventElapsedTime(&out->trace_kernel_ms, ctx->ev[EV_RT0], ctx->ev[EV_TRACE1]);
         unsigned long long c[16];
         CK(cudaMemcpy(c, ctx->dCounters, sizeof c, cudaMemcpyDeviceToHost));
         out->generic_hits = c[8];
@@ -829,6 +874,7 @@ int rg_debug_run_post(rg_ctx* ctx, uint32_t flags) {
     USE_DEVICE();
     CK(cudaEventRecord(ctx->ev[EV_RT0], ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_RTONLY1], ctx->stream));
+    ctx->debugPostOnly = true;
     if(runPost(ctx, flags)) return 1;
     ctx->haveFrame = true; ctx->lastFlags = flags;
     return 0;

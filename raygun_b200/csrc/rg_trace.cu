@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
     // this rank's share: chunks of kChunkTiles tiles dealt round-robin (world == 1: everything)
     const uint32_t nChunks = (nTiles + kChunkTiles - 1) / kChunkTiles;
     const uint32_t myChunks = nChunks > P.rank ? (nChunks - P.rank + P.world - 1) / P.world : 0u;
-    const uint32_t total = myChunks * kChunkTiles * 32u;
+    const uint32_t S = (uint32_t)numSamples;
+    const uint32_t total = myChunks * kChunkTiles * 32u * S;   // one work item per pixel SAMPLE
 
     float fr[kMaxFrames][F_WORDS];
     uint32_t cnt[CNT_N];
@@ -384,8 +385,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
     bool active = false, exhausted = false;
     uint32_t lx = 0, ly = 0;   // frame coordinates of the lane's pixel
     int sample = 0;
-    V3 accColor = v3(0, 0, 0), accNormal = v3(0, 0, 0), accRough = v3(0, 0, 0);
-    float accRoughA = 0, accContrib = 0, accDepth = 0;
+    uint32_t slot = 0, pslot = 0, sampleRays = 0;   // tile slot in this rank's share, pixel slot (slot * 32 + lane in tile), rays of this sample
     // payload (payload.h:29-39)
     V3 hv = v3(0, 0, 0), pNormal = v3(0, 0, 0), pRough = v3(0, 0, 0);
     float pRoughA = 0, pContrib = 0, depth = 0, curIOR = 1.0f, refDepth = 0;
@@ -426,13 +426,16 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                 if(!active) {
                     const uint32_t w = basew + __popc(idle & ((1u << lane) - 1u));
                     if(w < total) {
-                        const uint32_t j = w >> 5, l = w & 31u;
+                        // w = ((slot position * S) + sample) * 32 + lane: a warp works on one sample index of one 8x4 tile
+                        const uint32_t l = w & 31u, pos = (w >> 5) / S;
+                        sample = (int)((w >> 5) % S);
+                        const uint32_t j = P.tileOrder ? __ldg(P.tileOrder + pos) : pos;
+                        slot = j; pslot = j * 32u + l; sampleRays = 0;
                         const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
                         lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u); ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
                         if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
-                            active = true; sample = 0;
-                            accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
-                            primaryRay(0);
+                            active = true;
+                            primaryRay(sample);
                         }
                     }
                 }
@@ -446,6 +449,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
         // ---- trace the pending ray
         Hit hit;
         cnt[rayKind]++;
+        sampleRays++;
         traverse<COUNT>(P, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmin, rtmax, hit, cnt);
         const bool found = hit.inst != kInvalid;
         if(rayKind == CNT_PRIMARY && sample == 0 && P.idInst) {
@@ -565,10 +569,30 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
         // ---- resume suspended frames (the code after each traceRayEXT returns)
         while(!issue) {
             if(sp == 0) {   // raygen.h:105-111: the sample's trace returned
-                accColor = accColor + hv; accNormal = accNormal + pNormal; accRough = accRough + pRough; accRoughA += pRoughA;
-                accContrib += pContrib; accDepth += depth;
-                if(++sample < numSamples) { primaryRay(sample); issue = true; }
-                else {      // raygen.h:114 + raygen.rgen:35-38
+                if(P.tileCost) atomicAdd(P.tileCost + slot, sampleRays);
+                V3 accColor = hv, accNormal = pNormal, accRough = pRough;
+                float accRoughA = pRoughA, accContrib = pContrib, accDepth = depth;
+                bool last = true;
+                if(S > 1u) {   // park this sample; the lane finishing the pixel's last sample sums all of them in order
+                    float4* rec = P.sampleScratch + 3 * ((size_t)pslot * S + (uint32_t)sample);
+                    __stcg(rec, make_float4(hv.x, hv.y, hv.z, pContrib));
+                    __stcg(rec + 1, make_float4(pNormal.x, pNormal.y, pNormal.z, depth));
+                    __stcg(rec + 2, make_float4(pRough.x, pRough.y, pRough.z, pRoughA));
+                    __threadfence();
+                    last = atomicAdd(P.sampleDone + pslot, 1u) == S - 1u;
+                    if(last) {
+                        __threadfence();
+                        P.sampleDone[pslot] = 0u;   // ready for the next frame
+                        accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
+                        const float4* all = P.sampleScratch + 3 * (size_t)pslot * S;
+                        for(uint32_t i = 0; i < S; ++i) {   // raygen.h:105-111 in the loop's order
+                            const float4 a = __ldcg(all + 3 * i), b = __ldcg(all + 3 * i + 1), c = __ldcg(all + 3 * i + 2);
+                            accColor = accColor + v3(a.x, a.y, a.z); accNormal = accNormal + v3(b.x, b.y, b.z);
+                            accRough = accRough + v3(c.x, c.y, c.z); accRoughA += c.w; accContrib += a.w; accDepth += b.w;
+                        }
+                    }
+                }
+                if(last) {      // raygen.h:114 + raygen.rgen:35-38
                     const float inv = (float)numSamples;
                     const uint2 ob = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
                     const uint2 on = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
@@ -584,10 +608,9 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                             }
                         }
                     }
-                    active = false;
-                    break;
                 }
-                continue;
+                active = false;
+                break;
             }
             float* f = fr[sp - 1];
             const int flags = __float_as_int(f[F_FLAGS]);
@@ -703,6 +726,47 @@ __global__ void k_trace_rays(const TraceParams P, const float* __restrict__ rays
 }
 
 }  // namespace
+
+uint32_t traceShareTiles(uint32_t dw, uint32_t dh, uint32_t rank, uint32_t world) {
+    const uint32_t nTiles = ((dw + 7) / 8) * ((dh + 3) / 4);
+    const uint32_t nChunks = (nTiles + kChunkTiles - 1) / kChunkTiles;
+    const uint32_t myChunks = nChunks > rank ? (nChunks - rank + world - 1) / world : 0u;
+    return myChunks * kChunkTiles;
+}
+
+namespace {
+// Counting sort of the tile slots into 8 cost classes (relative to the mean), most expensive class first.
+__global__ void __launch_bounds__(1024) k_order_tiles(uint32_t* cost, uint32_t n, uint32_t* order) {
+    __shared__ unsigned long long sSum;
+    __shared__ uint32_t sCount[8], sBase[8];
+    if(threadIdx.x == 0) sSum = 0ull;
+    if(threadIdx.x < 8) sCount[threadIdx.x] = 0u;
+    __syncthreads();
+    unsigned long long local = 0;
+    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) local += cost[i];
+    atomicAdd(&sSum, local);
+    __syncthreads();
+    const float mean = fmaxf((float)sSum / (float)(n ? n : 1u), 1.0f);
+    auto classOf = [&](uint32_t c) {   // 7 = >= 8x mean ... 0 = < mean / 8
+        const float r = (float)c / mean;
+        int k = 3 + (int)floorf(log2f(fmaxf(r, 1e-6f)));
+        return k < 0 ? 0 : (k > 7 ? 7 : k);
+    };
+    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&sCount[classOf(cost[i])], 1u);
+    __syncthreads();
+    if(threadIdx.x == 0) { uint32_t run = 0; for(int k = 7; k >= 0; --k) { sBase[k] = run; run += sCount[k]; } }
+    __syncthreads();
+    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t c = cost[i];
+        order[atomicAdd(&sBase[classOf(c)], 1u)] = i;
+        cost[i] = 0u;
+    }
+}
+}  // namespace
+
+void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, cudaStream_t stream) {
+    if(nSlots) k_order_tiles<<<1, 1024, 0, stream>>>(cost, nSlots, order);
+}
 
 void launchTrace(const TraceParams& p, int numSms, cudaStream_t stream) {
     // persistent grid: a multiple of the SM count; resident CTAs per SM limited by registers / local memory

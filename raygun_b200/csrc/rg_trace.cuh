@@ -33,12 +33,23 @@ struct TraceParams {
     uint32_t nTargets, self;
     int32_t sx0, sy0, sw, sh;   // own rectangle (for the id images)
     uint32_t* idInst; uint32_t* idPrim;        // optional primary ids, own rectangle only
+    // One work item = one SAMPLE of one pixel (the heaviest pixels are glass with ~100 sequential rays per sample; splitting the
+    // numSamples samples over lanes cuts that critical path).  Samples park their result in sampleScratch (3 x float4) and the lane
+    // that finishes a pixel's last sample adds them up in the shader's order i = 0..S-1 (bit-identical to the sequential loop).
+    float4* sampleScratch; uint32_t* sampleDone;
+    // Heavy-first scheduling: tiles are handed out in the order of tileOrder (built from last frame's per-tile ray counts,
+    // most expensive first) so the long ray trees start early and overlap with the bulk; tileCost collects this frame's counts.
+    const uint32_t* tileOrder; uint32_t* tileCost;
     uint32_t* workCounter;
     unsigned long long* counters;  // 5 ray kinds + nodes, tris, instances
     uint32_t flags;
 };
 
 void launchTrace(const TraceParams& p, int numSms, cudaStream_t stream);
+// number of tile slots of this rank's share of the trace domain (sizes tileOrder / tileCost / sampleDone / sampleScratch)
+uint32_t traceShareTiles(uint32_t dw, uint32_t dh, uint32_t rank, uint32_t world);
+// order[] = tile slots sorted by descending cost class (8 classes relative to the mean); cost[] is cleared for the next frame
+void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, cudaStream_t stream);
 // debug: n rays (8 floats each) -> closest hits
 void launchTraceRays(const TraceParams& p, const float* rays8, uint32_t n, float* tuv, uint32_t* instPrim, cudaStream_t stream);
 
