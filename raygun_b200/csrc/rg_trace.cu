@@ -190,21 +190,13 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
             const bool negx = r.dx < 0.0f, negy = r.dy < 0.0f, negz = r.dz < 0.0f;
             const uint32_t octinv4 = r.octinv * 0x01010101u;
             uint32_t hitmask = 0;
-            {   // slots 0..3
-                const uint32_t lx = n2.x, ly = n2.z, lz = n3.x, hx = n3.z, hy = n4.x, hz = n4.z;
+#pragma unroll 1
+            for(int half = 0; half < 2; ++half) {   // slots 0..3, then 4..7: a rolled loop keeps the hot code small for the instruction cache
+                const uint32_t lx = half ? n2.y : n2.x, ly = half ? n2.w : n2.z, lz = half ? n3.y : n3.x;
+                const uint32_t hx = half ? n3.w : n3.z, hy = half ? n4.y : n4.x, hz = half ? n4.w : n4.z;
                 const uint32_t nx = negx ? hx : lx, fx = negx ? lx : hx, ny = negy ? hy : ly, fy = negy ? ly : hy, nz = negz ? hz : lz, fz = negz ? lz : hz;
                 uint32_t bits4, idx4;
-                decodeMeta4(n1.z, octinv4, bits4, idx4);
-                childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-                childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-                childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-                childTest<3>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-            }
-            {   // slots 4..7
-                const uint32_t lx = n2.y, ly = n2.w, lz = n3.y, hx = n3.w, hy = n4.y, hz = n4.w;
-                const uint32_t nx = negx ? hx : lx, fx = negx ? lx : hx, ny = negy ? hy : ly, fy = negy ? ly : hy, nz = negz ? hz : lz, fz = negz ? lz : hz;
-                uint32_t bits4, idx4;
-                decodeMeta4(n1.w, octinv4, bits4, idx4);
+                decodeMeta4(half ? n1.w : n1.z, octinv4, bits4, idx4);
                 childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
                 childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
                 childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
