@@ -172,7 +172,10 @@ __global__ void k_prepare_instances(const rg_instance* __restrict__ raw, uint32_
 #undef DS
 #undef DA
     t.blasRoot = in.mesh < nMeshes ? meshRoots[in.mesh] : kInvalid;
-    t.instId = i; t.pad0 = t.pad1 = 0;
+    t.instId = i;
+    // pure translation: the traversal keeps the ray direction and everything derived from it (bit-identical to the general path)
+    t.pad0 = (m[0] == 1.0f && m[1] == 0.0f && m[2] == 0.0f && m[4] == 0.0f && m[5] == 1.0f && m[6] == 0.0f && m[8] == 0.0f && m[9] == 0.0f && m[10] == 1.0f) ? 1u : 0u;
+    t.pad1 = 0;
     trav[i] = t;
     InstShade s;
     for(int j = 0; j < 12; ++j) s.o2w[j] = m[j];

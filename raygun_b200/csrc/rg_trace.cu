@@ -16,10 +16,18 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "../../include/rgb200.h"
 
+#ifndef RG_LANE_CONTEXTS
+#define RG_LANE_CONTEXTS 1
+#endif
 #ifndef RG_POSTPONE_THRESHOLD
 #define RG_POSTPONE_THRESHOLD 12
+#endif
+#ifndef RG_TRAVERSE_IFIF
+#define RG_TRAVERSE_IFIF 1
 #endif
 
 namespace rg {
@@ -164,7 +172,11 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
     const Node8* nodes = P.tlasNodes;
 
     while(true) {
+#if RG_TRAVERSE_IFIF
+        if((ng.y & 0xff000000u) && !tg.y) {   // one node per iteration, and only once this lane's pending primitives are done
+#else
         if(ng.y & 0xff000000u) {
+#endif
             const int bit = 31 - __clz(ng.y);
             ng.y &= ~(1u << bit);
             const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
@@ -204,48 +216,64 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
             }
             ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
             tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
-        } else {
+        }
+#if !RG_TRAVERSE_IFIF
+        else {
             tg = ng;
             ng = make_uint2(0u, 0u);
         }
+#endif
 
+#if RG_TRAVERSE_IFIF
+        if(tg.y) {      // ONE primitive per iteration: lanes without pending primitives go on with their next node meanwhile
+#else
         while(tg.y) {
+#endif
             const int bit = __ffs(tg.y) - 1;
             tg.y &= tg.y - 1u;
             if(!inBlas) {
                 const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + (tg.x + bit));
                 const uint4 l3 = __ldg(lp + 3);
                 if(l3.x == kInvalid) continue;  // instance of an empty mesh
-                const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
-                if(sp + 6 <= kStackSize) {
-                    if(tg.y) stack[sp++] = tg;
-                    if(ng.y & 0xff000000u) stack[sp++] = ng;
+                if(sp + 6 > kStackSize) continue;  // stack exhausted: skip (never with sane scenes)
+                if(COUNT) cnt[CNT_INST]++;
+                if(tg.y) stack[sp++] = tg;
+                if(ng.y & 0xff000000u) stack[sp++] = ng;
+                if(l3.z) {
+                    // pure translation (flagged by k_prepare_instances): the direction and everything derived from it stay; the
+                    // oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t
+                    const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+                    stack[sp++] = make_uint2(kInvalid, 0x1000u);
+                    r.ox = __fadd_rn(ox, __uint_as_float(l0.w)); r.oy = __fadd_rn(oy, __uint_as_float(l1.w)); r.oz = __fadd_rn(oz, __uint_as_float(l2.w));
+                } else {
+                    const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
                     // the world-space slab / shear constants ride on the stack while the instance is traversed
                     stack[sp++] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
                     stack[sp++] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx));
                     stack[sp++] = make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz));
                     stack[sp++] = make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8));
-                } else continue;  // stack exhausted: skip (never with sane scenes)
-                if(COUNT) cnt[CNT_INST]++;
-                // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
-                const float* w0 = reinterpret_cast<const float*>(&l0); const float* w1 = reinterpret_cast<const float*>(&l1);
-                const float* w2 = reinterpret_cast<const float*>(&l2);
-                const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0[0], ox), __fmul_rn(w0[1], oy)), __fmul_rn(w0[2], oz)), w0[3]);
-                const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1[0], ox), __fmul_rn(w1[1], oy)), __fmul_rn(w1[2], oz)), w1[3]);
-                const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2[0], ox), __fmul_rn(w2[1], oy)), __fmul_rn(w2[2], oz)), w2[3]);
-                const float odx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
-                const float ody = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
-                const float odz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
-                if(odx == 0.0f && ody == 0.0f && odz == 0.0f) { sp -= 4; if(ng.y & 0xff000000u) sp -= 1; if(tg.y) sp -= 1; continue; }
-                setupRay(r, oox, ooy, ooz, odx, ody, odz);
+                    // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
+                    const float* w0 = reinterpret_cast<const float*>(&l0); const float* w1 = reinterpret_cast<const float*>(&l1);
+                    const float* w2 = reinterpret_cast<const float*>(&l2);
+                    const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0[0], ox), __fmul_rn(w0[1], oy)), __fmul_rn(w0[2], oz)), w0[3]);
+                    const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1[0], ox), __fmul_rn(w1[1], oy)), __fmul_rn(w1[2], oz)), w1[3]);
+                    const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2[0], ox), __fmul_rn(w2[1], oy)), __fmul_rn(w2[2], oz)), w2[3]);
+                    const float odx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
+                    const float ody = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
+                    const float odz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
+                    if(odx == 0.0f && ody == 0.0f && odz == 0.0f) { sp -= 4; if(ng.y & 0xff000000u) sp -= 1; if(tg.y) sp -= 1; continue; }
+                    setupRay(r, oox, ooy, ooz, odx, ody, odz);
+                }
                 curInst = l3.y;
                 inBlas = true;
                 nodes = P.blasNodes;
                 ng = make_uint2(l3.x, 0x80000000u);
                 tg = make_uint2(0u, 0u);
+#if !RG_TRAVERSE_IFIF
                 break;
+#endif
             } else {
-#if RG_POSTPONE_THRESHOLD > 0
+#if RG_POSTPONE_THRESHOLD > 0 && !RG_TRAVERSE_IFIF
                 // too few lanes of this warp are in the triangle loop and this lane still has child nodes to visit: put the
                 // triangle group back (it goes to the stack) and test it later together with more lanes (after Ylitie et al. 2017)
                 if((ng.y & 0xff000000u) && sp < kStackSize && __popc(__activemask()) < RG_POSTPONE_THRESHOLD) {
@@ -268,23 +296,33 @@ __device__ __forceinline__ void traverse(const TraceParams& P, float ox, float o
             }
         }
 
+#if RG_TRAVERSE_IFIF
+        if(!(ng.y & 0xff000000u) && !tg.y) {
+#else
         if(!(ng.y & 0xff000000u)) {
+#endif
             bool done = false;
             while(true) {
                 if(sp == 0) { done = true; break; }
                 ng = stack[--sp];
                 if(ng.x == kInvalid) {  // leave the instance: back to the world-space ray
                     inBlas = false; nodes = P.tlasNodes;
-                    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
-                    r.octinv = ng.y & 7u; r.kx = (int)((ng.y >> 4) & 3u); r.ky = (int)((ng.y >> 6) & 3u); r.kz = (int)((ng.y >> 8) & 3u);
-                    const uint2 c2 = stack[--sp], c1 = stack[--sp], c0 = stack[--sp];
-                    r.ix = __uint_as_float(c0.x); r.iy = __uint_as_float(c0.y); r.iz = __uint_as_float(c1.x);
-                    r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
+                    r.ox = ox; r.oy = oy; r.oz = oz;
+                    if(!(ng.y & 0x1000u)) {   // a general instance: direction-derived constants come back from the stack
+                        r.dx = dx; r.dy = dy; r.dz = dz;
+                        r.octinv = ng.y & 7u; r.kx = (int)((ng.y >> 4) & 3u); r.ky = (int)((ng.y >> 6) & 3u); r.kz = (int)((ng.y >> 8) & 3u);
+                        const uint2 c2 = stack[--sp], c1 = stack[--sp], c0 = stack[--sp];
+                        r.ix = __uint_as_float(c0.x); r.iy = __uint_as_float(c0.y); r.iz = __uint_as_float(c1.x);
+                        r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
+                    }
                     continue;
                 }
                 break;
             }
             if(done) break;
+#if RG_TRAVERSE_IFIF
+            if(!(ng.y & 0xff000000u)) { tg = ng; ng = make_uint2(0u, 0u); }   // a primitive group came off the stack
+#endif
         }
     }
 }
@@ -346,7 +384,10 @@ __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) {
 #ifndef RG_TRACE_MIN_BLOCKS
 #define RG_TRACE_MIN_BLOCKS 4
 #endif
-template <bool COUNT, bool MULTI>
+// K = ray contexts per lane.  K == 1: the lane's state lives in registers.  K > 1: contexts live in local memory and every
+// lane traverses its K pending rays back to back, so a warp waits for the slowest SUM of K rays rather than for the slowest
+// single ray -- the cure for warps that idle on incoherent bounces (sphere-grid config).
+template <bool COUNT, bool MULTI, int K>
 __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     __shared__ float s_ubo[48];
     if(threadIdx.x < 48) s_ubo[threadIdx.x] = P.ubo[threadIdx.x];
@@ -368,13 +409,19 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
     const uint32_t S = (uint32_t)numSamples;
     const uint32_t total = myChunks * kChunkTiles * 32u * S;   // one work item per pixel SAMPLE
 
-    float fr[kMaxFrames][F_WORDS];
+    enum { CS_IDLE = 0, CS_RAY = 1, CS_HIT = 2 };
+    float frames[K][kMaxFrames][F_WORDS];   // suspended shader invocations, per context
+    float cRay[K][8], cPay[K][14];          // pending ray; payload (hv, depth, curIOR, refDepth, normal, rough, roughA, contrib)
+    uint32_t cHit[K][5], cPix[K][6];        // closest hit; lx, ly, slot, pslot, sampleRays, sample
+    int cSel[K], cStatus[K];                // rayType | missIndex << 2 | rayKind << 4 | recDepth << 8 | sp << 16; CS_*
+#pragma unroll
+    for(int k = 0; k < K; ++k) cStatus[k] = CS_IDLE;
     uint32_t cnt[CNT_N];
 #pragma unroll
     for(int k = 0; k < CNT_N; ++k) cnt[k] = 0;
 
     // per-pixel state
-    bool active = false, exhausted = false;
+    bool exhausted = false;
     uint32_t lx = 0, ly = 0;   // frame coordinates of the lane's pixel
     int sample = 0;
     uint32_t slot = 0, pslot = 0, sampleRays = 0;   // tile slot in this rank's share, pixel slot (slot * 32 + lane in tile), rays of this sample
@@ -406,16 +453,35 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
         depth = 0; refDepth = 0; curIOR = 1.0f; recDepth = 0; sp = 0;
     };
 
+    auto storeCtx = [&](int k) {
+        cRay[k][0] = ro.x; cRay[k][1] = ro.y; cRay[k][2] = ro.z; cRay[k][3] = rd.x; cRay[k][4] = rd.y; cRay[k][5] = rd.z; cRay[k][6] = rtmin; cRay[k][7] = rtmax;
+        cPay[k][0] = hv.x; cPay[k][1] = hv.y; cPay[k][2] = hv.z; cPay[k][3] = depth; cPay[k][4] = curIOR; cPay[k][5] = refDepth;
+        cPay[k][6] = pNormal.x; cPay[k][7] = pNormal.y; cPay[k][8] = pNormal.z; cPay[k][9] = pRough.x; cPay[k][10] = pRough.y; cPay[k][11] = pRough.z;
+        cPay[k][12] = pRoughA; cPay[k][13] = pContrib;
+        cPix[k][0] = lx; cPix[k][1] = ly; cPix[k][2] = slot; cPix[k][3] = pslot; cPix[k][4] = sampleRays; cPix[k][5] = (uint32_t)sample;
+        cSel[k] = rayType | (missIndex << 2) | (rayKind << 4) | (recDepth << 8) | (sp << 16);
+    };
+    auto loadCtx = [&](int k) {
+        ro = v3(cRay[k][0], cRay[k][1], cRay[k][2]); rd = v3(cRay[k][3], cRay[k][4], cRay[k][5]); rtmin = cRay[k][6]; rtmax = cRay[k][7];
+        hv = v3(cPay[k][0], cPay[k][1], cPay[k][2]); depth = cPay[k][3]; curIOR = cPay[k][4]; refDepth = cPay[k][5];
+        pNormal = v3(cPay[k][6], cPay[k][7], cPay[k][8]); pRough = v3(cPay[k][9], cPay[k][10], cPay[k][11]); pRoughA = cPay[k][12]; pContrib = cPay[k][13];
+        lx = cPix[k][0]; ly = cPix[k][1]; slot = cPix[k][2]; pslot = cPix[k][3]; sampleRays = cPix[k][4]; sample = (int)cPix[k][5];
+        const int sel = cSel[k];
+        rayType = sel & 3; missIndex = (sel >> 2) & 3; rayKind = (sel >> 4) & 15; recDepth = (sel >> 8) & 255; sp = (sel >> 16) & 255;
+    };
+
     while(true) {
-        // ---- refill idle lanes (warp vote + prefix compaction over one atomic)
-        uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if(idle) {
-            if(!exhausted && (idle == 0xffffffffu || __popc(idle) >= 8)) {
+        // ---- refill idle contexts (warp vote + prefix compaction over one atomic per context index)
+        bool mine = false;
+#pragma unroll 1
+        for(int k = 0; k < K; ++k) {
+            const uint32_t idle = __ballot_sync(0xffffffffu, cStatus[k] == CS_IDLE);
+            if(idle && !exhausted && (idle == 0xffffffffu || __popc(idle) >= 8)) {
                 const int n = __popc(idle), leader = __ffs(idle) - 1;
                 uint32_t basew = 0;
                 if((int)lane == leader) basew = atomicAdd(P.workCounter, (uint32_t)n);
                 basew = __shfl_sync(0xffffffffu, basew, leader);
-                if(!active) {
+                if(cStatus[k] == CS_IDLE) {
                     const uint32_t w = basew + __popc(idle & ((1u << lane) - 1u));
                     if(w < total) {
                         // w = ((slot position * S) + sample) * 32 + lane: a warp works on one sample index of one 8x4 tile
@@ -426,272 +492,291 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
                         const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
                         lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u); ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
                         if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
-                            active = true;
                             primaryRay(sample);
+                            storeCtx(k);
+                            cStatus[k] = CS_RAY;
                         }
                     }
                 }
                 if(basew + (uint32_t)n >= total) exhausted = true;
-                idle = __ballot_sync(0xffffffffu, !active);
             }
-            if(exhausted && idle == 0xffffffffu) break;
+            mine |= cStatus[k] != CS_IDLE;
         }
-        if(!active) continue;
+        if(!__any_sync(0xffffffffu, mine)) { if(exhausted) break; continue; }
 
-        // ---- trace the pending ray
-        Hit hit;
-        cnt[rayKind]++;
-        sampleRays++;
-        traverse<COUNT>(P, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmin, rtmax, hit, cnt);
-        const bool found = hit.inst != kInvalid;
-        if(rayKind == CNT_PRIMARY && sample == 0 && P.idInst) {
-            const int qx = (int)lx - P.sx0, qy = (int)ly - P.sy0;
-            if(qx >= 0 && qy >= 0 && qx < P.sw && qy < P.sh) { P.idInst[qy * P.sw + qx] = hit.inst; P.idPrim[qy * P.sw + qx] = hit.prim; }
-        }
-
-        // ---- shade: closest hit or miss, then resume suspended frames until a new ray is issued
-        bool issue = false;   // a new ray is pending
-        if(found) {
-            // closesthit.rchit:96-109
-            const uint4 is3 = __ldg(reinterpret_cast<const uint4*>(P.instShade + hit.inst) + 3);
-            const uint32_t vtxOff = is3.x, idxOff = is3.y, matOff = is3.z;
-            const uint32_t i0 = __ldg(P.indices + idxOff + 3 * hit.prim), i1 = __ldg(P.indices + idxOff + 3 * hit.prim + 1),
-                           i2 = __ldg(P.indices + idxOff + 3 * hit.prim + 2);
-            const float4 v0p = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0));
-            const float4 n0 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0) + 1), n1 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i1) + 1),
-                         n2 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i2) + 1);
-            const float4* mp = P.materials + 4 * (size_t)(matOff + __float_as_uint(v0p.w));
-            const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
-            V3 diffuse = v3(m0.x, m0.y, m0.z), specular = v3(m1.x, m1.y, m1.z);
-            const float transparency = m0.w; float reflectivity = m1.w;
-            const float roughness = m2.x, ior = m2.y, emission = m3.x;
-            const uint32_t effectId = __float_as_uint(m2.z), rayConsumption = __float_as_uint(m2.w);
-
-            const float b0 = 1.0f - hit.u - hit.v;
-            const V3 origin = ro + rd * hit.t;                                        // :114
-            const V3 vn = v3(n0.x, n0.y, n0.z) * b0 + v3(n1.x, n1.y, n1.z) * hit.u + v3(n2.x, n2.y, n2.z) * hit.v;  // :117
-            const float4* ow = reinterpret_cast<const float4*>(P.instShade + hit.inst);
-            const float4 o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2);
-            V3 n = normalize(v3(o0.x * vn.x + o0.y * vn.y + o0.z * vn.z, o1.x * vn.x + o1.y * vn.y + o1.z * vn.z, o2.x * vn.x + o2.y * vn.y + o2.z * vn.z));  // :118-119
-
-            if(effectId == 1u) {  // gridEffect, :74-91
-                const float aa = (refDepth + hit.t + 8.0f) / 30.0f;
-                const float aa2 = aa / 2.0f;
-                float minmod = glmin(fabsf(glmod((origin.x + 1000.0f) * 10.0f + aa2, 20.0f) - aa2), fabsf(glmod((origin.z + 1000.0f) * 10.0f + aa2, 20.0f) - aa2));
-                if(minmod < aa2) {
-                    minmod -= aa2 - (aa * aa) / 3.0f;
-                    minmod *= 3.0f / (aa * aa);
-                    const float f = mixf(aa / 10.0f, 1.0f, minmod);
-                    diffuse = diffuse * f; specular = specular * f; reflectivity *= f;
-                }
-                if(glmod((origin.x + 1000.0f) * 5.0f, 20.0f) < 10.0f && glmod((origin.z + 1000.0f) * 5.0f, 20.0f) < 10.0f) reflectivity *= 1.5f;
+        // ---- trace every pending ray of this lane, one after the other
+#pragma unroll 1
+        for(int k = 0; k < K; ++k) {
+            if(cStatus[k] != CS_RAY) continue;
+            Hit hit;
+            const int kind = (cSel[k] >> 4) & 15;
+            cnt[kind]++;
+            cPix[k][4]++;
+            traverse<COUNT>(P, cRay[k][0], cRay[k][1], cRay[k][2], cRay[k][3], cRay[k][4], cRay[k][5], cRay[k][6], cRay[k][7], hit, cnt);
+            cHit[k][0] = __float_as_uint(hit.t); cHit[k][1] = __float_as_uint(hit.u); cHit[k][2] = __float_as_uint(hit.v); cHit[k][3] = hit.inst; cHit[k][4] = hit.prim;
+            if(kind == CNT_PRIMARY && cPix[k][5] == 0u && P.idInst) {
+                const int qx = (int)cPix[k][0] - P.sx0, qy = (int)cPix[k][1] - P.sy0;
+                if(qx >= 0 && qy >= 0 && qx < P.sw && qy < P.sh) { P.idInst[qy * P.sw + qx] = hit.inst; P.idPrim[qy * P.sw + qx] = hit.prim; }
             }
-
-            if(rayType == RT_SHADOW_INTERNAL) {  // :125-152
-                const float thick = clampf(hit.t * (1.0f - transparency) * 10.0f, 0.0f, 1.0f);
-                const V3 nd = normalize(v3(1.1f - diffuse.x, 1.1f - diffuse.y, 1.1f - diffuse.z));
-                const V3 shadowCol = hv - mix3(v3(0, 0, 0), v3(nd.x + 0.1f, nd.y + 0.1f, nd.z + 0.1f), thick);
-                if(recDepth < maxRec) {
-                    float* f = fr[sp++];
-                    f[F_ORG] = shadowCol.x; f[F_ORG + 1] = shadowCol.y; f[F_ORG + 2] = shadowCol.z;
-                    f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
-                    f[F_N] = n.x; f[F_N + 1] = n.y; f[F_N + 2] = n.z;
-                    f[F_IOR] = ior; f[F_FLAGS] = __int_as_float(FR_SHI); f[F_RECDEPTH] = __int_as_float(recDepth);
-                    rayType = RT_SHADOW_TRACE; recDepth++;
-                    ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 0; rayKind = CNT_SHADOW;   // rd unchanged (T3)
-                    issue = true;
-                } else {
-                    hv = shadowCol * 0.4f;
-                }
-            } else if(rayType == RT_SHADOW_TRACE) {  // :153-166
-                if(transparency > 0.0f) {
-                    if(recDepth < maxRec) {   // T2: nothing to do after the child returns except recDepth--, which every
-                        rayType = RT_SHADOW_INTERNAL; recDepth++;                 // resuming frame restores from its own copy
-                        ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
-                        issue = true;
-                    }
-                } else {
-                    hv = hv * mixf(0.4f, 0.8f, clampf(logf(hit.t) / 8.0f, 0.0f, 1.0f));
-                }
-            } else {  // RT_GENERIC, :168-268
-                if(COUNT) cnt[CNT_GENHIT]++;
-                const bool frontFacing = dot(-rd, n) > 0.0f;
-                if(!frontFacing) n = normalize(-n);
-                const float ndl = dot(-L, n);
-                V3 baseColor = diffuse * glmax(ndl, 0.2f);
-                float* f = fr[sp++];
-                f[F_ORG] = origin.x; f[F_ORG + 1] = origin.y; f[F_ORG + 2] = origin.z;
-                f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
-                f[F_N] = n.x; f[F_N + 1] = n.y; f[F_N + 2] = n.z;
-                f[F_T] = hit.t;
-                f[F_DIFF] = diffuse.x; f[F_DIFF + 1] = diffuse.y; f[F_DIFF + 2] = diffuse.z;
-                f[F_SPEC] = specular.x; f[F_SPEC + 1] = specular.y; f[F_SPEC + 2] = specular.z;
-                f[F_TRANSP] = transparency; f[F_REFL] = reflectivity; f[F_ROUGH] = roughness; f[F_IOR] = ior; f[F_EMIS] = emission;
-                f[F_RECDEPTH] = __int_as_float(recDepth);
-                int stage;
-                bool shadowPending = false;
-                if(ndl > 0.07f) {   // :188
-                    if(recDepth < maxRec) {
-                        hv = v3(1.0f, 1.0f, 1.0f);
-                        rayType = RT_SHADOW_TRACE; recDepth++;
-                        ro = origin; rd = -L; rtmin = 0.1f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
-                        shadowPending = true;
-                    }
-                    // recDepth >= max: shadowColor stays 1
-                } else {
-                    const float sm = transparency * transparency;   // pow(t, 2)
-                    const V3 sc = transparency < 1.0f ? mix3(v3(1, 1, 1), diffuse * sm, transparency) : v3(0.4f, 0.4f, 0.4f);
-                    baseColor = baseColor * sc;
-                }
-                if(shadowPending) { stage = ST_SHADOW_RET; issue = true; }
-                else { baseColor = baseColor + diffuse * emission; stage = ST_TRY_REFLECT; }
-                f[F_BASE] = baseColor.x; f[F_BASE + 1] = baseColor.y; f[F_BASE + 2] = baseColor.z;
-                f[F_FLAGS] = __int_as_float(FR_GEN | (stage << 8) | ((frontFacing ? 1 : 0) << 16) | ((int)(rayConsumption & 0xffu) << 20));
-            }
-        } else {
-            if(missIndex == 0) {  // miss.rmiss:76-83
-                const V3 sky = skyColor(rd, L, strictIeee);
-                hv = sky; depth = 10000.0f;
-                if(sp == 0 && recDepth == 0) { pRough = sky; pRoughA = 0.0f; }   // roughValue is only observable for a primary miss
-            } else {              // shadowMiss.rmiss:33
-                hv = v3(1.0f, 1.0f, 1.0f);
-            }
+            cStatus[k] = CS_HIT;
         }
 
-        // ---- resume suspended frames (the code after each traceRayEXT returns)
-        while(!issue) {
-            if(sp == 0) {   // raygen.h:105-111: the sample's trace returned
-                if(P.tileCost) atomicAdd(P.tileCost + slot, sampleRays);
-                V3 accColor = hv, accNormal = pNormal, accRough = pRough;
-                float accRoughA = pRoughA, accContrib = pContrib, accDepth = depth;
-                bool last = true;
-                if(S > 1u) {   // park this sample; the lane finishing the pixel's last sample sums all of them in order
-                    float4* rec = P.sampleScratch + 3 * ((size_t)pslot * S + (uint32_t)sample);
-                    __stcg(rec, make_float4(hv.x, hv.y, hv.z, pContrib));
-                    __stcg(rec + 1, make_float4(pNormal.x, pNormal.y, pNormal.z, depth));
-                    __stcg(rec + 2, make_float4(pRough.x, pRough.y, pRough.z, pRoughA));
-                    __threadfence();
-                    last = atomicAdd(P.sampleDone + pslot, 1u) == S - 1u;
-                    if(last) {
-                        __threadfence();
-                        P.sampleDone[pslot] = 0u;   // ready for the next frame
-                        accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
-                        const float4* all = P.sampleScratch + 3 * (size_t)pslot * S;
-                        for(uint32_t i = 0; i < S; ++i) {   // raygen.h:105-111 in the loop's order
-                            const float4 a = __ldcg(all + 3 * i), b = __ldcg(all + 3 * i + 1), c = __ldcg(all + 3 * i + 2);
-                            accColor = accColor + v3(a.x, a.y, a.z); accNormal = accNormal + v3(b.x, b.y, b.z);
-                            accRough = accRough + v3(c.x, c.y, c.z); accRoughA += c.w; accContrib += a.w; accDepth += b.w;
+        // ---- shade every finished ray: context index by context index, so the lanes of the warp run the hit / miss programs together
+#pragma unroll 1
+        for(int k = 0; k < K; ++k) {
+            if(cStatus[k] != CS_HIT) continue;
+            loadCtx(k);
+            Hit hit;
+            hit.t = __uint_as_float(cHit[k][0]); hit.u = __uint_as_float(cHit[k][1]); hit.v = __uint_as_float(cHit[k][2]); hit.inst = cHit[k][3]; hit.prim = cHit[k][4];
+            const bool found = hit.inst != kInvalid;
+            float (*fr)[F_WORDS] = frames[k];
+            bool active = true;
+                // ---- shade: closest hit or miss, then resume suspended frames until a new ray is issued
+                bool issue = false;   // a new ray is pending
+                if(found) {
+                    // closesthit.rchit:96-109
+                    const uint4 is3 = __ldg(reinterpret_cast<const uint4*>(P.instShade + hit.inst) + 3);
+                    const uint32_t vtxOff = is3.x, idxOff = is3.y, matOff = is3.z;
+                    const uint32_t i0 = __ldg(P.indices + idxOff + 3 * hit.prim), i1 = __ldg(P.indices + idxOff + 3 * hit.prim + 1),
+                                   i2 = __ldg(P.indices + idxOff + 3 * hit.prim + 2);
+                    const float4 v0p = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0));
+                    const float4 n0 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0) + 1), n1 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i1) + 1),
+                                 n2 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i2) + 1);
+                    const float4* mp = P.materials + 4 * (size_t)(matOff + __float_as_uint(v0p.w));
+                    const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+                    V3 diffuse = v3(m0.x, m0.y, m0.z), specular = v3(m1.x, m1.y, m1.z);
+                    const float transparency = m0.w; float reflectivity = m1.w;
+                    const float roughness = m2.x, ior = m2.y, emission = m3.x;
+                    const uint32_t effectId = __float_as_uint(m2.z), rayConsumption = __float_as_uint(m2.w);
+
+                    const float b0 = 1.0f - hit.u - hit.v;
+                    const V3 origin = ro + rd * hit.t;                                        // :114
+                    const V3 vn = v3(n0.x, n0.y, n0.z) * b0 + v3(n1.x, n1.y, n1.z) * hit.u + v3(n2.x, n2.y, n2.z) * hit.v;  // :117
+                    const float4* ow = reinterpret_cast<const float4*>(P.instShade + hit.inst);
+                    const float4 o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2);
+                    V3 n = normalize(v3(o0.x * vn.x + o0.y * vn.y + o0.z * vn.z, o1.x * vn.x + o1.y * vn.y + o1.z * vn.z, o2.x * vn.x + o2.y * vn.y + o2.z * vn.z));  // :118-119
+
+                    if(effectId == 1u) {  // gridEffect, :74-91
+                        const float aa = (refDepth + hit.t + 8.0f) / 30.0f;
+                        const float aa2 = aa / 2.0f;
+                        float minmod = glmin(fabsf(glmod((origin.x + 1000.0f) * 10.0f + aa2, 20.0f) - aa2), fabsf(glmod((origin.z + 1000.0f) * 10.0f + aa2, 20.0f) - aa2));
+                        if(minmod < aa2) {
+                            minmod -= aa2 - (aa * aa) / 3.0f;
+                            minmod *= 3.0f / (aa * aa);
+                            const float f = mixf(aa / 10.0f, 1.0f, minmod);
+                            diffuse = diffuse * f; specular = specular * f; reflectivity *= f;
                         }
+                        if(glmod((origin.x + 1000.0f) * 5.0f, 20.0f) < 10.0f && glmod((origin.z + 1000.0f) * 5.0f, 20.0f) < 10.0f) reflectivity *= 1.5f;
+                    }
+
+                    if(rayType == RT_SHADOW_INTERNAL) {  // :125-152
+                        const float thick = clampf(hit.t * (1.0f - transparency) * 10.0f, 0.0f, 1.0f);
+                        const V3 nd = normalize(v3(1.1f - diffuse.x, 1.1f - diffuse.y, 1.1f - diffuse.z));
+                        const V3 shadowCol = hv - mix3(v3(0, 0, 0), v3(nd.x + 0.1f, nd.y + 0.1f, nd.z + 0.1f), thick);
+                        if(recDepth < maxRec) {
+                            float* f = fr[sp++];
+                            f[F_ORG] = shadowCol.x; f[F_ORG + 1] = shadowCol.y; f[F_ORG + 2] = shadowCol.z;
+                            f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
+                            f[F_N] = n.x; f[F_N + 1] = n.y; f[F_N + 2] = n.z;
+                            f[F_IOR] = ior; f[F_FLAGS] = __int_as_float(FR_SHI); f[F_RECDEPTH] = __int_as_float(recDepth);
+                            rayType = RT_SHADOW_TRACE; recDepth++;
+                            ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 0; rayKind = CNT_SHADOW;   // rd unchanged (T3)
+                            issue = true;
+                        } else {
+                            hv = shadowCol * 0.4f;
+                        }
+                    } else if(rayType == RT_SHADOW_TRACE) {  // :153-166
+                        if(transparency > 0.0f) {
+                            if(recDepth < maxRec) {   // T2: nothing to do after the child returns except recDepth--, which every
+                                rayType = RT_SHADOW_INTERNAL; recDepth++;                 // resuming frame restores from its own copy
+                                ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
+                                issue = true;
+                            }
+                        } else {
+                            hv = hv * mixf(0.4f, 0.8f, clampf(logf(hit.t) / 8.0f, 0.0f, 1.0f));
+                        }
+                    } else {  // RT_GENERIC, :168-268
+                        if(COUNT) cnt[CNT_GENHIT]++;
+                        const bool frontFacing = dot(-rd, n) > 0.0f;
+                        if(!frontFacing) n = normalize(-n);
+                        const float ndl = dot(-L, n);
+                        V3 baseColor = diffuse * glmax(ndl, 0.2f);
+                        float* f = fr[sp++];
+                        f[F_ORG] = origin.x; f[F_ORG + 1] = origin.y; f[F_ORG + 2] = origin.z;
+                        f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
+                        f[F_N] = n.x; f[F_N + 1] = n.y; f[F_N + 2] = n.z;
+                        f[F_T] = hit.t;
+                        f[F_DIFF] = diffuse.x; f[F_DIFF + 1] = diffuse.y; f[F_DIFF + 2] = diffuse.z;
+                        f[F_SPEC] = specular.x; f[F_SPEC + 1] = specular.y; f[F_SPEC + 2] = specular.z;
+                        f[F_TRANSP] = transparency; f[F_REFL] = reflectivity; f[F_ROUGH] = roughness; f[F_IOR] = ior; f[F_EMIS] = emission;
+                        f[F_RECDEPTH] = __int_as_float(recDepth);
+                        int stage;
+                        bool shadowPending = false;
+                        if(ndl > 0.07f) {   // :188
+                            if(recDepth < maxRec) {
+                                hv = v3(1.0f, 1.0f, 1.0f);
+                                rayType = RT_SHADOW_TRACE; recDepth++;
+                                ro = origin; rd = -L; rtmin = 0.1f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
+                                shadowPending = true;
+                            }
+                            // recDepth >= max: shadowColor stays 1
+                        } else {
+                            const float sm = transparency * transparency;   // pow(t, 2)
+                            const V3 sc = transparency < 1.0f ? mix3(v3(1, 1, 1), diffuse * sm, transparency) : v3(0.4f, 0.4f, 0.4f);
+                            baseColor = baseColor * sc;
+                        }
+                        if(shadowPending) { stage = ST_SHADOW_RET; issue = true; }
+                        else { baseColor = baseColor + diffuse * emission; stage = ST_TRY_REFLECT; }
+                        f[F_BASE] = baseColor.x; f[F_BASE + 1] = baseColor.y; f[F_BASE + 2] = baseColor.z;
+                        f[F_FLAGS] = __int_as_float(FR_GEN | (stage << 8) | ((frontFacing ? 1 : 0) << 16) | ((int)(rayConsumption & 0xffu) << 20));
+                    }
+                } else {
+                    if(missIndex == 0) {  // miss.rmiss:76-83
+                        const V3 sky = skyColor(rd, L, strictIeee);
+                        hv = sky; depth = 10000.0f;
+                        if(sp == 0 && recDepth == 0) { pRough = sky; pRoughA = 0.0f; }   // roughValue is only observable for a primary miss
+                    } else {              // shadowMiss.rmiss:33
+                        hv = v3(1.0f, 1.0f, 1.0f);
                     }
                 }
-                if(last) {      // raygen.h:114 + raygen.rgen:35-38
-                    const float inv = (float)numSamples;
-                    const uint2 ob = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
-                    const uint2 on = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
-                    const uint2 orr = packHalf4(accRough.x / inv, accRough.y / inv, accRough.z / inv, accRoughA / inv);
-                    // the pixel goes to every GPU whose post-chain rectangle contains it (own images or peer memory over NVLink)
-#pragma unroll
-                    for(int q = 0; q < (MULTI ? kMaxPeers : 1); ++q) {   // static indices: the targets stay in the constant bank
-                        if((uint32_t)q < P.nTargets) {
-                            const int qx = (int)lx - P.targets[q].x0, qy = (int)ly - P.targets[q].y0;
-                            if(qx >= 0 && qy >= 0 && qx < P.targets[q].w && qy < P.targets[q].h) {
-                                const size_t o = (size_t)qy * P.targets[q].w + qx;
-                                P.targets[q].base[o] = ob; P.targets[q].normal[o] = on; P.targets[q].rough[o] = orr;
+
+                // ---- resume suspended frames (the code after each traceRayEXT returns)
+                while(!issue) {
+                    if(sp == 0) {   // raygen.h:105-111: the sample's trace returned
+                        if(P.tileCost) atomicAdd(P.tileCost + slot, sampleRays);
+                        V3 accColor = hv, accNormal = pNormal, accRough = pRough;
+                        float accRoughA = pRoughA, accContrib = pContrib, accDepth = depth;
+                        bool last = true;
+                        if(S > 1u) {   // park this sample; the lane finishing the pixel's last sample sums all of them in order
+                            float4* rec = P.sampleScratch + 3 * ((size_t)pslot * S + (uint32_t)sample);
+                            __stcg(rec, make_float4(hv.x, hv.y, hv.z, pContrib));
+                            __stcg(rec + 1, make_float4(pNormal.x, pNormal.y, pNormal.z, depth));
+                            __stcg(rec + 2, make_float4(pRough.x, pRough.y, pRough.z, pRoughA));
+                            __threadfence();
+                            last = atomicAdd(P.sampleDone + pslot, 1u) == S - 1u;
+                            if(last) {
+                                __threadfence();
+                                P.sampleDone[pslot] = 0u;   // ready for the next frame
+                                accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
+                                const float4* all = P.sampleScratch + 3 * (size_t)pslot * S;
+                                for(uint32_t i = 0; i < S; ++i) {   // raygen.h:105-111 in the loop's order
+                                    const float4 a = __ldcg(all + 3 * i), b = __ldcg(all + 3 * i + 1), c = __ldcg(all + 3 * i + 2);
+                                    accColor = accColor + v3(a.x, a.y, a.z); accNormal = accNormal + v3(b.x, b.y, b.z);
+                                    accRough = accRough + v3(c.x, c.y, c.z); accRoughA += c.w; accContrib += a.w; accDepth += b.w;
+                                }
                             }
                         }
+                        if(last) {      // raygen.h:114 + raygen.rgen:35-38
+                            const float inv = (float)numSamples;
+                            const uint2 ob = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
+                            const uint2 on = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
+                            const uint2 orr = packHalf4(accRough.x / inv, accRough.y / inv, accRough.z / inv, accRoughA / inv);
+                            // the pixel goes to every GPU whose post-chain rectangle contains it (own images or peer memory over NVLink)
+        #pragma unroll
+                            for(int q = 0; q < (MULTI ? kMaxPeers : 1); ++q) {   // static indices: the targets stay in the constant bank
+                                if((uint32_t)q < P.nTargets) {
+                                    const int qx = (int)lx - P.targets[q].x0, qy = (int)ly - P.targets[q].y0;
+                                    if(qx >= 0 && qy >= 0 && qx < P.targets[q].w && qy < P.targets[q].h) {
+                                        const size_t o = (size_t)qy * P.targets[q].w + qx;
+                                        P.targets[q].base[o] = ob; P.targets[q].normal[o] = on; P.targets[q].rough[o] = orr;
+                                    }
+                                }
+                            }
+                        }
+                        active = false;
+                        break;
+                    }
+                    float* f = fr[sp - 1];
+                    const int flags = __float_as_int(f[F_FLAGS]);
+                    recDepth = __float_as_int(f[F_RECDEPTH]);   // undoes every recDepth++ / += rayConsumption below this frame
+                    if((flags & 0xff) == FR_SHI) {   // closesthit.rchit:136-146, after T3 returned
+                        V3 shadowCol = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]);
+                        if(depth < 1000.0f) {
+                            hv = hv * shadowCol;
+                        } else {
+                            const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
+                            const V3 dir = refract3(D, n, f[F_IOR]);
+                            const float dp = dot(L, dir);
+                            const float dp2 = dp * dp;
+                            shadowCol = shadowCol * (dp2 * dp2 * dp + 0.75f);   // pow(x, 5)
+                            cnt[CNT_SKY]++;   // T4: cull mask 0 -> always miss 0
+                            const V3 sky = skyColor(-dir, L, strictIeee);
+                            depth = 10000.0f;
+                            hv = shadowCol + sky * 0.1f;
+                        }
+                        sp--;
+                        continue;
+                    }
+                    int stage = (flags >> 8) & 0xff;
+                    const bool frontFacing = ((flags >> 16) & 1) != 0;
+                    const int rc = (flags >> 20) & 0xff;
+                    if(stage == ST_SHADOW_RET) {   // :196-197 then :254-255
+                        const V3 diffuse = v3(f[F_DIFF], f[F_DIFF + 1], f[F_DIFF + 2]);
+                        V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]) * hv + diffuse * f[F_EMIS];
+                        f[F_BASE] = base.x; f[F_BASE + 1] = base.y; f[F_BASE + 2] = base.z;
+                        stage = ST_TRY_REFLECT;
+                    }
+                    if(stage == ST_TRY_REFLECT) {  // :207-221
+                        if(recDepth < maxRec && f[F_REFL] > 0.0f) {
+                            const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
+                            recDepth += rc; refDepth += f[F_T];
+                            ro = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]); rd = reflect3(D, n); rtmin = 0.01f; rtmax = 1000.0f;
+                            rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFLECT;
+                            f[F_FLAGS] = __int_as_float((flags & ~0xff00) | (ST_REFLECT_RET << 8));
+                            issue = true;
+                            break;
+                        }
+                        f[F_RCOL] = 1.0f; f[F_RCOL + 1] = 1.0f; f[F_RCOL + 2] = 1.0f; f[F_RDEPTH] = 0.0f;
+                        stage = ST_TRY_REFRACT;
+                    }
+                    if(stage == ST_REFLECT_RET) {
+                        f[F_RCOL] = hv.x * f[F_SPEC]; f[F_RCOL + 1] = hv.y * f[F_SPEC + 1]; f[F_RCOL + 2] = hv.z * f[F_SPEC + 2];
+                        f[F_RDEPTH] = depth;
+                        stage = ST_TRY_REFRACT;
+                    }
+                    V3 refractColor = v3(1.0f, 1.0f, 1.0f);
+                    if(stage == ST_TRY_REFRACT) {  // :224-251
+                        if(recDepth < maxRec && f[F_TRANSP] > 0.0f) {
+                            const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
+                            const float ior = f[F_IOR];
+                            const float eta = frontFacing ? curIOR / ior : ior / 1.0f;
+                            recDepth++;
+                            curIOR = frontFacing ? ior : 1.0f;
+                            ro = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]); rd = refract3(D, n, eta); rtmin = 0.01f; rtmax = 1000.0f;
+                            rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFRACT;
+                            f[F_FLAGS] = __int_as_float((flags & ~0xff00) | ((frontFacing ? ST_REFRACT_RET_FRONT : ST_REFRACT_RET_BACK) << 8));
+                            issue = true;
+                            break;
+                        }
+                        stage = ST_COMBINE;
+                    } else if(stage == ST_REFRACT_RET_FRONT) {
+                        refractColor = hv;
+                    } else if(stage == ST_REFRACT_RET_BACK) {
+                        const V3 diffuse = v3(f[F_DIFF], f[F_DIFF + 1], f[F_DIFF + 2]);
+                        refractColor = mix3(v3(1, 1, 1), diffuse, logf(1.0f + f[F_T])) * hv;
+                    }
+                    // combine, :254-267
+                    {
+                        const V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]);
+                        const V3 reflectColor = v3(f[F_RCOL], f[F_RCOL + 1], f[F_RCOL + 2]);
+                        const float transparency = f[F_TRANSP], reflectivity = f[F_REFL], roughness = f[F_ROUGH];
+                        const float totalContrib = glmax(transparency, reflectivity);
+                        float weight = reflectivity / (transparency + reflectivity);
+                        if(!strictIeee && (transparency + reflectivity) == 0.0f) weight = 0.0f;   // SURVEY hazard 8
+                        const V3 roughCol = mix3(refractColor, reflectColor, weight);
+                        hv = mix3(base, roughCol, totalContrib);
+                        if(recDepth == 0) {
+                            hv = base;
+                            pNormal = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
+                            pRough = roughCol; pRoughA = glmin((f[F_RDEPTH] / 50.0f) * roughness, roughness / 2.1f);
+                            pContrib = totalContrib;
+                        }
+                        depth = f[F_T];
+                        sp--;
                     }
                 }
-                active = false;
-                break;
-            }
-            float* f = fr[sp - 1];
-            const int flags = __float_as_int(f[F_FLAGS]);
-            recDepth = __float_as_int(f[F_RECDEPTH]);   // undoes every recDepth++ / += rayConsumption below this frame
-            if((flags & 0xff) == FR_SHI) {   // closesthit.rchit:136-146, after T3 returned
-                V3 shadowCol = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]);
-                if(depth < 1000.0f) {
-                    hv = hv * shadowCol;
-                } else {
-                    const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                    const V3 dir = refract3(D, n, f[F_IOR]);
-                    const float dp = dot(L, dir);
-                    const float dp2 = dp * dp;
-                    shadowCol = shadowCol * (dp2 * dp2 * dp + 0.75f);   // pow(x, 5)
-                    cnt[CNT_SKY]++;   // T4: cull mask 0 -> always miss 0
-                    const V3 sky = skyColor(-dir, L, strictIeee);
-                    depth = 10000.0f;
-                    hv = shadowCol + sky * 0.1f;
-                }
-                sp--;
-                continue;
-            }
-            int stage = (flags >> 8) & 0xff;
-            const bool frontFacing = ((flags >> 16) & 1) != 0;
-            const int rc = (flags >> 20) & 0xff;
-            if(stage == ST_SHADOW_RET) {   // :196-197 then :254-255
-                const V3 diffuse = v3(f[F_DIFF], f[F_DIFF + 1], f[F_DIFF + 2]);
-                V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]) * hv + diffuse * f[F_EMIS];
-                f[F_BASE] = base.x; f[F_BASE + 1] = base.y; f[F_BASE + 2] = base.z;
-                stage = ST_TRY_REFLECT;
-            }
-            if(stage == ST_TRY_REFLECT) {  // :207-221
-                if(recDepth < maxRec && f[F_REFL] > 0.0f) {
-                    const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                    recDepth += rc; refDepth += f[F_T];
-                    ro = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]); rd = reflect3(D, n); rtmin = 0.01f; rtmax = 1000.0f;
-                    rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFLECT;
-                    f[F_FLAGS] = __int_as_float((flags & ~0xff00) | (ST_REFLECT_RET << 8));
-                    issue = true;
-                    break;
-                }
-                f[F_RCOL] = 1.0f; f[F_RCOL + 1] = 1.0f; f[F_RCOL + 2] = 1.0f; f[F_RDEPTH] = 0.0f;
-                stage = ST_TRY_REFRACT;
-            }
-            if(stage == ST_REFLECT_RET) {
-                f[F_RCOL] = hv.x * f[F_SPEC]; f[F_RCOL + 1] = hv.y * f[F_SPEC + 1]; f[F_RCOL + 2] = hv.z * f[F_SPEC + 2];
-                f[F_RDEPTH] = depth;
-                stage = ST_TRY_REFRACT;
-            }
-            V3 refractColor = v3(1.0f, 1.0f, 1.0f);
-            if(stage == ST_TRY_REFRACT) {  // :224-251
-                if(recDepth < maxRec && f[F_TRANSP] > 0.0f) {
-                    const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                    const float ior = f[F_IOR];
-                    const float eta = frontFacing ? curIOR / ior : ior / 1.0f;
-                    recDepth++;
-                    curIOR = frontFacing ? ior : 1.0f;
-                    ro = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]); rd = refract3(D, n, eta); rtmin = 0.01f; rtmax = 1000.0f;
-                    rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFRACT;
-                    f[F_FLAGS] = __int_as_float((flags & ~0xff00) | ((frontFacing ? ST_REFRACT_RET_FRONT : ST_REFRACT_RET_BACK) << 8));
-                    issue = true;
-                    break;
-                }
-                stage = ST_COMBINE;
-            } else if(stage == ST_REFRACT_RET_FRONT) {
-                refractColor = hv;
-            } else if(stage == ST_REFRACT_RET_BACK) {
-                const V3 diffuse = v3(f[F_DIFF], f[F_DIFF + 1], f[F_DIFF + 2]);
-                refractColor = mix3(v3(1, 1, 1), diffuse, logf(1.0f + f[F_T])) * hv;
-            }
-            // combine, :254-267
-            {
-                const V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]);
-                const V3 reflectColor = v3(f[F_RCOL], f[F_RCOL + 1], f[F_RCOL + 2]);
-                const float transparency = f[F_TRANSP], reflectivity = f[F_REFL], roughness = f[F_ROUGH];
-                const float totalContrib = glmax(transparency, reflectivity);
-                float weight = reflectivity / (transparency + reflectivity);
-                if(!strictIeee && (transparency + reflectivity) == 0.0f) weight = 0.0f;   // SURVEY hazard 8
-                const V3 roughCol = mix3(refractColor, reflectColor, weight);
-                hv = mix3(base, roughCol, totalContrib);
-                if(recDepth == 0) {
-                    hv = base;
-                    pNormal = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                    pRough = roughCol; pRoughA = glmin((f[F_RDEPTH] / 50.0f) * roughness, roughness / 2.1f);
-                    pContrib = totalContrib;
-                }
-                depth = f[F_T];
-                sp--;
-            }
+            storeCtx(k);
+            cStatus[k] = active ? CS_RAY : CS_IDLE;
         }
     }
 
@@ -760,22 +845,22 @@ void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, cudaStre
     if(nSlots) k_order_tiles<<<1, 1024, 0, stream>>>(cost, nSlots, order);
 }
 
-void launchTrace(const TraceParams& p, int numSms, cudaStream_t stream) {
+template <bool COUNT, bool MULTI, int K>
+static void launchTraceK(const TraceParams& p, int numSms, cudaStream_t stream) {
     // persistent grid: a multiple of the SM count; resident CTAs per SM limited by registers / local memory
     int perSm = 0;
-    if(p.flags & RG_COUNT_TRAVERSAL) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<true, true>, 128, 0);
-        if(perSm < 1) perSm = 1;
-        k_trace<true, true><<<numSms * perSm, 128, 0, stream>>>(p);
-    } else if(p.nTargets > 1) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false, true>, 128, 0);
-        if(perSm < 1) perSm = 1;
-        k_trace<false, true><<<numSms * perSm, 128, 0, stream>>>(p);
-    } else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<false, false>, 128, 0);
-        if(perSm < 1) perSm = 1;
-        k_trace<false, false><<<numSms * perSm, 128, 0, stream>>>(p);
-    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<COUNT, MULTI, K>, 128, 0);
+    if(perSm < 1) perSm = 1;
+    k_trace<COUNT, MULTI, K><<<numSms * perSm, 128, 0, stream>>>(p);
+}
+
+void launchTrace(const TraceParams& p, int numSms, cudaStream_t stream) {
+    static int contexts = [] { const char* e = getenv("RGB200_LANE_CONTEXTS"); const int v = e ? atoi(e) : RG_LANE_CONTEXTS; return v == 2 || v == 4 ? v : 1; }();
+    if(p.flags & RG_COUNT_TRAVERSAL) { launchTraceK<true, true, 1>(p, numSms, stream); return; }
+    const bool multi = p.nTargets > 1;
+    if(contexts == 4) { if(multi) launchTraceK<false, true, 4>(p, numSms, stream); else launchTraceK<false, false, 4>(p, numSms, stream); }
+    else if(contexts == 2) { if(multi) launchTraceK<false, true, 2>(p, numSms, stream); else launchTraceK<false, false, 2>(p, numSms, stream); }
+    else { if(multi) launchTraceK<false, true, 1>(p, numSms, stream); else launchTraceK<false, false, 1>(p, numSms, stream); }
 }
 
 void launchTraceRays(const TraceParams& p, const float* rays8, uint32_t n, float* tuv, uint32_t* instPrim, cudaStream_t stream) {
