@@ -382,7 +382,7 @@ __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) {
 #define RG_POSTPONE_THRESHOLD 12
 #endif
 #ifndef RG_TRACE_MIN_BLOCKS
-#define RG_TRACE_MIN_BLOCKS 4
+#define RG_TRACE_MIN_BLOCKS 8
 #endif
 // K = ray contexts per lane.  K == 1: the lane's state lives in registers.  K > 1: contexts live in local memory and every
 // lane traverses its K pending rays back to back, so a warp waits for the slowest SUM of K rays rather than for the slowest
