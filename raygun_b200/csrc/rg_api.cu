@@ -144,45 +144,6 @@ __global__ void k_wait(const uint32_t* myFlags, uint32_t nPeers, uint32_t frame,
     __threadfence_system();
 }
 
-// world->object from the 3x4 (binary64, explicitly rounded operations; same formula as oracle/orc_scene.cpp invert3x4)
-__global__ void k_prepare_instances(const rg_instance* __restrict__ raw, uint32_t n, const uint32_t* __restrict__ meshRoots, uint32_t nMeshes,
-                                    InstTrav* __restrict__ trav, InstShade* __restrict__ shade) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if(i >= n) return;
-    const rg_instance in = raw[i];
-    const float* m = in.xform;
-    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], k = m[10];
-#define DM(x, y) __dmul_rn((x), (y))
-#define DS(x, y) __dsub_rn((x), (y))
-#define DA(x, y) __dadd_rn((x), (y))
-    const double A = DS(DM(e, k), DM(f, h)), B = -DS(DM(d, k), DM(f, g)), C = DS(DM(d, h), DM(e, g));
-    const double det = DA(DA(DM(a, A), DM(b, B)), DM(c, C));
-    const double r = __ddiv_rn(1.0, det);
-    double R[9];
-    R[0] = DM(A, r); R[1] = DM(-DS(DM(b, k), DM(c, h)), r); R[2] = DM(DS(DM(b, f), DM(c, e)), r);
-    R[3] = DM(B, r); R[4] = DM(DS(DM(a, k), DM(c, g)), r); R[5] = DM(-DS(DM(a, f), DM(c, d)), r);
-    R[6] = DM(C, r); R[7] = DM(-DS(DM(a, h), DM(b, g)), r); R[8] = DM(DS(DM(a, e), DM(b, d)), r);
-    const double tx = m[3], ty = m[7], tz = m[11];
-    InstTrav t;
-    for(int rr = 0; rr < 3; ++rr) {
-        t.w2o[rr * 4 + 0] = (float)R[rr * 3 + 0]; t.w2o[rr * 4 + 1] = (float)R[rr * 3 + 1]; t.w2o[rr * 4 + 2] = (float)R[rr * 3 + 2];
-        t.w2o[rr * 4 + 3] = (float)(-DA(DA(DM(R[rr * 3 + 0], tx), DM(R[rr * 3 + 1], ty)), DM(R[rr * 3 + 2], tz)));
-    }
-#undef DM
-#undef DS
-#undef DA
-    t.blasRoot = in.mesh < nMeshes ? meshRoots[in.mesh] : kInvalid;
-    t.instId = i;
-    // pure translation: the traversal keeps the ray direction and everything derived from it (bit-identical to the general path)
-    t.pad0 = (m[0] == 1.0f && m[1] == 0.0f && m[2] == 0.0f && m[4] == 0.0f && m[5] == 1.0f && m[6] == 0.0f && m[8] == 0.0f && m[9] == 0.0f && m[10] == 1.0f) ? 1u : 0u;
-    t.pad1 = 0;
-    trav[i] = t;
-    InstShade s;
-    for(int j = 0; j < 12; ++j) s.o2w[j] = m[j];
-    s.vtxOff = in.vtx_off; s.idxOff = in.idx_off; s.matOff = in.mat_off; s.mesh = in.mesh < nMeshes ? in.mesh : 0;
-    shade[i] = s;
-}
-
 int ensureInstanceCapacity(rg_ctx* ctx, uint32_t n) {
     if(n <= ctx->instCap) return 0;
     cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
@@ -201,11 +162,9 @@ int buildTlasFromRaw(rg_ctx* ctx, uint32_t n) {
     ctx->nInst = n;
     CK(cudaEventRecord(ctx->ev[EV_AS0], ctx->stream));
     if(n) {
-        k_prepare_instances<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->dInstRaw, n, ctx->dMeshRoots, (uint32_t)ctx->meshes.size(), ctx->dInstTrav,
-                                                                      ctx->dInstShade);
-        ctx->launches++;
         const uint64_t before = ctx->tlasScratch.launches;
-        buildTlas(ctx->tlasScratch, ctx->dInstTrav, ctx->dInstShade, ctx->dMeshBoxes, n, ctx->tlasNodes, ctx->tlasLeaves, ctx->stream);
+        buildTlas(ctx->tlasScratch, ctx->dInstRaw, n, ctx->dMeshRoots, (uint32_t)ctx->meshes.size(), ctx->dInstTrav, ctx->dInstShade, ctx->dMeshBoxes,
+                  ctx->tlasNodes, ctx->tlasLeaves, ctx->stream);
         ctx->launches += ctx->tlasScratch.launches - before;
     }
     CK(cudaEventRecord(ctx->ev[EV_AS1], ctx->stream));

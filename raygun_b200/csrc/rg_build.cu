@@ -7,6 +7,8 @@
 // explicitly rounded single binary32 operation (__fadd_rn & co are never contracted into FMAs).
 #include "rg_build.cuh"
 
+#include "../../include/rgb200.h"
+
 #include <cfloat>
 #include <cstdio>
 
@@ -70,9 +72,8 @@ __global__ void k_tri_boxes(const float4* __restrict__ vertices /*2 float4 per v
 
 // Per-instance world box: the 8 corners of the mesh box mapped by the 3x4, each coordinate
 // ((m0*x + m1*y) + m2*z) + m3 in single rounded operations (oracle: orc_instance_world_box).
-__global__ void k_inst_boxes(const InstShade* __restrict__ inst, const float* __restrict__ meshBoxes, uint32_t nInst, Aabb* __restrict__ primBox,
-                             int32_t* sceneBox) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d_inst_boxes(uint32_t i, const InstShade* __restrict__ inst, const float* __restrict__ meshBoxes, uint32_t nInst,
+                                             Aabb* __restrict__ primBox, int32_t* sceneBox) {
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     const bool valid = i < nInst;
     if(valid) {
@@ -97,10 +98,13 @@ __global__ void k_inst_boxes(const InstShade* __restrict__ inst, const float* __
     }
     reduceSceneBox(lo, hi, valid, sceneBox);
 }
+__global__ void k_inst_boxes(const InstShade* __restrict__ inst, const float* __restrict__ meshBoxes, uint32_t nInst, Aabb* __restrict__ primBox,
+                             int32_t* sceneBox) {
+    d_inst_boxes(blockIdx.x * blockDim.x + threadIdx.x, inst, meshBoxes, nInst, primBox, sceneBox);
+}
 
-__global__ void k_morton(const Aabb* __restrict__ primBox, uint32_t n, const int32_t* __restrict__ sceneBox, uint32_t* __restrict__ keys,
-                         uint32_t* __restrict__ vals) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d_morton(uint32_t p, const Aabb* __restrict__ primBox, uint32_t n, const int32_t* __restrict__ sceneBox,
+                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     if(p >= n) return;
     const Aabb b = primBox[p];
     uint32_t q[3];
@@ -117,6 +121,10 @@ __global__ void k_morton(const Aabb* __restrict__ primBox, uint32_t n, const int
     }
     keys[p] = (expandBits10(q[0]) << 2) | (expandBits10(q[1]) << 1) | expandBits10(q[2]);
     vals[p] = p;
+}
+__global__ void k_morton(const Aabb* __restrict__ primBox, uint32_t n, const int32_t* __restrict__ sceneBox, uint32_t* __restrict__ keys,
+                         uint32_t* __restrict__ vals) {
+    d_morton(blockIdx.x * blockDim.x + threadIdx.x, primBox, n, sceneBox, keys, vals);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -221,9 +229,8 @@ __device__ __forceinline__ int deltaKey(const uint32_t* __restrict__ keys, int n
     return a == b ? 32 + __clz((uint32_t)i ^ (uint32_t)j) : __clz(a ^ b);
 }
 
-__global__ void k_hierarchy(const uint32_t* __restrict__ keys, uint32_t n, BNode* __restrict__ bnodes, uint2* __restrict__ range,
-                            uint32_t* __restrict__ parent, uint32_t* __restrict__ flags) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d_hierarchy(int i, const uint32_t* __restrict__ keys, uint32_t n, BNode* __restrict__ bnodes, uint2* __restrict__ range,
+                                            uint32_t* __restrict__ parent, uint32_t* __restrict__ flags) {
     const int N = (int)n;
     if(i >= N - 1) return;
     const int d = (deltaKey(keys, N, i, i + 1) - deltaKey(keys, N, i, i - 1)) >= 0 ? 1 : -1;
@@ -251,6 +258,10 @@ __global__ void k_hierarchy(const uint32_t* __restrict__ keys, uint32_t n, BNode
     if(right & kLeafBit) parent[(N - 1) + gamma + 1] = (uint32_t)i; else parent[gamma + 1] = (uint32_t)i;
     if(i == 0) parent[0] = kInvalid;
 }
+__global__ void k_hierarchy(const uint32_t* __restrict__ keys, uint32_t n, BNode* __restrict__ bnodes, uint2* __restrict__ range,
+                            uint32_t* __restrict__ parent, uint32_t* __restrict__ flags) {
+    d_hierarchy((int)(blockIdx.x * blockDim.x + threadIdx.x), keys, n, bnodes, range, parent, flags);
+}
 
 __device__ __forceinline__ void loadRefBox(uint32_t ref, const BNode* bnodes, const Aabb* primBox, const uint32_t* vals, float lo[3], float hi[3]) {
     if(ref & kLeafBit) {
@@ -263,9 +274,8 @@ __device__ __forceinline__ void loadRefBox(uint32_t ref, const BNode* bnodes, co
 }
 
 // Bottom-up refit: one thread per leaf; the second thread to arrive at a node computes its box.
-__global__ void k_refit_binary(uint32_t n, BNode* bnodes, const Aabb* __restrict__ primBox, const uint32_t* __restrict__ vals,
-                               const uint32_t* __restrict__ parent, uint32_t* flags) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void d_refit_binary(uint32_t s, uint32_t n, BNode* bnodes, const Aabb* __restrict__ primBox, const uint32_t* __restrict__ vals,
+                                               const uint32_t* __restrict__ parent, uint32_t* flags) {
     if(s >= n) return;
     uint32_t node = parent[(n - 1) + s];
     while(node != kInvalid) {
@@ -282,6 +292,10 @@ __global__ void k_refit_binary(uint32_t n, BNode* bnodes, const Aabb* __restrict
         for(int a = 0; a < 3; ++a) { vb[node].lo[a] = fminf(lo[a], lo2[a]); vb[node].hi[a] = fmaxf(hi[a], hi2[a]); }
         node = parent[node];
     }
+}
+__global__ void k_refit_binary(uint32_t n, BNode* bnodes, const Aabb* __restrict__ primBox, const uint32_t* __restrict__ vals,
+                               const uint32_t* __restrict__ parent, uint32_t* flags) {
+    d_refit_binary(blockIdx.x * blockDim.x + threadIdx.x, n, bnodes, primBox, vals, parent, flags);
 }
 
 __global__ void k_reset_flags(uint32_t* flags, uint32_t n) {
@@ -492,6 +506,109 @@ __global__ void __launch_bounds__(1024) k_collapse_all(uint2* queue0, uint2* que
     }
 }
 
+// world->object from the 3x4 (binary64, explicitly rounded operations; same formula as oracle/orc_scene.cpp invert3x4)
+__device__ __forceinline__ void d_prepare_instance(uint32_t i, const rg_instance* __restrict__ raw, uint32_t n, const uint32_t* __restrict__ meshRoots,
+                                                   uint32_t nMeshes, InstTrav* __restrict__ trav, InstShade* __restrict__ shade) {
+    if(i >= n) return;
+    const rg_instance in = raw[i];
+    const float* m = in.xform;
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], k = m[10];
+#define DM(x, y) __dmul_rn((x), (y))
+#define DS(x, y) __dsub_rn((x), (y))
+#define DA(x, y) __dadd_rn((x), (y))
+    const double A = DS(DM(e, k), DM(f, h)), B = -DS(DM(d, k), DM(f, g)), C = DS(DM(d, h), DM(e, g));
+    const double det = DA(DA(DM(a, A), DM(b, B)), DM(c, C));
+    const double r = __ddiv_rn(1.0, det);
+    double R[9];
+    R[0] = DM(A, r); R[1] = DM(-DS(DM(b, k), DM(c, h)), r); R[2] = DM(DS(DM(b, f), DM(c, e)), r);
+    R[3] = DM(B, r); R[4] = DM(DS(DM(a, k), DM(c, g)), r); R[5] = DM(-DS(DM(a, f), DM(c, d)), r);
+    R[6] = DM(C, r); R[7] = DM(-DS(DM(a, h), DM(b, g)), r); R[8] = DM(DS(DM(a, e), DM(b, d)), r);
+    const double tx = m[3], ty = m[7], tz = m[11];
+    InstTrav t;
+    for(int rr = 0; rr < 3; ++rr) {
+        t.w2o[rr * 4 + 0] = (float)R[rr * 3 + 0]; t.w2o[rr * 4 + 1] = (float)R[rr * 3 + 1]; t.w2o[rr * 4 + 2] = (float)R[rr * 3 + 2];
+        t.w2o[rr * 4 + 3] = (float)(-DA(DA(DM(R[rr * 3 + 0], tx), DM(R[rr * 3 + 1], ty)), DM(R[rr * 3 + 2], tz)));
+    }
+#undef DM
+#undef DS
+#undef DA
+    t.blasRoot = in.mesh < nMeshes ? meshRoots[in.mesh] : kInvalid;
+    t.instId = i;
+    // pure translation: the traversal keeps the ray direction and everything derived from it (bit-identical to the general path)
+    t.pad0 = (m[0] == 1.0f && m[1] == 0.0f && m[2] == 0.0f && m[4] == 0.0f && m[5] == 1.0f && m[6] == 0.0f && m[8] == 0.0f && m[9] == 0.0f && m[10] == 1.0f) ? 1u : 0u;
+    t.pad1 = 0;
+    trav[i] = t;
+    InstShade s;
+    for(int j = 0; j < 12; ++j) s.o2w[j] = m[j];
+    s.vtxOff = in.vtx_off; s.idxOff = in.idx_off; s.matOff = in.mat_off; s.mesh = in.mesh < nMeshes ? in.mesh : 0;
+    shade[i] = s;
+}
+__global__ void k_prepare_instances(const rg_instance* __restrict__ raw, uint32_t n, const uint32_t* __restrict__ meshRoots, uint32_t nMeshes,
+                                    InstTrav* __restrict__ trav, InstShade* __restrict__ shade) {
+    d_prepare_instance(blockIdx.x * blockDim.x + threadIdx.x, raw, n, meshRoots, nMeshes, trav, shade);
+}
+
+struct TlasFusedArgs {
+    const rg_instance* raw; uint32_t n; const uint32_t* meshRoots; uint32_t nMeshes; InstTrav* trav; InstShade* shade; const float* meshBoxes;
+    Aabb* primBox; int32_t* sceneBox; uint32_t* keys0; uint32_t* vals0; uint32_t* keys1; uint32_t* vals1;
+    BNode* bnodes; uint2* range; uint32_t* parent; uint32_t* flags; uint2* queue0; uint2* queue1; uint32_t* counters; uint32_t* wideRef;
+    Node8* tlasNodes; InstTrav* tlasLeaves;
+};
+
+// The whole per-frame TLAS build in ONE block for small scenes (n <= kTlasFusedMax): instance preparation, world boxes, Morton keys,
+// a stable rank sort (identical order to the radix sort), Karras hierarchy, bottom-up refit and every collapse level.
+// One launch instead of ~20: the per-frame acceleration-structure cost drops to the latency of one small kernel.
+__global__ void __launch_bounds__(1024) k_tlas_fused(const TlasFusedArgs A) {
+    __shared__ uint32_t sCount;
+    const uint32_t n = A.n, tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t nUp = (n + 31u) & ~31u;
+    if(tid < 3) A.sceneBox[tid] = 0x7fffffff; else if(tid < 6) A.sceneBox[tid] = (int)0x80000000;
+    for(uint32_t i = tid; i < n; i += nt) d_prepare_instance(i, A.raw, n, A.meshRoots, A.nMeshes, A.trav, A.shade);
+    __syncthreads();
+    for(uint32_t i = tid; i < nUp; i += nt) d_inst_boxes(i, A.shade, A.meshBoxes, n, A.primBox, A.sceneBox);   // whole warps: shuffles inside
+    __syncthreads();
+    for(uint32_t i = tid; i < n; i += nt) d_morton(i, A.primBox, n, A.sceneBox, A.keys0, A.vals0);
+    __syncthreads();
+    for(uint32_t i = tid; i < n; i += nt) {   // rank sort by (key, index): the order of a stable sort
+        const uint32_t ki = A.keys0[i];
+        uint32_t rank = 0;
+        for(uint32_t j = 0; j < n; ++j) { const uint32_t kj = A.keys0[j]; rank += (kj < ki || (kj == ki && j < i)) ? 1u : 0u; }
+        A.keys1[rank] = ki; A.vals1[rank] = i;
+    }
+    __syncthreads();
+    if(n >= 2) {
+        for(uint32_t i = tid; i + 1 < n; i += nt) d_hierarchy((int)i, A.keys1, n, A.bnodes, A.range, A.parent, A.flags);
+        __syncthreads();
+        for(uint32_t i = tid; i < n; i += nt) d_refit_binary(i, n, A.bnodes, A.primBox, A.vals1, A.parent, A.flags);
+        __threadfence();
+        __syncthreads();
+    }
+    // collapse, level by level (as k_collapse_all)
+    if(tid == 0) {
+        A.queue0[0] = make_uint2(n >= 2 ? 0u : kLeafBit, 0u);
+        A.counters[0] = 1; A.counters[1] = 0; A.counters[2] = 1; A.counters[3] = 0;
+    }
+    __syncthreads();
+    const LeafSourceInst ls{A.trav, A.tlasLeaves};
+    int in = 0;
+    while(true) {
+        if(tid == 0) sCount = A.counters[in];
+        __syncthreads();
+        const uint32_t count = sCount;
+        if(count == 0) break;
+        uint2* qIn = in ? A.queue1 : A.queue0;
+        uint2* qOut = in ? A.queue0 : A.queue1;
+        for(uint32_t item = tid; item < count; item += nt)
+            collapseItem<LeafSourceInst>(qIn[item], qOut, &A.counters[in ^ 1], &A.counters[2], &A.counters[3], A.bnodes, A.range, A.primBox, A.vals1, A.tlasNodes,
+                                         0, 0, ls, A.wideRef);
+        __threadfence_block();
+        __syncthreads();
+        if(tid == 0) A.counters[in] = 0;
+        in ^= 1;
+        __syncthreads();
+    }
+}
+
 __global__ void k_collapse_seed(uint2* queue, uint32_t* counters, uint32_t n) {
     // root item: binary node 0 (or the single leaf) -> wide node 0
     queue[0] = make_uint2(n >= 2 ? 0u : kLeafBit, 0u);
@@ -659,15 +776,23 @@ void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t 
     s.launches += 2;
 }
 
-void buildTlas(LbvhScratch& s, const InstTrav* instTrav, const InstShade* instShade, const float* meshBoxes, uint32_t nInst, Node8* tlasNodes,
-               InstTrav* tlasLeavesOut, cudaStream_t st) {
+void buildTlas(LbvhScratch& s, const rg_instance* raw, uint32_t nInst, const uint32_t* meshRoots, uint32_t nMeshes, InstTrav* instTrav,
+               InstShade* instShade, const float* meshBoxes, Node8* tlasNodes, InstTrav* tlasLeavesOut, cudaStream_t st) {
     const uint32_t n = nInst;
     s.reserve(n ? n : 1);
+    if(n == 0) { k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters); s.launches++; return; }
+    if(n <= kTlasFusedMax) {   // one launch for the whole build
+        TlasFusedArgs a{raw, n, meshRoots, nMeshes, instTrav, instShade, meshBoxes, s.primBox, s.sceneBox, s.keys[0], s.vals[0], s.keys[1], s.vals[1],
+                        s.bnodes, s.range, s.parent, s.flags, s.queue[0], s.queue[1], s.counters, s.wideRef, tlasNodes, tlasLeavesOut};
+        k_tlas_fused<<<1, n <= 32 ? 64 : (n <= 256 ? 256 : 1024), 0, st>>>(a);
+        s.launches++;
+        s.sortedBuf = 1;
+        return;
+    }
+    k_prepare_instances<<<cdiv(n, 128), 128, 0, st>>>(raw, n, meshRoots, nMeshes, instTrav, instShade);
     k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters);
-    s.launches++;
-    if(n == 0) return;
     k_inst_boxes<<<cdiv(n, 128), 128, 0, st>>>(instShade, meshBoxes, n, s.primBox, s.sceneBox);
-    s.launches++;
+    s.launches += 3;
     lbvhCommon(s, n, st);
     LeafSourceInst ls{instTrav, tlasLeavesOut};
     if(n <= kTlasSingleBlockMax) {   // fully asynchronous: every level inside one block

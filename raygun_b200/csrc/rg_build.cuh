@@ -4,6 +4,8 @@
 #pragma once
 #include "rg_types.cuh"
 
+struct rg_instance;
+
 namespace rg {
 
 // Scratch + result of one LBVH build over n primitives (triangles of a mesh, or instances).
@@ -27,6 +29,7 @@ struct LbvhScratch {
     void release();
 };
 
+constexpr uint32_t kTlasFusedMax = 1024;             // instances: the whole TLAS build in one block / one launch
 constexpr uint32_t kTlasSingleBlockMax = 1u << 17;   // instances; above this the level loop goes back to the host
 
 struct TriSource { const void* vertices; const uint32_t* indices; uint32_t vtxOff, idxOff, nTri; };
@@ -41,10 +44,10 @@ void buildBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t 
 void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t nodeOffset, uint32_t nNodes, Tri* trisBase, uint32_t triOffset,
                float* rootBoxOut, cudaStream_t stream);
 
-// Per-frame TLAS: world boxes from meshBoxes (device, 6 floats per mesh) and the instance transforms, LBVH, collapse.
-// instTrav is indexed by instance id; tlasLeavesOut receives the InstTrav records in leaf order.
-// nNodesOut (device u32) receives the node count.  Fully asynchronous for n <= kTlasSingleBlockMax.
-void buildTlas(LbvhScratch& s, const InstTrav* instTrav, const InstShade* instShade, const float* meshBoxes, uint32_t nInst, Node8* tlasNodes,
-               InstTrav* tlasLeavesOut, cudaStream_t stream);
+// Per-frame TLAS from the raw instance records: instance preparation (world->object, offset table), world boxes from
+// meshBoxes (device, 6 floats per mesh), LBVH, collapse.  instTrav / instShade are indexed by instance id; tlasLeavesOut
+// receives the InstTrav records in leaf order.  One launch for n <= kTlasFusedMax; fully asynchronous for n <= kTlasSingleBlockMax.
+void buildTlas(LbvhScratch& s, const rg_instance* raw, uint32_t nInst, const uint32_t* meshRoots, uint32_t nMeshes, InstTrav* instTrav,
+               InstShade* instShade, const float* meshBoxes, Node8* tlasNodes, InstTrav* tlasLeavesOut, cudaStream_t stream);
 
 }  // namespace rg
