@@ -95,7 +95,7 @@ typedef struct rg_timings {
     uint64_t rays_primary, rays_shadow, rays_reflect, rays_refract, sky_lookups;
     uint64_t nodes_visited, tris_tested, instances_entered, generic_hits; /* only with RG_COUNT_TRAVERSAL */
     float trace_kernel_ms; /* the trace kernel alone (rt_only_ms additionally holds the cross-GPU barrier in partitioned mode) */
-    float pad_;
+    uint32_t trace_scheduler; /* RG_SCHED_LANES or RG_SCHED_POOL: the trace kernel the last frame used */
 } rg_timings;
 
 /* rg_render flags */
@@ -145,6 +145,15 @@ int rg_set_ubo(rg_ctx* ctx, const rg_ubo* ubo);
 /* Raytracer::doRaytracing (raytracer.cpp:87-147) + the blit to the 8-bit target (render_system.cpp:130-144). */
 int rg_render(rg_ctx* ctx, uint32_t flags);
 int rg_sync(rg_ctx* ctx);
+
+/* Scheduler of the trace kernel (no reference counterpart: traceRaysKHR leaves scheduling to the driver).  LANES: one pixel sample
+ * per lane, fastest on coherent scenes.  POOL: per-warp context pools with shared-memory ray / hit queues, fastest on incoherent
+ * bounces.  AUTO (default): times both on consecutive frames, keeps the faster, re-checks every 64 frames.  Images are
+ * bit-identical either way. */
+#define RG_SCHED_LANES 0
+#define RG_SCHED_POOL 1
+#define RG_SCHED_AUTO 2
+int rg_set_trace_scheduler(rg_ctx* ctx, int mode);
 
 /* Read-back.  dst is tightly packed width x height (full frame when no region is set, else the region).
  * rg_read_rgba8: 4 bytes / pixel.  rg_read_image: 8 bytes / pixel (4 x binary16), 1 byte for RG_IMG_TRANSITIONS. */

@@ -22,6 +22,7 @@ LIB_PATH = os.environ.get("RGB200_LIB") or os.path.join(_HERE, "librgb200.so")  
 
 # rg_render flags (include/rgb200.h)
 RG_FXAA, RG_SRGB8, RG_STRICT_IEEE, RG_DEBUG_IDS, RG_COUNT_TRAVERSAL, RG_NO_GATHER = 1, 2, 4, 8, 16, 32
+RG_SCHED_LANES, RG_SCHED_POOL, RG_SCHED_AUTO = 0, 1, 2
 IMG_FINAL, IMG_BASE, IMG_NORMAL, IMG_ROUGH, IMG_TRANSITIONS, IMG_ROUGH_A, IMG_ROUGH_B = range(7)
 
 ABI_SYMBOLS = (
@@ -30,7 +31,7 @@ ABI_SYMBOLS = (
     "rg_set_instances_device", "rg_set_ubo_device", "rg_framebuffer_device_ptr", "rg_set_gather_target", "rg_gather_buffer_export",
     "rg_gather_buffer_open", "rg_gather_buffer_close", "rg_read_gathered_rgba8", "rg_debug_blas_sort", "rg_debug_tlas_sort", "rg_debug_trace_rays",
     "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2", "rg_debug_last_trace_rays_ms",
-    "rg_set_partition", "rg_peer_export", "rg_peer_attach", "rg_peer_detach_all", "rg_sync_error",
+    "rg_set_trace_scheduler", "rg_set_partition", "rg_peer_export", "rg_peer_attach", "rg_peer_detach_all", "rg_sync_error",
 )
 
 
@@ -39,7 +40,7 @@ class RgTimings(C.Structure):
                 ("postproc_ms", C.c_float), ("gather_ms", C.c_float),
                 ("rays_primary", C.c_uint64), ("rays_shadow", C.c_uint64), ("rays_reflect", C.c_uint64), ("rays_refract", C.c_uint64),
                 ("sky_lookups", C.c_uint64), ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("instances_entered", C.c_uint64),
-                ("generic_hits", C.c_uint64), ("trace_kernel_ms", C.c_float), ("pad_", C.c_float)]
+                ("generic_hits", C.c_uint64), ("trace_kernel_ms", C.c_float), ("trace_scheduler", C.c_uint32)]
 
 
 class RgPeerDesc(C.Structure):
@@ -157,6 +158,10 @@ class Raytracer:
 
     def doRaytracing(self, flags=RG_FXAA):
         self._ck(self.lib.rg_render(self.h, C.c_uint32(flags)))
+
+    def set_trace_scheduler(self, mode: int):
+        """RG_SCHED_LANES / RG_SCHED_POOL / RG_SCHED_AUTO (default): which trace kernel runs; images are bit-identical."""
+        self._ck(self.lib.rg_set_trace_scheduler(self.h, int(mode)))
 
     def sync(self):
         self._ck(self.lib.rg_sync(self.h))

@@ -2,6 +2,7 @@
 // Mirrors raygun::render::Raytracer (raygun/render/raytracer.{hpp,cpp}) for the one path this library replaces.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -27,7 +28,7 @@ struct MeshBlas {
     bool built = false;
 };
 
-enum { EV_AS0, EV_AS1, EV_RT0, EV_RTONLY1, EV_ROUGH0, EV_ROUGH1, EV_POST1, EV_GATHER1, EV_USER0, EV_USER1, EV_TRACE1, EV_N };
+enum { EV_AS0, EV_AS1, EV_RT0, EV_RTONLY1, EV_ROUGH0, EV_ROUGH1, EV_POST1, EV_GATHER1, EV_USER0, EV_USER1, EV_TRACE1, EV_PROBE0, EV_PROBE1, EV_N };
 
 }  // namespace
 
@@ -73,7 +74,12 @@ struct rg_ctx {
     rg_instance* hInstPinned = nullptr; uint32_t hInstCap = 0;
 
     float* dUbo = nullptr; rg_ubo hUbo{}; rg_ubo* hUboPinned = nullptr; bool uboOnDevice = false;
-    uint32_t* dWork = nullptr; unsigned long long* dCounters = nullptr;
+    uint32_t* dWork = nullptr; unsigned long long* dCounters = nullptr; float4* ctxPool = nullptr;
+    // trace scheduler (rg_trace.cu: k_trace_lanes / k_trace_pool).  RG_SCHED_AUTO times both on consecutive frames and keeps the
+    // faster one; the comparison is repeated every kSchedReprobe frames so a changing scene can change the choice.
+    int schedMode = RG_SCHED_AUTO, schedChosen = RG_SCHED_LANES, schedProbe = -1, schedLast = RG_SCHED_LANES;
+    float schedMs[2] = {-1.0f, -1.0f};
+    uint32_t schedFrames = 0;
     cudaEvent_t ev[EV_N]{};
     bool haveFrame = false, haveAs = false, blasBuilt = false;
     uint32_t lastFlags = 0;
@@ -201,6 +207,30 @@ int ensureSchedule(rg_ctx* ctx) {
     return 0;
 }
 
+constexpr uint32_t kSchedReprobe = 64;
+
+// Which trace kernel runs this frame.  AUTO: once the heavy-first tile order exists (second frame on), one frame is timed with
+// each scheduler (CUDA events around the kernel; the host waits for that one frame's kernel when it needs the number) and the
+// faster one is kept for the next kSchedReprobe frames.  Both produce bit-identical images, so switching is invisible.
+bool chooseScheduler(rg_ctx* c) {
+    if(c->schedMode != RG_SCHED_AUTO) { c->schedProbe = -1; c->schedLast = c->schedMode; return c->schedMode == RG_SCHED_POOL; }
+    if(c->schedProbe >= 0) {   // harvest the probe frame
+        float ms = -1.0f;
+        if(cudaEventSynchronize(c->ev[EV_PROBE1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev[EV_PROBE0], c->ev[EV_PROBE1]) == cudaSuccess) c->schedMs[c->schedProbe] = ms;
+        else c->schedMs[c->schedProbe] = 1e30f;
+        c->schedProbe = -1;
+        if(c->schedMs[0] >= 0.0f && c->schedMs[1] >= 0.0f) { c->schedChosen = c->schedMs[1] < c->schedMs[0] ? RG_SCHED_POOL : RG_SCHED_LANES; c->schedFrames = 0; }
+    }
+    int mode = c->schedChosen;
+    if(c->haveTileHistory) {
+        if(c->schedMs[0] < 0.0f) mode = c->schedProbe = RG_SCHED_LANES;
+        else if(c->schedMs[1] < 0.0f) mode = c->schedProbe = RG_SCHED_POOL;
+        else if(++c->schedFrames >= kSchedReprobe) { c->schedMs[0] = c->schedMs[1] = -1.0f; mode = c->schedProbe = RG_SCHED_LANES; }
+    }
+    c->schedLast = mode;
+    return mode == RG_SCHED_POOL;
+}
+
 void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
     p.tlasNodes = c->tlasNodes; p.tlasLeaves = c->tlasLeaves; p.blasNodes = c->blasNodes; p.tris = c->tris; p.instShade = c->dInstShade;
     p.vertices = (const float4*)c->dVertices; p.indices = c->dIndices; p.materials = (const float4*)c->dMaterials; p.ubo = c->dUbo;
@@ -217,7 +247,7 @@ void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
         p.targets[0] = self; p.nTargets = 1; p.self = 0;
     }
     p.idInst = (flags & RG_DEBUG_IDS) ? c->idInst : nullptr; p.idPrim = (flags & RG_DEBUG_IDS) ? c->idPrim : nullptr;
-    p.workCounter = c->dWork; p.counters = c->dCounters; p.flags = flags;
+    p.workCounter = c->dWork; p.counters = c->dCounters; p.flags = flags; p.ctxPool = c->ctxPool;
     p.sampleScratch = c->sampleScratch; p.sampleDone = c->sampleDone;
     p.tileOrder = c->haveTileHistory ? c->tileOrder : nullptr; p.tileCost = c->tileCost;
 }
@@ -281,6 +311,9 @@ int rg_create(rg_ctx** out, int cuda_device, uint32_t width, uint32_t height) {
     for(auto& e: ctx->ev) cudaEventCreate(&e);
     cudaMalloc(&ctx->dUbo, 192); cudaMemset(ctx->dUbo, 0, 192);
     cudaMalloc(&ctx->dWork, 4); cudaMalloc(&ctx->dCounters, 16 * 8); cudaMemset(ctx->dCounters, 0, 128);
+    cudaMalloc(&ctx->ctxPool, tracePoolBytes(ctx->numSms));
+    if(const char* e = getenv("RGB200_TRACE_SCHED"))   // developer override for A/B timing: lanes | pool | auto
+        ctx->schedMode = !strcmp(e, "lanes") ? RG_SCHED_LANES : (!strcmp(e, "pool") ? RG_SCHED_POOL : RG_SCHED_AUTO);
     cudaMallocHost(&ctx->hUboPinned, sizeof(rg_ubo));
     cudaMalloc(&ctx->arriveTrace, 4 * kMaxPeers); cudaMalloc(&ctx->arrivePost, 4 * kMaxPeers); cudaMalloc(&ctx->dSyncErr, 4);
     cudaMemset(ctx->arriveTrace, 0, 4 * kMaxPeers); cudaMemset(ctx->arrivePost, 0, 4 * kMaxPeers); cudaMemset(ctx->dSyncErr, 0, 4);
@@ -303,7 +336,7 @@ void rg_destroy(rg_ctx* ctx) {
     cudaFree(ctx->gatherOwn); cudaFree(ctx->flushBuf);
     cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes);
     cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->dMeshRoots); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
-    cudaFree(ctx->dUbo); cudaFree(ctx->dWork); cudaFree(ctx->dCounters);
+    cudaFree(ctx->dUbo); cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->ctxPool);
     cudaFreeHost(ctx->hInstPinned); cudaFreeHost(ctx->hUboPinned);
     for(auto& m: ctx->meshes) m.scratch.release();
     ctx->tlasScratch.release();
@@ -510,7 +543,10 @@ int rg_render(rg_ctx* ctx, uint32_t flags) {
         ctx->haveTileHistory = true;
     }
     TraceParams tp; fillTraceParams(ctx, tp, flags);
-    launchTrace(tp, ctx->numSms, ctx->stream);
+    const bool pool = chooseScheduler(ctx);
+    if(ctx->schedProbe >= 0) CK(cudaEventRecord(ctx->ev[EV_PROBE0], ctx->stream));
+    launchTrace(tp, ctx->numSms, pool, ctx->stream);
+    if(ctx->schedProbe >= 0) CK(cudaEventRecord(ctx->ev[EV_PROBE1], ctx->stream));
     ctx->launches++;
     ctx->frameCostsValid = true;
     CK(cudaEventRecord(ctx->ev[EV_TRACE1], ctx->stream));
@@ -584,6 +620,7 @@ int rg_get_timings(rg_ctx* ctx, rg_timings* out) {
         cudaEventElapsedTime(&out->postproc_ms, ctx->ev[EV_RTONLY1], ctx->ev[EV_POST1]);
         cudaEventElapsedTime(&out->gather_ms, ctx->ev[EV_POST1], ctx->ev[EV_GATHER1]);
         if(!ctx->debugPostOnly) cudaEventElapsedTime(&out->trace_kernel_ms, ctx->ev[EV_RT0], ctx->ev[EV_TRACE1]);
+        out->trace_scheduler = (uint32_t)ctx->schedLast;
         unsigned long long c[16];
         CK(cudaMemcpy(c, ctx->dCounters, sizeof c, cudaMemcpyDeviceToHost));
         out->generic_hits = c[8];
@@ -716,6 +753,13 @@ int rg_peer_detach_all(rg_ctx* ctx) {
         for(int k = 0; k < 5; ++k) if(ctx->peerIpcOpened[q][k]) { cudaIpcCloseMemHandle(ctx->peerIpcOpened[q][k]); ctx->peerIpcOpened[q][k] = nullptr; }
         ctx->peerAttached[q] = false;
     }
+    return 0;
+}
+
+int rg_set_trace_scheduler(rg_ctx* ctx, int mode) {
+    if(!ctx) return 1;
+    if(mode != RG_SCHED_LANES && mode != RG_SCHED_POOL && mode != RG_SCHED_AUTO) return fail(ctx, "rg_set_trace_scheduler: mode must be RG_SCHED_LANES, RG_SCHED_POOL or RG_SCHED_AUTO");
+    ctx->schedMode = mode; ctx->schedProbe = -1; ctx->schedMs[0] = ctx->schedMs[1] = -1.0f; ctx->schedFrames = 0;
     return 0;
 }
 

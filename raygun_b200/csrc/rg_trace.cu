@@ -5,10 +5,11 @@
 //   closest hit resources/shaders/closesthit.rchit:74-268
 //   miss 0 / 1  resources/shaders/miss.rmiss:38-83, shadowMiss.rmiss:30-34
 // B200 has no RT cores, so traceRayEXT becomes a software traversal of compressed 8-wide nodes (rg_types.cuh) and
-// the shader recursion becomes an explicit per-lane stack of frames: each lane owns one pixel and walks that pixel's
-// ray tree depth-first in the reference's order (shadow -> reflection -> refraction), with ONE mutable payload, so
-// every stale-state effect of the GLSL (SURVEY.md 8a hazards 1-6) is reproduced.  Lanes that finish a pixel are
-// refilled from a global work counter with warp vote / shuffle compaction, so a warp keeps traversing 32 live rays.
+// the shader recursion becomes an explicit stack of frames per pixel sample ("context"): its ray tree is walked
+// depth-first in the reference's order (shadow -> reflection -> refraction), with ONE mutable payload, so every
+// stale-state effect of the GLSL (SURVEY.md 8a hazards 1-6) is reproduced.  Every warp of the persistent grid runs a pool
+// of contexts with ray / hit queues in shared memory: lanes take the next ray the moment theirs is done (warp vote +
+// prefix rank), and hits are shaded 32 at a time -- see k_trace.
 //
 // Ray / triangle arithmetic is bit-identical to the oracle (explicitly rounded operations, never contracted):
 // watertight Woop test, t preserved across the instance transform, ties resolved to the smallest (instance, primitive).
@@ -19,16 +20,6 @@
 #include <cstdlib>
 
 #include "../../include/rgb200.h"
-
-#ifndef RG_LANE_CONTEXTS
-#define RG_LANE_CONTEXTS 1
-#endif
-#ifndef RG_POSTPONE_THRESHOLD
-#define RG_POSTPONE_THRESHOLD 12
-#endif
-#ifndef RG_TRAVERSE_IFIF
-#define RG_TRAVERSE_IFIF 1
-#endif
 
 namespace rg {
 
@@ -94,6 +85,12 @@ __device__ __forceinline__ void setupRay(RayCtx& r, float ox, float oy, float oz
     r.Sz = __frcp_rn(dkz);
 }
 
+__device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {   // (m & a) | (~m & b), opaque to the optimiser
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(d) : "r"(m), "r"(a), "r"(b));
+    return d;
+}
+
 template <int J>
 __device__ __forceinline__ float byteF(uint32_t w) {  // 1 + b / 32768 for byte J of w: ONE PRMT puts b into mantissa bits 15..8 of 1.0f;
     return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u + (J << 4)));   // the affine map back to b is folded into the FFMA constants
@@ -152,179 +149,182 @@ __device__ __forceinline__ bool triTest(const RayCtx& r, const float4 p0, const 
     return true;
 }
 
-// Closest hit in [tmin, tmax] (exclusive).  hit.inst == kInvalid on miss.
-template <bool COUNT>
-__device__ __forceinline__ void traverse(const TraceParams& P, float ox, float oy, float oz, float dx, float dy, float dz, float tmin, float tmax,
-                                         Hit& hit, uint32_t* cnt) {
+// The world-space ray of the traversal in flight: in registers (one ray per lane), or in the warp pool in shared memory.
+struct WorldRayRegs {
+    float o[3], d[3], tm;
+    __device__ __forceinline__ float ox() const { return o[0]; }
+    __device__ __forceinline__ float oy() const { return o[1]; }
+    __device__ __forceinline__ float oz() const { return o[2]; }
+    __device__ __forceinline__ float dx() const { return d[0]; }
+    __device__ __forceinline__ float dy() const { return d[1]; }
+    __device__ __forceinline__ float dz() const { return d[2]; }
+    __device__ __forceinline__ float tmax() const { return tm; }
+};
+struct WorldRayPool {   // structure-of-arrays: component k of context c at p[k * kPoolCtx]
+    const float* p;
+    __device__ __forceinline__ float ox() const { return p[0]; }
+    __device__ __forceinline__ float oy() const { return p[kPoolCtx]; }
+    __device__ __forceinline__ float oz() const { return p[2 * kPoolCtx]; }
+    __device__ __forceinline__ float dx() const { return p[3 * kPoolCtx]; }
+    __device__ __forceinline__ float dy() const { return p[4 * kPoolCtx]; }
+    __device__ __forceinline__ float dz() const { return p[5 * kPoolCtx]; }
+    __device__ __forceinline__ float tmax() const { return p[7 * kPoolCtx]; }
+};
+
+// Resumable closest-hit traversal.  The state of one ray lives in registers (+ a stack in local memory) and travStep advances
+// it by ONE node test and / or ONE primitive test, so a warp can hand a finished lane its next ray at any step, and can leave
+// the traversal loop to shade while some lanes are still on their way.
+struct Trav {
+    RayCtx r;            // the ray in the space being traversed (world in the TLAS, object inside an instance)
+    uint2 ng, tg;        // current node group (child base, hit bits << 24 | imask) and primitive group (base, hit bits)
+    int sp;
+    uint32_t curInst;    // instance being traversed; kInvalid while in the TLAS
+};
+
+// Closest hit in (tmin, tmax).  hit.inst == kInvalid on miss.
+__device__ __forceinline__ void travInit(const TraceParams& P, Trav& T, Hit& hit, float ox, float oy, float oz, float dx, float dy, float dz, float tmax) {
     hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.inst = kInvalid; hit.prim = kInvalid;
-    if(P.nInst == 0) return;
-    if(dx == 0.0f && dy == 0.0f && dz == 0.0f) return;       // zero direction (refract on total internal reflection): miss
-    if(!(dx == dx && dy == dy && dz == dz && ox == ox && oy == oy && oz == oz)) return;  // NaN ray: miss
+    T.sp = 0;
+    T.tg = make_uint2(0u, 0u);
+    T.curInst = kInvalid;
+    // nothing to traverse (the first travStep reports a miss): empty scene, zero direction (refract on total internal reflection), NaN ray
+    const bool none = P.nInst == 0 || (dx == 0.0f && dy == 0.0f && dz == 0.0f) || !(dx == dx && dy == dy && dz == dz && ox == ox && oy == oy && oz == oz);
+    T.ng = make_uint2(0u, none ? 0u : 0x80000000u);
+    if(!none) setupRay(T.r, ox, oy, oz, dx, dy, dz);
+}
 
-    RayCtx r;
-    setupRay(r, ox, oy, oz, dx, dy, dz);
-    uint2 stack[kStackSize];
-    int sp = 0;
-    uint2 ng = make_uint2(0u, 0x80000000u);
-    uint2 tg = make_uint2(0u, 0u);
-    bool inBlas = false;
-    uint32_t curInst = kInvalid;
-    const Node8* nodes = P.tlasNodes;
-
-    while(true) {
-#if RG_TRAVERSE_IFIF
-        if((ng.y & 0xff000000u) && !tg.y) {   // one node per iteration, and only once this lane's pending primitives are done
-#else
-        if(ng.y & 0xff000000u) {
-#endif
-            const int bit = 31 - __clz(ng.y);
-            ng.y &= ~(1u << bit);
-            const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
-            const uint32_t rel = __popc(ng.y & 0xffu & ((1u << slot) - 1u));
-            if((ng.y & 0xff000000u) && sp < kStackSize) stack[sp++] = ng;
-            const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
-            const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-            if(COUNT) cnt[CNT_NODES]++;
-            const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
-                        sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
-            const float px = __uint_as_float(n0.x) - r.ox, py = __uint_as_float(n0.y) - r.oy, pz = __uint_as_float(n0.z) - r.oz;
-            // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
-            // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.
-            // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
-            // byteF gives v = 1 + q / 32768, so t = v * A + (b - A) with A = 32768 * 2^e / d.  Rounding: ulp(A) = 1/256 of one
-            // quantisation step in t, plus the error of b = (p - o) / d; both are covered by the slack (relative to |b| and to a step).
-            const float ax = sx * r.ix * 32768.0f, ay = sy * r.iy * 32768.0f, az = sz * r.iz * 32768.0f;
-            const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
-            const float kSlack = 7.2e-7f, kStep = 1.0f / (32768.0f * 64.0f);   // 1/64 of a quantisation step
-            const float wx = fmaf(fabsf(bx), kSlack, fabsf(ax) * kStep), wy = fmaf(fabsf(by), kSlack, fabsf(ay) * kStep), wz = fmaf(fabsf(bz), kSlack, fabsf(az) * kStep);
-            const float onx = (bx - ax) - wx, ony = (by - ay) - wy, onz = (bz - az) - wz;
-            const float ofx = (bx - ax) + wx, ofy = (by - ay) + wy, ofz = (bz - az) + wz;
-            const bool negx = r.dx < 0.0f, negy = r.dy < 0.0f, negz = r.dz < 0.0f;
-            const uint32_t octinv4 = r.octinv * 0x01010101u;
-            uint32_t hitmask = 0;
+// One step; true when the traversal is complete.  wray: the world-space ray given to travInit (needed again when an instance is entered or left).
+template <bool COUNT, class WR>
+__device__ __forceinline__ bool travStep(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
+    RayCtx& r = T.r;
+    if((T.ng.y & 0xff000000u) && !T.tg.y) {   // one node per step, and only once this lane's pending primitives are done
+        uint2 ng = T.ng;
+        const int bit = 31 - __clz(ng.y);
+        ng.y &= ~(1u << bit);
+        const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
+        const uint32_t rel = __popc(ng.y & 0xffu & ((1u << slot) - 1u));
+        if((ng.y & 0xff000000u) && T.sp < kStackSize) stack[T.sp++] = ng;
+        const Node8* nodes = T.curInst != kInvalid ? P.blasNodes : P.tlasNodes;
+        const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
+        const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        if(COUNT) cnt[CNT_NODES]++;
+        const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
+                    sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
+        const float px = __uint_as_float(n0.x) - r.ox, py = __uint_as_float(n0.y) - r.oy, pz = __uint_as_float(n0.z) - r.oz;
+        // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
+        // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.
+        // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
+        // byteF gives v = 1 + q / 32768, so t = v * A + (b - A) with A = 32768 * 2^e / d.  Rounding: ulp(A) = 1/256 of one
+        // quantisation step in t, plus the error of b = (p - o) / d; both are covered by the slack (relative to |b| and to a step).
+        const float ax = sx * r.ix * 32768.0f, ay = sy * r.iy * 32768.0f, az = sz * r.iz * 32768.0f;
+        const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
+        const float kSlack = 7.2e-7f, kStep = 1.0f / (32768.0f * 64.0f);   // 1/64 of a quantisation step
+        const float wx = fmaf(fabsf(bx), kSlack, fabsf(ax) * kStep), wy = fmaf(fabsf(by), kSlack, fabsf(ay) * kStep), wz = fmaf(fabsf(bz), kSlack, fabsf(az) * kStep);
+        const float onx = (bx - ax) - wx, ony = (by - ay) - wy, onz = (bz - az) - wz;
+        const float ofx = (bx - ax) + wx, ofy = (by - ay) + wy, ofz = (bz - az) + wz;
+        // near / far plane words by the sign of the direction: one LOP3 each on the packed words BEFORE the byte decode
+        // (a plain ?: lets the compiler select after decoding both, which doubles the PRMTs)
+        const uint32_t mx = (r.octinv & 4u) ? 0u : 0xffffffffu, my = (r.octinv & 2u) ? 0u : 0xffffffffu, mz = (r.octinv & 1u) ? 0u : 0xffffffffu;
+        const uint32_t octinv4 = r.octinv * 0x01010101u;
+        uint32_t hitmask = 0;
 #pragma unroll 1
-            for(int half = 0; half < 2; ++half) {   // slots 0..3, then 4..7: a rolled loop keeps the hot code small for the instruction cache
-                const uint32_t lx = half ? n2.y : n2.x, ly = half ? n2.w : n2.z, lz = half ? n3.y : n3.x;
-                const uint32_t hx = half ? n3.w : n3.z, hy = half ? n4.y : n4.x, hz = half ? n4.w : n4.z;
-                const uint32_t nx = negx ? hx : lx, fx = negx ? lx : hx, ny = negy ? hy : ly, fy = negy ? ly : hy, nz = negz ? hz : lz, fz = negz ? lz : hz;
-                uint32_t bits4, idx4;
-                decodeMeta4(half ? n1.w : n1.z, octinv4, bits4, idx4);
-                childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-                childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-                childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-                childTest<3>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-            }
-            ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
-            tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+        for(int half = 0; half < 2; ++half) {   // slots 0..3, then 4..7: a rolled loop keeps the hot code small for the instruction cache
+            const uint32_t lx = half ? n2.y : n2.x, ly = half ? n2.w : n2.z, lz = half ? n3.y : n3.x;
+            const uint32_t hx = half ? n3.w : n3.z, hy = half ? n4.y : n4.x, hz = half ? n4.w : n4.z;
+            const uint32_t nx = bitsel(mx, hx, lx), fx = bitsel(mx, lx, hx), ny = bitsel(my, hy, ly), fy = bitsel(my, ly, hy), nz = bitsel(mz, hz, lz), fz = bitsel(mz, lz, hz);
+            uint32_t bits4, idx4;
+            decodeMeta4(half ? n1.w : n1.z, octinv4, bits4, idx4);
+            childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+            childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+            childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+            childTest<3>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
         }
-#if !RG_TRAVERSE_IFIF
-        else {
-            tg = ng;
-            ng = make_uint2(0u, 0u);
-        }
-#endif
+        T.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+        T.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+    }
 
-#if RG_TRAVERSE_IFIF
-        if(tg.y) {      // ONE primitive per iteration: lanes without pending primitives go on with their next node meanwhile
-#else
-        while(tg.y) {
-#endif
-            const int bit = __ffs(tg.y) - 1;
-            tg.y &= tg.y - 1u;
-            if(!inBlas) {
-                const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + (tg.x + bit));
-                const uint4 l3 = __ldg(lp + 3);
-                if(l3.x == kInvalid) continue;  // instance of an empty mesh
-                if(sp + 6 > kStackSize) continue;  // stack exhausted: skip (never with sane scenes)
+    if(T.tg.y) {      // ONE primitive per step: lanes without pending primitives go on with their next node meanwhile
+        const int bit = __ffs(T.tg.y) - 1;
+        T.tg.y &= T.tg.y - 1u;
+        if(T.curInst == kInvalid) {
+            const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + (T.tg.x + bit));
+            const uint4 l3 = __ldg(lp + 3);
+            // instance of an empty mesh, or stack exhausted (never with sane scenes): skip
+            if(l3.x != kInvalid && T.sp + 6 <= kStackSize) {
                 if(COUNT) cnt[CNT_INST]++;
-                if(tg.y) stack[sp++] = tg;
-                if(ng.y & 0xff000000u) stack[sp++] = ng;
+                const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+                const float ox = wray.ox(), oy = wray.oy(), oz = wray.oz();
+                bool enter = true;
                 if(l3.z) {
-                    // pure translation (flagged by k_prepare_instances): the direction and everything derived from it stay; the
-                    // oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t
-                    const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
-                    stack[sp++] = make_uint2(kInvalid, 0x1000u);
+                    // pure translation (flagged by the instance preparation): the direction and everything derived from it stay;
+                    // the oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t
+                    if(T.tg.y) stack[T.sp++] = T.tg;
+                    if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
+                    stack[T.sp++] = make_uint2(kInvalid, 0x1000u);
                     r.ox = __fadd_rn(ox, __uint_as_float(l0.w)); r.oy = __fadd_rn(oy, __uint_as_float(l1.w)); r.oz = __fadd_rn(oz, __uint_as_float(l2.w));
                 } else {
-                    const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
-                    // the world-space slab / shear constants ride on the stack while the instance is traversed
-                    stack[sp++] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
-                    stack[sp++] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx));
-                    stack[sp++] = make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz));
-                    stack[sp++] = make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8));
                     // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
                     const float* w0 = reinterpret_cast<const float*>(&l0); const float* w1 = reinterpret_cast<const float*>(&l1);
                     const float* w2 = reinterpret_cast<const float*>(&l2);
+                    const float dx = wray.dx(), dy = wray.dy(), dz = wray.dz();
                     const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0[0], ox), __fmul_rn(w0[1], oy)), __fmul_rn(w0[2], oz)), w0[3]);
                     const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1[0], ox), __fmul_rn(w1[1], oy)), __fmul_rn(w1[2], oz)), w1[3]);
                     const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2[0], ox), __fmul_rn(w2[1], oy)), __fmul_rn(w2[2], oz)), w2[3]);
                     const float odx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
                     const float ody = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
                     const float odz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
-                    if(odx == 0.0f && ody == 0.0f && odz == 0.0f) { sp -= 4; if(ng.y & 0xff000000u) sp -= 1; if(tg.y) sp -= 1; continue; }
-                    setupRay(r, oox, ooy, ooz, odx, ody, odz);
-                }
-                curInst = l3.y;
-                inBlas = true;
-                nodes = P.blasNodes;
-                ng = make_uint2(l3.x, 0x80000000u);
-                tg = make_uint2(0u, 0u);
-#if !RG_TRAVERSE_IFIF
-                break;
-#endif
-            } else {
-#if RG_POSTPONE_THRESHOLD > 0 && !RG_TRAVERSE_IFIF
-                // too few lanes of this warp are in the triangle loop and this lane still has child nodes to visit: put the
-                // triangle group back (it goes to the stack) and test it later together with more lanes (after Ylitie et al. 2017)
-                if((ng.y & 0xff000000u) && sp < kStackSize && __popc(__activemask()) < RG_POSTPONE_THRESHOLD) {
-                    tg.y |= 1u << bit;
-                    stack[sp++] = tg;
-                    tg.y = 0u;
-                    break;
-                }
-#endif
-                const float4* tp = reinterpret_cast<const float4*>(P.tris + (tg.x + bit));
-                const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
-                if(COUNT) cnt[CNT_TRIS]++;
-                float t, u, v;
-                if(triTest(r, p0, p1, p2, tmin, t, u, v)) {
-                    const uint32_t prim = __float_as_uint(p0.w);
-                    if(t < hit.t || (t == hit.t && t < tmax && (curInst < hit.inst || (curInst == hit.inst && prim < hit.prim)))) {
-                        hit.t = t; hit.u = u; hit.v = v; hit.inst = curInst; hit.prim = prim;
+                    if(odx == 0.0f && ody == 0.0f && odz == 0.0f) {
+                        enter = false;
+                    } else {
+                        if(T.tg.y) stack[T.sp++] = T.tg;
+                        if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
+                        // the world-space slab / shear constants ride on the stack while the instance is traversed
+                        stack[T.sp++] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
+                        stack[T.sp++] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx));
+                        stack[T.sp++] = make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz));
+                        stack[T.sp++] = make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8));
+                        setupRay(r, oox, ooy, ooz, odx, ody, odz);
                     }
                 }
-            }
-        }
-
-#if RG_TRAVERSE_IFIF
-        if(!(ng.y & 0xff000000u) && !tg.y) {
-#else
-        if(!(ng.y & 0xff000000u)) {
-#endif
-            bool done = false;
-            while(true) {
-                if(sp == 0) { done = true; break; }
-                ng = stack[--sp];
-                if(ng.x == kInvalid) {  // leave the instance: back to the world-space ray
-                    inBlas = false; nodes = P.tlasNodes;
-                    r.ox = ox; r.oy = oy; r.oz = oz;
-                    if(!(ng.y & 0x1000u)) {   // a general instance: direction-derived constants come back from the stack
-                        r.dx = dx; r.dy = dy; r.dz = dz;
-                        r.octinv = ng.y & 7u; r.kx = (int)((ng.y >> 4) & 3u); r.ky = (int)((ng.y >> 6) & 3u); r.kz = (int)((ng.y >> 8) & 3u);
-                        const uint2 c2 = stack[--sp], c1 = stack[--sp], c0 = stack[--sp];
-                        r.ix = __uint_as_float(c0.x); r.iy = __uint_as_float(c0.y); r.iz = __uint_as_float(c1.x);
-                        r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
-                    }
-                    continue;
+                if(enter) {
+                    T.curInst = l3.y;
+                    T.ng = make_uint2(l3.x, 0x80000000u);
+                    T.tg = make_uint2(0u, 0u);
                 }
-                break;
             }
-            if(done) break;
-#if RG_TRAVERSE_IFIF
-            if(!(ng.y & 0xff000000u)) { tg = ng; ng = make_uint2(0u, 0u); }   // a primitive group came off the stack
-#endif
+            return false;
+        } else {
+            const float4* tp = reinterpret_cast<const float4*>(P.tris + (T.tg.x + bit));
+            const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+            if(COUNT) cnt[CNT_TRIS]++;
+            float t, u, v;
+            if(triTest(r, p0, p1, p2, tmin, t, u, v)) {
+                const uint32_t prim = __float_as_uint(p0.w);
+                if(t < hit.t || (t == hit.t && t < wray.tmax() && (T.curInst < hit.inst || (T.curInst == hit.inst && prim < hit.prim)))) {
+                    hit.t = t; hit.u = u; hit.v = v; hit.inst = T.curInst; hit.prim = prim;
+                }
+            }
         }
     }
+
+    if(!(T.ng.y & 0xff000000u) && !T.tg.y) {
+        while(true) {
+            if(T.sp == 0) return true;
+            T.ng = stack[--T.sp];
+            if(T.ng.x != kInvalid) break;
+            // leave the instance: back to the world-space ray
+            T.curInst = kInvalid;
+            r.ox = wray.ox(); r.oy = wray.oy(); r.oz = wray.oz();
+            if(!(T.ng.y & 0x1000u)) {   // a general instance: direction-derived constants come back from the stack
+                r.octinv = T.ng.y & 7u; r.kx = (int)((T.ng.y >> 4) & 3u); r.ky = (int)((T.ng.y >> 6) & 3u); r.kz = (int)((T.ng.y >> 8) & 3u);
+                const uint2 c2 = stack[--T.sp], c1 = stack[--T.sp], c0 = stack[--T.sp];
+                r.ix = __uint_as_float(c0.x); r.iy = __uint_as_float(c0.y); r.iz = __uint_as_float(c1.x);
+                r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
+            }
+        }
+        if(!(T.ng.y & 0xff000000u)) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }   // a primitive group came off the stack
+    }
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------------ shading
@@ -367,30 +367,333 @@ __device__ __noinline__ V3 skyColor(V3 d, V3 lightDir, bool strict) {
     return sunColor + skyScatter;
 }
 
-// frame layout (words) in local memory
-enum {
-    F_ORG = 0, F_DIR = 3, F_N = 6, F_T = 9, F_DIFF = 10, F_SPEC = 13, F_TRANSP = 16, F_REFL = 17, F_ROUGH = 18, F_IOR = 19, F_EMIS = 20, F_FLAGS = 21,
-    F_BASE = 22, F_RCOL = 25, F_RDEPTH = 28, F_RECDEPTH = 29, F_WORDS = 30
-};
 enum { FR_GEN = 0, FR_SHI = 1 };
 enum { ST_SHADOW_RET = 0, ST_TRY_REFLECT = 1, ST_REFLECT_RET = 2, ST_TRY_REFRACT = 3, ST_REFRACT_RET_FRONT = 4, ST_REFRACT_RET_BACK = 5, ST_COMBINE = 6 };
 
 __device__ __forceinline__ uint32_t f2h(float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); }
 __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) { return make_uint2(f2h(x) | (f2h(y) << 16), f2h(z) | (f2h(w) << 16)); }
 
-#ifndef RG_POSTPONE_THRESHOLD
-#define RG_POSTPONE_THRESHOLD 12
-#endif
 #ifndef RG_TRACE_MIN_BLOCKS
-#define RG_TRACE_MIN_BLOCKS 8
+#define RG_TRACE_MIN_BLOCKS 4
 #endif
-// K = ray contexts per lane.  K == 1: the lane's state lives in registers.  K > 1: contexts live in local memory and every
-// lane traverses its K pending rays back to back, so a warp waits for the slowest SUM of K rays rather than for the slowest
-// single ray -- the cure for warps that idle on incoherent bounces (sphere-grid config).
-template <bool COUNT, bool MULTI, int K>
-__global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
+#ifndef RG_FETCH_THRESHOLD
+#define RG_FETCH_THRESHOLD 8     // lanes without a ray before the warp fetches from its ray queue
+#endif
+#ifndef RG_EXIT_THRESHOLD
+#define RG_EXIT_THRESHOLD 12     // lanes without a ray, with the ray queue empty, before the warp leaves the traversal loop to shade
+#endif
+#ifndef RG_REFILL_THRESHOLD
+#define RG_REFILL_THRESHOLD 16   // free contexts before new work items are fetched (consecutive items = neighbouring pixels)
+#endif
+
+// Per-warp pool of ray-tree contexts.  A context = one pixel SAMPLE whose ray tree is walked depth-first in the shader's order
+// (shadow -> reflection -> refraction) with ONE mutable payload, so every stale-state effect of the GLSL (SURVEY.md 8a hazards
+// 1-6) is reproduced.  The hot part of a context (pending ray, closest hit, payload) lives in shared memory, structure-of-arrays
+// so that 32 lanes holding 32 different contexts hit different banks; the suspended shader invocations (frames) live in global
+// memory (kCtxQuads float4 per context, L2 resident).  Three byte queues hold context ids: rays waiting for traversal, hits
+// waiting for shading, free contexts.
+struct WarpPool {
+    float ray[8][kPoolCtx];      // o.xyz, d.xyz, tmin, tmax
+    uint32_t hit[5][kPoolCtx];   // t, u, v, instance, primitive
+    float pay[6][kPoolCtx];      // hitValue.xyz, depth, curIOR, refDepth
+    uint32_t sel[kPoolCtx];      // rayType | missIndex << 2 | rayKind << 4 | recDepth << 8 | frames << 16
+    uint32_t pix[4][kPoolCtx];   // lx | ly << 16, pixel slot, sample, rays of this sample
+    uint8_t rayQ[kPoolCtx], hitQ[kPoolCtx], freeQ[kPoolCtx];
+};
+constexpr uint32_t kNoCtx = 0xffu;
+constexpr uint32_t kQMask = kPoolCtx - 1;
+static_assert((kPoolCtx & (kPoolCtx - 1)) == 0 && kPoolCtx >= 32 && kPoolCtx <= 128, "kPoolCtx: power of two, 32..128");
+
+// frame layout: 8 float4 per suspended invocation
+enum { Q_ORG_T = 0, Q_DIR_FLAGS = 1, Q_N_RECDEPTH = 2, Q_DIFF_TRANSP = 3, Q_SPEC_REFL = 4, Q_BASE_ROUGH = 5, Q_RCOL_RDEPTH = 6, Q_IOR_EMIS = 7 };
+
+// What the shaders do between two traceRayEXT calls of one pixel sample: the closest-hit or miss program of the ray that just
+// came back, then the code after every traceRayEXT that returned (suspended frames, innermost first) up to the next traceRayEXT.
+// Shared by both trace kernels; they differ only in where the state lives.  h: closest hit of the ray (ro, rd).  On return 1 the
+// next ray is in (ro, rd, rtmin, rtmax) / (rayType, missIndex, rayKind); on return 2 the sample ended and its pixel share is stored.
+// fr: the context's frames, 8 float4 each, + 2 float4 for the payload members that are only observable at recDepth 0.
+struct ShadeConsts { V3 L; int maxRec; bool strictIeee; int numSamples; uint32_t S; };
+struct PixInfo { uint32_t xy, pslot, sample, rays; };   // lx | ly << 16, pixel slot, sample index, rays traced for this sample so far
+template <bool COUNT, bool MULTI>
+__device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeConsts& K, const Hit& h, V3& ro, V3& rd, float& rtmin, float& rtmax, V3& hv,
+                                            float& depth, float& curIOR, float& refDepth, int& rayType, int& missIndex, int& rayKind, int& recDepth, int& sp,
+                                            float4* fr, const PixInfo& pix, uint32_t* skyLookups, uint32_t* cntT) {
+    const bool found = h.inst != kInvalid;
+    if(rayKind == CNT_PRIMARY && P.idInst && pix.sample == 0u) {
+        const uint32_t xy = pix.xy;
+        const int qx = (int)(xy & 0xffffu) - P.sx0, qy = (int)(xy >> 16) - P.sy0;
+        if(qx >= 0 && qy >= 0 && qx < P.sw && qy < P.sh) { P.idInst[qy * P.sw + qx] = h.inst; P.idPrim[qy * P.sw + qx] = h.prim; }
+    }
+    bool issue = false;   // a new ray is pending
+    if(found) {
+        // closesthit.rchit:96-109
+        const uint4 is3 = __ldg(reinterpret_cast<const uint4*>(P.instShade + h.inst) + 3);
+        const uint32_t vtxOff = is3.x, idxOff = is3.y, matOff = is3.z;
+        const uint32_t i0 = __ldg(P.indices + idxOff + 3 * h.prim), i1 = __ldg(P.indices + idxOff + 3 * h.prim + 1),
+                       i2 = __ldg(P.indices + idxOff + 3 * h.prim + 2);
+        const float4 v0p = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0));
+        const float4 n0 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0) + 1), n1 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i1) + 1),
+                     n2 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i2) + 1);
+        const float4* mp = P.materials + 4 * (size_t)(matOff + __float_as_uint(v0p.w));
+        const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
+        V3 diffuse = v3(m0.x, m0.y, m0.z), specular = v3(m1.x, m1.y, m1.z);
+        const float transparency = m0.w; float reflectivity = m1.w;
+        const float roughness = m2.x, ior = m2.y, emission = m3.x;
+        const uint32_t effectId = __float_as_uint(m2.z), rayConsumption = __float_as_uint(m2.w);
+
+        const float b0 = 1.0f - h.u - h.v;
+        const V3 origin = ro + rd * h.t;                                        // :114
+        const V3 vn = v3(n0.x, n0.y, n0.z) * b0 + v3(n1.x, n1.y, n1.z) * h.u + v3(n2.x, n2.y, n2.z) * h.v;  // :117
+        const float4* ow = reinterpret_cast<const float4*>(P.instShade + h.inst);
+        const float4 o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2);
+        V3 n = normalize(v3(o0.x * vn.x + o0.y * vn.y + o0.z * vn.z, o1.x * vn.x + o1.y * vn.y + o1.z * vn.z, o2.x * vn.x + o2.y * vn.y + o2.z * vn.z));  // :118-119
+
+        if(effectId == 1u) {  // gridEffect, :74-91
+            const float aa = (refDepth + h.t + 8.0f) / 30.0f;
+            const float aa2 = aa / 2.0f;
+            float minmod = glmin(fabsf(glmod((origin.x + 1000.0f) * 10.0f + aa2, 20.0f) - aa2), fabsf(glmod((origin.z + 1000.0f) * 10.0f + aa2, 20.0f) - aa2));
+            if(minmod < aa2) {
+                minmod -= aa2 - (aa * aa) / 3.0f;
+                minmod *= 3.0f / (aa * aa);
+                const float f = mixf(aa / 10.0f, 1.0f, minmod);
+                diffuse = diffuse * f; specular = specular * f; reflectivity *= f;
+            }
+            if(glmod((origin.x + 1000.0f) * 5.0f, 20.0f) < 10.0f && glmod((origin.z + 1000.0f) * 5.0f, 20.0f) < 10.0f) reflectivity *= 1.5f;
+        }
+
+        if(rayType == RT_SHADOW_INTERNAL) {  // :125-152
+            const float thick = clampf(h.t * (1.0f - transparency) * 10.0f, 0.0f, 1.0f);
+            const V3 nd = normalize(v3(1.1f - diffuse.x, 1.1f - diffuse.y, 1.1f - diffuse.z));
+            const V3 shadowCol = hv - mix3(v3(0, 0, 0), v3(nd.x + 0.1f, nd.y + 0.1f, nd.z + 0.1f), thick);
+            if(recDepth < K.maxRec) {
+                float4* f = fr + 8 * sp++;
+                f[Q_ORG_T] = make_float4(shadowCol.x, shadowCol.y, shadowCol.z, 0.0f);
+                f[Q_DIR_FLAGS] = make_float4(rd.x, rd.y, rd.z, __int_as_float(FR_SHI));
+                f[Q_N_RECDEPTH] = make_float4(n.x, n.y, n.z, __int_as_float(recDepth));
+                f[Q_IOR_EMIS] = make_float4(ior, 0.0f, 0.0f, 0.0f);
+                rayType = RT_SHADOW_TRACE; recDepth++;
+                ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 0; rayKind = CNT_SHADOW;   // rd unchanged (T3)
+                issue = true;
+            } else {
+                hv = shadowCol * 0.4f;
+            }
+        } else if(rayType == RT_SHADOW_TRACE) {  // :153-166
+            if(transparency > 0.0f) {
+                if(recDepth < K.maxRec) {   // T2: nothing to do after the child returns except recDepth--, which every
+                    rayType = RT_SHADOW_INTERNAL; recDepth++;                 // resuming frame restores from its own copy
+                    ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
+                    issue = true;
+                }
+            } else {
+                hv = hv * mixf(0.4f, 0.8f, clampf(logf(h.t) / 8.0f, 0.0f, 1.0f));
+            }
+        } else {  // RT_GENERIC, :168-268
+            if(COUNT) cntT[CNT_GENHIT]++;
+            const bool frontFacing = dot(-rd, n) > 0.0f;
+            if(!frontFacing) n = normalize(-n);
+            const float ndl = dot(-K.L, n);
+            V3 baseColor = diffuse * glmax(ndl, 0.2f);
+            float4* f = fr + 8 * sp++;
+            const V3 rdIn = rd;
+            int stage;
+            bool shadowPending = false;
+            if(ndl > 0.07f) {   // :188
+                if(recDepth < K.maxRec) {
+                    hv = v3(1.0f, 1.0f, 1.0f);
+                    rayType = RT_SHADOW_TRACE;
+                    ro = origin; rd = -K.L; rtmin = 0.1f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
+                    shadowPending = true;
+                }
+                // recDepth >= max: shadowColor stays 1
+            } else {
+                const float sm = transparency * transparency;   // pow(t, 2)
+                const V3 sc = transparency < 1.0f ? mix3(v3(1, 1, 1), diffuse * sm, transparency) : v3(0.4f, 0.4f, 0.4f);
+                baseColor = baseColor * sc;
+            }
+            if(shadowPending) { stage = ST_SHADOW_RET; issue = true; }
+            else { baseColor = baseColor + diffuse * emission; stage = ST_TRY_REFLECT; }
+            const int flags = FR_GEN | (stage << 8) | ((frontFacing ? 1 : 0) << 16) | ((int)(rayConsumption & 0xffu) << 20);
+            f[Q_ORG_T] = make_float4(origin.x, origin.y, origin.z, h.t);
+            f[Q_DIR_FLAGS] = make_float4(rdIn.x, rdIn.y, rdIn.z, __int_as_float(flags));
+            f[Q_N_RECDEPTH] = make_float4(n.x, n.y, n.z, __int_as_float(recDepth));
+            f[Q_DIFF_TRANSP] = make_float4(diffuse.x, diffuse.y, diffuse.z, transparency);
+            f[Q_SPEC_REFL] = make_float4(specular.x, specular.y, specular.z, reflectivity);
+            f[Q_BASE_ROUGH] = make_float4(baseColor.x, baseColor.y, baseColor.z, roughness);
+            f[Q_IOR_EMIS] = make_float4(ior, emission, 0.0f, 0.0f);
+            if(shadowPending) recDepth++;
+        }
+    } else {
+        if(missIndex == 0) {  // miss.rmiss:76-83
+            const V3 sky = skyColor(rd, K.L, K.strictIeee);
+            hv = sky; depth = 10000.0f;
+            if(sp == 0 && recDepth == 0) fr[kMaxFrames * 8 + 1] = make_float4(sky.x, sky.y, sky.z, 0.0f);   // roughValue is only observable for a primary miss
+        } else {              // shadowMiss.rmiss:33
+            hv = v3(1.0f, 1.0f, 1.0f);
+        }
+    }
+
+    // ---- resume suspended frames (the code after each traceRayEXT returns)
+    bool ended = false;
+    while(!issue) {
+        if(sp == 0) {   // raygen.h:105-111: the sample's trace returned
+            const uint32_t xy = pix.xy, pslot = pix.pslot, sample = pix.sample;
+            const uint32_t lx = xy & 0xffffu, ly = xy >> 16;
+            if(P.tileCost) atomicAdd(P.tileCost + (pslot >> 5), pix.rays);
+            const float4 cold0 = fr[kMaxFrames * 8], cold1 = fr[kMaxFrames * 8 + 1];   // normal + reflectContribution, roughValue
+            V3 accColor = hv, accNormal = v3(cold0.x, cold0.y, cold0.z), accRough = v3(cold1.x, cold1.y, cold1.z);
+            float accRoughA = cold1.w, accContrib = cold0.w, accDepth = depth;
+            bool last = true;
+            if(K.S > 1u) {   // park this sample; the lane finishing the pixel's last sample sums all of them in order
+                float4* rec = P.sampleScratch + 3 * ((size_t)pslot * K.S + sample);
+                __stcg(rec, make_float4(hv.x, hv.y, hv.z, cold0.w));
+                __stcg(rec + 1, make_float4(cold0.x, cold0.y, cold0.z, depth));
+                __stcg(rec + 2, cold1);
+                __threadfence();
+                last = atomicAdd(P.sampleDone + pslot, 1u) == K.S - 1u;
+                if(last) {
+                    __threadfence();
+                    P.sampleDone[pslot] = 0u;   // ready for the next frame
+                    accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
+                    const float4* all = P.sampleScratch + 3 * (size_t)pslot * K.S;
+                    for(uint32_t i = 0; i < K.S; ++i) {   // raygen.h:105-111 in the loop's order
+                        const float4 a = __ldcg(all + 3 * i), b = __ldcg(all + 3 * i + 1), cc = __ldcg(all + 3 * i + 2);
+                        accColor = accColor + v3(a.x, a.y, a.z); accNormal = accNormal + v3(b.x, b.y, b.z);
+                        accRough = accRough + v3(cc.x, cc.y, cc.z); accRoughA += cc.w; accContrib += a.w; accDepth += b.w;
+                    }
+                }
+            }
+            if(last) {      // raygen.h:114 + raygen.rgen:35-38
+                const float inv = (float)K.numSamples;
+                const uint2 ob = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
+                const uint2 on = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
+                const uint2 orr = packHalf4(accRough.x / inv, accRough.y / inv, accRough.z / inv, accRoughA / inv);
+                // the pixel goes to every GPU whose post-chain rectangle contains it (own images or peer memory over NVLink)
+#pragma unroll
+                for(int q = 0; q < (MULTI ? kMaxPeers : 1); ++q) {   // static indices: the targets stay in the constant bank
+                    if((uint32_t)q < P.nTargets) {
+                        const int qx = (int)lx - P.targets[q].x0, qy = (int)ly - P.targets[q].y0;
+                        if(qx >= 0 && qy >= 0 && qx < P.targets[q].w && qy < P.targets[q].h) {
+                            const size_t o = (size_t)qy * P.targets[q].w + qx;
+                            P.targets[q].base[o] = ob; P.targets[q].normal[o] = on; P.targets[q].rough[o] = orr;
+                        }
+                    }
+                }
+            }
+            ended = true;
+            break;
+        }
+        float4* f = fr + 8 * (sp - 1);
+        const float4 qDir = f[Q_DIR_FLAGS], qN = f[Q_N_RECDEPTH], qOrg = f[Q_ORG_T], qIor = f[Q_IOR_EMIS];
+        const int flags = __float_as_int(qDir.w);
+        recDepth = __float_as_int(qN.w);   // undoes every recDepth++ / += rayConsumption below this frame
+        if((flags & 0xff) == FR_SHI) {   // closesthit.rchit:136-146, after T3 returned
+            V3 shadowCol = v3(qOrg.x, qOrg.y, qOrg.z);
+            if(depth < 1000.0f) {
+                hv = hv * shadowCol;
+            } else {
+                const V3 dir = refract3(v3(qDir.x, qDir.y, qDir.z), v3(qN.x, qN.y, qN.z), qIor.x);
+                const float dp = dot(K.L, dir);
+                const float dp2 = dp * dp;
+                shadowCol = shadowCol * (dp2 * dp2 * dp + 0.75f);   // pow(x, 5)
+                (*skyLookups)++;   // T4: cull mask 0 -> always miss 0
+                const V3 sky = skyColor(-dir, K.L, K.strictIeee);
+                depth = 10000.0f;
+                hv = shadowCol + sky * 0.1f;
+            }
+            sp--;
+            continue;
+        }
+        const float4 qDiff = f[Q_DIFF_TRANSP], qSpec = f[Q_SPEC_REFL];
+        float4 qBase = f[Q_BASE_ROUGH], qRcol = f[Q_RCOL_RDEPTH];
+        int stage = (flags >> 8) & 0xff;
+        const bool frontFacing = ((flags >> 16) & 1) != 0;
+        const int rc = (flags >> 20) & 0xff;
+        const V3 D = v3(qDir.x, qDir.y, qDir.z), n = v3(qN.x, qN.y, qN.z);
+        if(stage == ST_SHADOW_RET) {   // :196-197 then :254-255
+            const V3 diffuse = v3(qDiff.x, qDiff.y, qDiff.z);
+            const V3 base = v3(qBase.x, qBase.y, qBase.z) * hv + diffuse * qIor.y;
+            qBase.x = base.x; qBase.y = base.y; qBase.z = base.z;
+            stage = ST_TRY_REFLECT;
+        }
+        if(stage == ST_TRY_REFLECT) {  // :207-221
+            if(recDepth < K.maxRec && qSpec.w > 0.0f) {
+                recDepth += rc; refDepth += qOrg.w;
+                ro = v3(qOrg.x, qOrg.y, qOrg.z); rd = reflect3(D, n); rtmin = 0.01f; rtmax = 1000.0f;
+                rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFLECT;
+                f[Q_DIR_FLAGS] = make_float4(qDir.x, qDir.y, qDir.z, __int_as_float((flags & ~0xff00) | (ST_REFLECT_RET << 8)));
+                f[Q_BASE_ROUGH] = qBase;
+                issue = true;
+                break;
+            }
+            qRcol = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            stage = ST_TRY_REFRACT;
+        }
+        if(stage == ST_REFLECT_RET) {
+            qRcol = make_float4(hv.x * qSpec.x, hv.y * qSpec.y, hv.z * qSpec.z, depth);
+            stage = ST_TRY_REFRACT;
+        }
+        V3 refractColor = v3(1.0f, 1.0f, 1.0f);
+        if(stage == ST_TRY_REFRACT) {  // :224-251
+            if(recDepth < K.maxRec && qDiff.w > 0.0f) {
+                const float ior = qIor.x;
+                const float eta = frontFacing ? curIOR / ior : ior / 1.0f;
+                recDepth++;
+                curIOR = frontFacing ? ior : 1.0f;
+                ro = v3(qOrg.x, qOrg.y, qOrg.z); rd = refract3(D, n, eta); rtmin = 0.01f; rtmax = 1000.0f;
+                rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFRACT;
+                f[Q_DIR_FLAGS] = make_float4(qDir.x, qDir.y, qDir.z,
+                                             __int_as_float((flags & ~0xff00) | ((frontFacing ? ST_REFRACT_RET_FRONT : ST_REFRACT_RET_BACK) << 8)));
+                f[Q_BASE_ROUGH] = qBase; f[Q_RCOL_RDEPTH] = qRcol;
+                issue = true;
+                break;
+            }
+            stage = ST_COMBINE;
+        } else if(stage == ST_REFRACT_RET_FRONT) {
+            refractColor = hv;
+        } else if(stage == ST_REFRACT_RET_BACK) {
+            const V3 diffuse = v3(qDiff.x, qDiff.y, qDiff.z);
+            refractColor = mix3(v3(1, 1, 1), diffuse, logf(1.0f + qOrg.w)) * hv;
+        }
+        // combine, :254-267
+        {
+            const V3 base = v3(qBase.x, qBase.y, qBase.z);
+            const V3 reflectColor = v3(qRcol.x, qRcol.y, qRcol.z);
+            const float transparency = qDiff.w, reflectivity = qSpec.w, roughness = qBase.w;
+            const float totalContrib = glmax(transparency, reflectivity);
+            float weight = reflectivity / (transparency + reflectivity);
+            if(!K.strictIeee && (transparency + reflectivity) == 0.0f) weight = 0.0f;   // SURVEY hazard 8
+            const V3 roughCol = mix3(refractColor, reflectColor, weight);
+            hv = mix3(base, roughCol, totalContrib);
+            if(recDepth == 0) {
+                hv = base;
+                fr[kMaxFrames * 8] = make_float4(n.x, n.y, n.z, totalContrib);
+                fr[kMaxFrames * 8 + 1] = make_float4(roughCol.x, roughCol.y, roughCol.z, glmin((qRcol.w / 50.0f) * roughness, roughness / 2.1f));
+            }
+            depth = qOrg.w;
+            sp--;
+        }
+    }
+    return ended ? 2 : 1;
+}
+
+
+// The warp is a small scheduler over its pool (the decoupling the per-lane recursion lacked: with one context per lane a warp
+// waited for its longest ray and shaded with a handful of lanes, BASELINE config 3 ran at 7 of 32 lanes):
+//   TRAVERSE  lanes hold rays in flight (registers + stack).  A lane whose ray is done parks the hit in the pool, and as soon as
+//             RG_FETCH_THRESHOLD lanes are empty they take the next rays from the ray queue (vote + prefix rank).  The loop is
+//             left when 32 hits wait, or when the ray queue is dry and RG_EXIT_THRESHOLD lanes idle; rays in flight stay in flight.
+//   SHADE     up to 32 waiting hits are shaded together, one per lane: hit / miss program, then the code after the traceRayEXT
+//             that returned, up to the next traceRayEXT (whose ray goes to the ray queue) or the end of the sample.
+//   REFILL    free contexts take the next work items (pixel samples) from the global counter.
+template <bool COUNT, bool MULTI>
+__global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const TraceParams P) {
     __shared__ float s_ubo[48];
-    if(threadIdx.x < 48) s_ubo[threadIdx.x] = P.ubo[threadIdx.x];
+    __shared__ WarpPool s_pool[4];
+    __shared__ uint32_t s_cnt[5][128];    // per lane: rays by kind + sky lookups
+    const uint32_t tid = threadIdx.x;
+    if(tid < 48) s_ubo[tid] = P.ubo[tid];
+#pragma unroll
+    for(int k = 0; k < 5; ++k) s_cnt[k][tid] = 0u;
     __syncthreads();
     const float* VI = s_ubo;       // viewInverse, column-major
     const float* PI = s_ubo + 16;  // projInverse
@@ -398,9 +701,11 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
     const V3 L = v3(s_ubo[36], s_ubo[37], s_ubo[38]);
     int maxRec = __float_as_int(s_ubo[39]);
     maxRec = maxRec > kMaxRecursions ? kMaxRecursions : maxRec;
-    const bool strictIeee = (P.flags & RG_STRICT_IEEE) != 0;
+    ShadeConsts K;
+    K.L = L; K.maxRec = maxRec; K.strictIeee = (P.flags & RG_STRICT_IEEE) != 0; K.numSamples = numSamples; K.S = (uint32_t)numSamples;
 
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = tid & 31;
+    const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t tilesX = (P.dw + 7) / 8, tilesY = (P.dh + 3) / 4;
     const uint32_t nTiles = tilesX * tilesY;
     // this rank's share: chunks of kChunkTiles tiles dealt round-robin (world == 1: everything)
@@ -409,374 +714,278 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
     const uint32_t S = (uint32_t)numSamples;
     const uint32_t total = myChunks * kChunkTiles * 32u * S;   // one work item per pixel SAMPLE
 
-    enum { CS_IDLE = 0, CS_RAY = 1, CS_HIT = 2 };
-    float frames[K][kMaxFrames][F_WORDS];   // suspended shader invocations, per context
-    float cRay[K][8], cPay[K][14];          // pending ray; payload (hv, depth, curIOR, refDepth, normal, rough, roughA, contrib)
-    uint32_t cHit[K][5], cPix[K][6];        // closest hit; lx, ly, slot, pslot, sampleRays, sample
-    int cSel[K], cStatus[K];                // rayType | missIndex << 2 | rayKind << 4 | recDepth << 8 | sp << 16; CS_*
-#pragma unroll
-    for(int k = 0; k < K; ++k) cStatus[k] = CS_IDLE;
-    uint32_t cnt[CNT_N];
-#pragma unroll
-    for(int k = 0; k < CNT_N; ++k) cnt[k] = 0;
-
-    // per-pixel state
+    WarpPool& W = s_pool[tid >> 5];
+    float4* const ctxMem = P.ctxPool + (size_t)(blockIdx.x * 4u + (tid >> 5)) * kPoolCtx * kCtxQuads;
+    for(uint32_t i = lane; i < (uint32_t)kPoolCtx; i += 32u) W.freeQ[i] = (uint8_t)i;
+    __syncwarp();
+    // warp-uniform scheduler state
+    uint32_t rayHead = 0, rayCount = 0, hitHead = 0, hitCount = 0, freeHead = 0, freeCount = kPoolCtx;
     bool exhausted = false;
-    uint32_t lx = 0, ly = 0;   // frame coordinates of the lane's pixel
-    int sample = 0;
-    uint32_t slot = 0, pslot = 0, sampleRays = 0;   // tile slot in this rank's share, pixel slot (slot * 32 + lane in tile), rays of this sample
-    // payload (payload.h:29-39)
-    V3 hv = v3(0, 0, 0), pNormal = v3(0, 0, 0), pRough = v3(0, 0, 0);
-    float pRoughA = 0, pContrib = 0, depth = 0, curIOR = 1.0f, refDepth = 0;
-    int recDepth = 0;
-    int sp = 0;  // frames
-    // pending ray
-    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 0);
-    float rtmin = 0, rtmax = 0;
-    int rayType = RT_GENERIC, missIndex = 0, rayKind = CNT_PRIMARY;
+    // the lane's ray in flight
+    uint32_t myCtx = kNoCtx;
+    float tmin = 0.0f;
+    uint2 stack[kStackSize];
+    Trav T;
+    T.ng = make_uint2(0u, 0u); T.tg = make_uint2(0u, 0u); T.sp = 0; T.curInst = kInvalid;
+    Hit hit;
+    hit.t = 0.0f; hit.u = 0.0f; hit.v = 0.0f; hit.inst = kInvalid; hit.prim = kInvalid;
+    uint32_t cntT[CNT_N];
+    if(COUNT) {
+#pragma unroll
+        for(int k = 0; k < CNT_N; ++k) cntT[k] = 0;
+    }
     // camera origin: viewInverse * (0,0,0,1) in GLM order (c0*0 + c1*0) + (c2*0 + c3*1)
     const V3 camO = v3((VI[0] * 0.0f + VI[4] * 0.0f) + (VI[8] * 0.0f + VI[12] * 1.0f), (VI[1] * 0.0f + VI[5] * 0.0f) + (VI[9] * 0.0f + VI[13] * 1.0f),
                        (VI[2] * 0.0f + VI[6] * 0.0f) + (VI[10] * 0.0f + VI[14] * 1.0f));
 
-    auto primaryRay = [&](int i) {
-        const float2 off = aaOffset(numSamples, i);
-        const float pcx = (float)lx + 0.5f + off.x, pcy = (float)ly + 0.5f + off.y;
-        const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
-        // target = projInverse * (d.x, d.y, 1, 1); direction = viewInverse * (normalize(target.xyz), 0)
-        const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
-                          (PI[2] * ddx + PI[6] * ddy) + (PI[10] + PI[14]));
-        const V3 nt = normalize(tgt);
-        rd = v3((VI[0] * nt.x + VI[4] * nt.y) + (VI[8] * nt.z), (VI[1] * nt.x + VI[5] * nt.y) + (VI[9] * nt.z), (VI[2] * nt.x + VI[6] * nt.y) + (VI[10] * nt.z));
-        ro = camO; rtmin = 0.001f; rtmax = 10000.0f;
-        rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_PRIMARY;
-        hv = v3(0, 0, 0); pNormal = v3(0, 0, 0); pRough = v3(0, 0, 0); pRoughA = 0; pContrib = 0;
-        depth = 0; refDepth = 0; curIOR = 1.0f; recDepth = 0; sp = 0;
-    };
+    uint32_t guard = 0;
+    while(true) {
+        if(++guard > (1u << 22)) { if(lane == 0) atomicAdd(P.counters + 15, 1ull); break; }   // scheduler watchdog (never trips; a trip shows in rg_timings)
+        const uint32_t nActive = __popc(__ballot_sync(0xffffffffu, myCtx != kNoCtx));
 
-    auto storeCtx = [&](int k) {
-        cRay[k][0] = ro.x; cRay[k][1] = ro.y; cRay[k][2] = ro.z; cRay[k][3] = rd.x; cRay[k][4] = rd.y; cRay[k][5] = rd.z; cRay[k][6] = rtmin; cRay[k][7] = rtmax;
-        cPay[k][0] = hv.x; cPay[k][1] = hv.y; cPay[k][2] = hv.z; cPay[k][3] = depth; cPay[k][4] = curIOR; cPay[k][5] = refDepth;
-        cPay[k][6] = pNormal.x; cPay[k][7] = pNormal.y; cPay[k][8] = pNormal.z; cPay[k][9] = pRough.x; cPay[k][10] = pRough.y; cPay[k][11] = pRough.z;
-        cPay[k][12] = pRoughA; cPay[k][13] = pContrib;
-        cPix[k][0] = lx; cPix[k][1] = ly; cPix[k][2] = slot; cPix[k][3] = pslot; cPix[k][4] = sampleRays; cPix[k][5] = (uint32_t)sample;
-        cSel[k] = rayType | (missIndex << 2) | (rayKind << 4) | (recDepth << 8) | (sp << 16);
-    };
-    auto loadCtx = [&](int k) {
-        ro = v3(cRay[k][0], cRay[k][1], cRay[k][2]); rd = v3(cRay[k][3], cRay[k][4], cRay[k][5]); rtmin = cRay[k][6]; rtmax = cRay[k][7];
-        hv = v3(cPay[k][0], cPay[k][1], cPay[k][2]); depth = cPay[k][3]; curIOR = cPay[k][4]; refDepth = cPay[k][5];
-        pNormal = v3(cPay[k][6], cPay[k][7], cPay[k][8]); pRough = v3(cPay[k][9], cPay[k][10], cPay[k][11]); pRoughA = cPay[k][12]; pContrib = cPay[k][13];
-        lx = cPix[k][0]; ly = cPix[k][1]; slot = cPix[k][2]; pslot = cPix[k][3]; sampleRays = cPix[k][4]; sample = (int)cPix[k][5];
-        const int sel = cSel[k];
-        rayType = sel & 3; missIndex = (sel >> 2) & 3; rayKind = (sel >> 4) & 15; recDepth = (sel >> 8) & 255; sp = (sel >> 16) & 255;
-    };
+        // ---- REFILL: free contexts take new work items
+        if(!exhausted && freeCount && (freeCount >= RG_REFILL_THRESHOLD || (rayCount == 0u && hitCount == 0u))) {
+            const uint32_t n = freeCount < 32u ? freeCount : 32u;
+            uint32_t basew = 0;
+            if(lane == 0) basew = atomicAdd(P.workCounter, n);
+            basew = __shfl_sync(0xffffffffu, basew, 0);
+            const uint32_t c = lane < n ? W.freeQ[(freeHead + lane) & kQMask] : kNoCtx;
+            freeHead += n; freeCount -= n;
+            bool ok = false;
+            const uint32_t w = basew + lane;
+            if(c != kNoCtx && w < total) {
+                // w = ((slot position * S) + sample) * 32 + pixel in tile: consecutive items = one sample index of one 8x4 tile
+                const uint32_t l = w & 31u, pos = (w >> 5) / S;
+                const uint32_t sample = (w >> 5) % S;
+                const uint32_t j = P.tileOrder ? __ldg(P.tileOrder + pos) : pos;
+                const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
+                const uint32_t lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u), ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
+                if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
+                    ok = true;
+                    W.pix[0][c] = lx | (ly << 16); W.pix[1][c] = j * 32u + l; W.pix[2][c] = sample; W.pix[3][c] = 1u;
+                    // raygen.h:80-100
+                    const float2 off = aaOffset(numSamples, (int)sample);
+                    const float pcx = (float)lx + 0.5f + off.x, pcy = (float)ly + 0.5f + off.y;
+                    const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
+                    // target = projInverse * (d.x, d.y, 1, 1); direction = viewInverse * (normalize(target.xyz), 0)
+                    const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
+                                      (PI[2] * ddx + PI[6] * ddy) + (PI[10] + PI[14]));
+                    const V3 nt = normalize(tgt);
+                    W.ray[0][c] = camO.x; W.ray[1][c] = camO.y; W.ray[2][c] = camO.z;
+                    W.ray[3][c] = (VI[0] * nt.x + VI[4] * nt.y) + (VI[8] * nt.z);
+                    W.ray[4][c] = (VI[1] * nt.x + VI[5] * nt.y) + (VI[9] * nt.z);
+                    W.ray[5][c] = (VI[2] * nt.x + VI[6] * nt.y) + (VI[10] * nt.z);
+                    W.ray[6][c] = 0.001f; W.ray[7][c] = 10000.0f;
+                    W.pay[0][c] = 0.0f; W.pay[1][c] = 0.0f; W.pay[2][c] = 0.0f; W.pay[3][c] = 0.0f; W.pay[4][c] = 1.0f; W.pay[5][c] = 0.0f;
+                    W.sel[c] = (uint32_t)(RT_GENERIC | (0 << 2) | (CNT_PRIMARY << 4));   // recDepth 0, no frames
+                    float4* cold = ctxMem + (size_t)c * kCtxQuads + kMaxFrames * 8;
+                    cold[0] = make_float4(0, 0, 0, 0); cold[1] = make_float4(0, 0, 0, 0);
+                    s_cnt[CNT_PRIMARY][tid]++;
+                }
+            }
+            const uint32_t mOk = __ballot_sync(0xffffffffu, ok), mBack = __ballot_sync(0xffffffffu, c != kNoCtx && !ok);
+            if(ok) W.rayQ[(rayHead + rayCount + __popc(mOk & ltMask)) & kQMask] = (uint8_t)c;
+            rayCount += __popc(mOk);
+            if(c != kNoCtx && !ok) W.freeQ[(freeHead + freeCount + __popc(mBack & ltMask)) & kQMask] = (uint8_t)c;   // padding pixels: try the next item
+            freeCount += __popc(mBack);
+            if(basew + n >= total) exhausted = true;
+            __syncwarp();
+            continue;
+        }
+
+        // ---- SHADE one batch: closest hit or miss, then resume suspended frames until a new ray is issued
+        if(hitCount >= 32u || (hitCount && rayCount == 0u && nActive <= 32u - RG_EXIT_THRESHOLD)) {
+            const uint32_t nb = hitCount < 32u ? hitCount : 32u;
+            const uint32_t c = lane < nb ? W.hitQ[(hitHead + lane) & kQMask] : kNoCtx;
+            hitHead += nb; hitCount -= nb;
+            int outcome = 0;   // 1: a new ray is pending, 2: the sample ended
+            if(c != kNoCtx) {
+                float4* const fr = ctxMem + (size_t)c * kCtxQuads;
+                Hit h;
+                h.t = __uint_as_float(W.hit[0][c]); h.u = __uint_as_float(W.hit[1][c]); h.v = __uint_as_float(W.hit[2][c]); h.inst = W.hit[3][c]; h.prim = W.hit[4][c];
+                V3 ro = v3(W.ray[0][c], W.ray[1][c], W.ray[2][c]), rd = v3(W.ray[3][c], W.ray[4][c], W.ray[5][c]);
+                float rtmin = 0.0f, rtmax = 0.0f;
+                V3 hv = v3(W.pay[0][c], W.pay[1][c], W.pay[2][c]);
+                float depth = W.pay[3][c], curIOR = W.pay[4][c], refDepth = W.pay[5][c];
+                const uint32_t sel = W.sel[c];
+                int rayType = (int)(sel & 3u), missIndex = (int)((sel >> 2) & 3u), rayKind = (int)((sel >> 4) & 15u), recDepth = (int)((sel >> 8) & 255u);
+                int sp = (int)((sel >> 16) & 255u);
+                PixInfo pix;
+                pix.xy = W.pix[0][c]; pix.pslot = W.pix[1][c]; pix.sample = W.pix[2][c]; pix.rays = W.pix[3][c];
+                const bool ended = shadeContext<COUNT, MULTI>(P, K, h, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp, fr,
+                                                              pix, &s_cnt[CNT_SKY][tid], cntT) == 2;
+                if(ended) {
+                    outcome = 2;
+                } else {   // the next traceRayEXT of this sample
+                    outcome = 1;
+                    s_cnt[rayKind][tid]++;
+                    W.pix[3][c]++;
+                    W.ray[0][c] = ro.x; W.ray[1][c] = ro.y; W.ray[2][c] = ro.z; W.ray[3][c] = rd.x; W.ray[4][c] = rd.y; W.ray[5][c] = rd.z;
+                    W.ray[6][c] = rtmin; W.ray[7][c] = rtmax;
+                    W.pay[0][c] = hv.x; W.pay[1][c] = hv.y; W.pay[2][c] = hv.z; W.pay[3][c] = depth; W.pay[4][c] = curIOR; W.pay[5][c] = refDepth;
+                    W.sel[c] = (uint32_t)(rayType | (missIndex << 2) | (rayKind << 4) | (recDepth << 8) | (sp << 16));
+                }
+            }
+            const uint32_t mNew = __ballot_sync(0xffffffffu, outcome == 1), mEnd = __ballot_sync(0xffffffffu, outcome == 2);
+            if(outcome == 1) W.rayQ[(rayHead + rayCount + __popc(mNew & ltMask)) & kQMask] = (uint8_t)c;
+            rayCount += __popc(mNew);
+            if(outcome == 2) W.freeQ[(freeHead + freeCount + __popc(mEnd & ltMask)) & kQMask] = (uint8_t)c;
+            freeCount += __popc(mEnd);
+            __syncwarp();
+            continue;
+        }
+
+        if(nActive == 0u && rayCount == 0u) {   // nothing in flight, nothing to trace, nothing to shade (or it was shaded above)
+            if(exhausted || freeCount == 0u) break;
+            continue;   // not exhausted: the refill above takes whatever is free
+        }
+
+        // ---- TRAVERSE
+        while(true) {
+            const uint32_t mEmpty = __ballot_sync(0xffffffffu, myCtx == kNoCtx);
+            uint32_t nEmpty = __popc(mEmpty);
+            if(rayCount && nEmpty >= RG_FETCH_THRESHOLD) {   // hand the next rays to the empty lanes
+                const uint32_t take = nEmpty < rayCount ? nEmpty : rayCount;
+                const uint32_t r = __popc(mEmpty & ltMask);
+                if(myCtx == kNoCtx && r < take) {
+                    myCtx = W.rayQ[(rayHead + r) & kQMask];
+                    tmin = W.ray[6][myCtx];
+                    travInit(P, T, hit, W.ray[0][myCtx], W.ray[1][myCtx], W.ray[2][myCtx], W.ray[3][myCtx], W.ray[4][myCtx], W.ray[5][myCtx], W.ray[7][myCtx]);
+                }
+                rayHead += take; rayCount -= take; nEmpty -= take;
+            }
+            if(nEmpty == 32u || hitCount >= 32u) break;
+            if(rayCount == 0u && nEmpty >= RG_EXIT_THRESHOLD && hitCount) break;
+            if(!exhausted && freeCount >= RG_REFILL_THRESHOLD && rayCount == 0u) break;
+            bool done = false;
+            if(myCtx != kNoCtx) done = travStep<COUNT>(P, T, stack, hit, WorldRayPool{&W.ray[0][myCtx]}, tmin, cntT);
+            const uint32_t mDone = __ballot_sync(0xffffffffu, done);
+            if(mDone) {
+                if(done) {   // park the closest hit; the lane is free for the next ray
+                    W.hit[0][myCtx] = __float_as_uint(hit.t); W.hit[1][myCtx] = __float_as_uint(hit.u); W.hit[2][myCtx] = __float_as_uint(hit.v);
+                    W.hit[3][myCtx] = hit.inst; W.hit[4][myCtx] = hit.prim;
+                    W.hitQ[(hitHead + hitCount + __popc(mDone & ltMask)) & kQMask] = (uint8_t)myCtx;
+                    myCtx = kNoCtx;
+                }
+                hitCount += __popc(mDone);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- ray counters: warp reduce, one atomic per warp and counter
+#pragma unroll
+    for(int k = 0; k < CNT_N; ++k) {
+        if(!COUNT && k >= CNT_NODES) break;
+        unsigned long long v = k < CNT_NODES ? (unsigned long long)s_cnt[k][tid] : (unsigned long long)cntT[k];
+#pragma unroll
+        for(int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if(lane == 0 && v) atomicAdd(P.counters + k, v);
+    }
+}
+
+
+#ifndef RG_LANES_MIN_BLOCKS
+#define RG_LANES_MIN_BLOCKS 8
+#endif
+// The second scheduler, for COHERENT workloads: one context per lane, state in registers, frames in local memory.  A warp takes 32
+// consecutive work items (one sample index of one 8x4 tile), so its lanes trace neighbouring rays and then run the same shader
+// stage together; every lane traverses its ray to completion, then all shade.  Lanes whose sample ended are refilled from the
+// global counter 8 or more at a time.  On the example scene (BASELINE config 2) this keeps 21 of 32 lanes busy at 8 CTAs / SM and
+// beats the pool scheduler; on incoherent bounces (config 3) a warp waits for its longest ray and the pool wins.  rg_render
+// picks per scene by timing both (rg_api.cu).
+template <bool COUNT, bool MULTI>
+__global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const TraceParams P) {
+    __shared__ float s_ubo[48];
+    __shared__ uint32_t s_cnt[5][128];    // per lane: rays by kind + sky lookups
+    const uint32_t tid = threadIdx.x;
+    if(tid < 48) s_ubo[tid] = P.ubo[tid];
+#pragma unroll
+    for(int k = 0; k < 5; ++k) s_cnt[k][tid] = 0u;
+    __syncthreads();
+    const float* VI = s_ubo;       // viewInverse, column-major
+    const float* PI = s_ubo + 16;  // projInverse
+    const int numSamples = __float_as_int(s_ubo[35]);
+    int maxRec = __float_as_int(s_ubo[39]);
+    maxRec = maxRec > kMaxRecursions ? kMaxRecursions : maxRec;
+    ShadeConsts K;
+    K.L = v3(s_ubo[36], s_ubo[37], s_ubo[38]); K.maxRec = maxRec; K.strictIeee = (P.flags & RG_STRICT_IEEE) != 0; K.numSamples = numSamples; K.S = (uint32_t)numSamples;
+
+    const uint32_t lane = tid & 31;
+    const uint32_t tilesX = (P.dw + 7) / 8, tilesY = (P.dh + 3) / 4;
+    const uint32_t nTiles = tilesX * tilesY;
+    const uint32_t nChunks = (nTiles + kChunkTiles - 1) / kChunkTiles;
+    const uint32_t myChunks = nChunks > P.rank ? (nChunks - P.rank + P.world - 1) / P.world : 0u;
+    const uint32_t S = (uint32_t)numSamples;
+    const uint32_t total = myChunks * kChunkTiles * 32u * S;   // one work item per pixel SAMPLE
+
+    float4 frames[kCtxQuads];   // suspended shader invocations (local memory)
+    uint2 stack[kStackSize];
+    uint32_t cntT[CNT_N];
+    if(COUNT) {
+#pragma unroll
+        for(int k = 0; k < CNT_N; ++k) cntT[k] = 0;
+    }
+    bool exhausted = false, busy = false;
+    PixInfo pix;
+    pix.xy = 0; pix.pslot = 0; pix.sample = 0; pix.rays = 0;
+    V3 hv = v3(0, 0, 0), ro = v3(0, 0, 0), rd = v3(0, 0, 0);
+    float depth = 0, curIOR = 1.0f, refDepth = 0, rtmin = 0, rtmax = 0;
+    int recDepth = 0, sp = 0, rayType = RT_GENERIC, missIndex = 0, rayKind = CNT_PRIMARY;
+    const V3 camO = v3((VI[0] * 0.0f + VI[4] * 0.0f) + (VI[8] * 0.0f + VI[12] * 1.0f), (VI[1] * 0.0f + VI[5] * 0.0f) + (VI[9] * 0.0f + VI[13] * 1.0f),
+                       (VI[2] * 0.0f + VI[6] * 0.0f) + (VI[10] * 0.0f + VI[14] * 1.0f));
 
     while(true) {
-        // ---- refill idle contexts (warp vote + prefix compaction over one atomic per context index)
-        bool mine = false;
-#pragma unroll 1
-        for(int k = 0; k < K; ++k) {
-            const uint32_t idle = __ballot_sync(0xffffffffu, cStatus[k] == CS_IDLE);
-            if(idle && !exhausted && (idle == 0xffffffffu || __popc(idle) >= 8)) {
-                const int n = __popc(idle), leader = __ffs(idle) - 1;
-                uint32_t basew = 0;
-                if((int)lane == leader) basew = atomicAdd(P.workCounter, (uint32_t)n);
-                basew = __shfl_sync(0xffffffffu, basew, leader);
-                if(cStatus[k] == CS_IDLE) {
-                    const uint32_t w = basew + __popc(idle & ((1u << lane) - 1u));
-                    if(w < total) {
-                        // w = ((slot position * S) + sample) * 32 + lane: a warp works on one sample index of one 8x4 tile
-                        const uint32_t l = w & 31u, pos = (w >> 5) / S;
-                        sample = (int)((w >> 5) % S);
-                        const uint32_t j = P.tileOrder ? __ldg(P.tileOrder + pos) : pos;
-                        slot = j; pslot = j * 32u + l; sampleRays = 0;
-                        const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
-                        lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u); ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
-                        if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
-                            primaryRay(sample);
-                            storeCtx(k);
-                            cStatus[k] = CS_RAY;
-                        }
+        // ---- refill idle lanes (warp vote + prefix compaction over one atomic)
+        const uint32_t idle = __ballot_sync(0xffffffffu, !busy);
+        if(!exhausted && __popc(idle) >= 8) {
+            const int n = __popc(idle), leader = __ffs(idle) - 1;
+            uint32_t basew = 0;
+            if((int)lane == leader) basew = atomicAdd(P.workCounter, (uint32_t)n);
+            basew = __shfl_sync(0xffffffffu, basew, leader);
+            if(!busy) {
+                const uint32_t w = basew + __popc(idle & ((1u << lane) - 1u));
+                if(w < total) {
+                    const uint32_t l = w & 31u, pos = (w >> 5) / S;
+                    const uint32_t sample = (w >> 5) % S;
+                    const uint32_t j = P.tileOrder ? __ldg(P.tileOrder + pos) : pos;
+                    const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
+                    const uint32_t lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u), ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
+                    if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
+                        busy = true;
+                        pix.xy = lx | (ly << 16); pix.pslot = j * 32u + l; pix.sample = sample; pix.rays = 1u;
+                        // raygen.h:80-100
+                        const float2 off = aaOffset(numSamples, (int)sample);
+                        const float pcx = (float)lx + 0.5f + off.x, pcy = (float)ly + 0.5f + off.y;
+                        const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
+                        const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
+                                          (PI[2] * ddx + PI[6] * ddy) + (PI[10] + PI[14]));
+                        const V3 nt = normalize(tgt);
+                        rd = v3((VI[0] * nt.x + VI[4] * nt.y) + (VI[8] * nt.z), (VI[1] * nt.x + VI[5] * nt.y) + (VI[9] * nt.z), (VI[2] * nt.x + VI[6] * nt.y) + (VI[10] * nt.z));
+                        ro = camO; rtmin = 0.001f; rtmax = 10000.0f;
+                        rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_PRIMARY;
+                        hv = v3(0, 0, 0); depth = 0; refDepth = 0; curIOR = 1.0f; recDepth = 0; sp = 0;
+                        frames[kMaxFrames * 8] = make_float4(0, 0, 0, 0); frames[kMaxFrames * 8 + 1] = make_float4(0, 0, 0, 0);
+                        s_cnt[CNT_PRIMARY][tid]++;
                     }
                 }
-                if(basew + (uint32_t)n >= total) exhausted = true;
             }
-            mine |= cStatus[k] != CS_IDLE;
+            if(basew + (uint32_t)n >= total) exhausted = true;
         }
-        if(!__any_sync(0xffffffffu, mine)) { if(exhausted) break; continue; }
+        if(!__any_sync(0xffffffffu, busy)) { if(exhausted) break; continue; }
 
-        // ---- trace every pending ray of this lane, one after the other
-#pragma unroll 1
-        for(int k = 0; k < K; ++k) {
-            if(cStatus[k] != CS_RAY) continue;
+        if(busy) {
+            // ---- trace the lane's ray to completion
             Hit hit;
-            const int kind = (cSel[k] >> 4) & 15;
-            cnt[kind]++;
-            cPix[k][4]++;
-            traverse<COUNT>(P, cRay[k][0], cRay[k][1], cRay[k][2], cRay[k][3], cRay[k][4], cRay[k][5], cRay[k][6], cRay[k][7], hit, cnt);
-            cHit[k][0] = __float_as_uint(hit.t); cHit[k][1] = __float_as_uint(hit.u); cHit[k][2] = __float_as_uint(hit.v); cHit[k][3] = hit.inst; cHit[k][4] = hit.prim;
-            if(kind == CNT_PRIMARY && cPix[k][5] == 0u && P.idInst) {
-                const int qx = (int)cPix[k][0] - P.sx0, qy = (int)cPix[k][1] - P.sy0;
-                if(qx >= 0 && qy >= 0 && qx < P.sw && qy < P.sh) { P.idInst[qy * P.sw + qx] = hit.inst; P.idPrim[qy * P.sw + qx] = hit.prim; }
-            }
-            cStatus[k] = CS_HIT;
-        }
-
-        // ---- shade every finished ray: context index by context index, so the lanes of the warp run the hit / miss programs together
-#pragma unroll 1
-        for(int k = 0; k < K; ++k) {
-            if(cStatus[k] != CS_HIT) continue;
-            loadCtx(k);
-            Hit hit;
-            hit.t = __uint_as_float(cHit[k][0]); hit.u = __uint_as_float(cHit[k][1]); hit.v = __uint_as_float(cHit[k][2]); hit.inst = cHit[k][3]; hit.prim = cHit[k][4];
-            const bool found = hit.inst != kInvalid;
-            float (*fr)[F_WORDS] = frames[k];
-            bool active = true;
-                // ---- shade: closest hit or miss, then resume suspended frames until a new ray is issued
-                bool issue = false;   // a new ray is pending
-                if(found) {
-                    // closesthit.rchit:96-109
-                    const uint4 is3 = __ldg(reinterpret_cast<const uint4*>(P.instShade + hit.inst) + 3);
-                    const uint32_t vtxOff = is3.x, idxOff = is3.y, matOff = is3.z;
-                    const uint32_t i0 = __ldg(P.indices + idxOff + 3 * hit.prim), i1 = __ldg(P.indices + idxOff + 3 * hit.prim + 1),
-                                   i2 = __ldg(P.indices + idxOff + 3 * hit.prim + 2);
-                    const float4 v0p = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0));
-                    const float4 n0 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i0) + 1), n1 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i1) + 1),
-                                 n2 = __ldg(P.vertices + 2 * (size_t)(vtxOff + i2) + 1);
-                    const float4* mp = P.materials + 4 * (size_t)(matOff + __float_as_uint(v0p.w));
-                    const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2), m3 = __ldg(mp + 3);
-                    V3 diffuse = v3(m0.x, m0.y, m0.z), specular = v3(m1.x, m1.y, m1.z);
-                    const float transparency = m0.w; float reflectivity = m1.w;
-                    const float roughness = m2.x, ior = m2.y, emission = m3.x;
-                    const uint32_t effectId = __float_as_uint(m2.z), rayConsumption = __float_as_uint(m2.w);
-
-                    const float b0 = 1.0f - hit.u - hit.v;
-                    const V3 origin = ro + rd * hit.t;                                        // :114
-                    const V3 vn = v3(n0.x, n0.y, n0.z) * b0 + v3(n1.x, n1.y, n1.z) * hit.u + v3(n2.x, n2.y, n2.z) * hit.v;  // :117
-                    const float4* ow = reinterpret_cast<const float4*>(P.instShade + hit.inst);
-                    const float4 o0 = __ldg(ow), o1 = __ldg(ow + 1), o2 = __ldg(ow + 2);
-                    V3 n = normalize(v3(o0.x * vn.x + o0.y * vn.y + o0.z * vn.z, o1.x * vn.x + o1.y * vn.y + o1.z * vn.z, o2.x * vn.x + o2.y * vn.y + o2.z * vn.z));  // :118-119
-
-                    if(effectId == 1u) {  // gridEffect, :74-91
-                        const float aa = (refDepth + hit.t + 8.0f) / 30.0f;
-                        const float aa2 = aa / 2.0f;
-                        float minmod = glmin(fabsf(glmod((origin.x + 1000.0f) * 10.0f + aa2, 20.0f) - aa2), fabsf(glmod((origin.z + 1000.0f) * 10.0f + aa2, 20.0f) - aa2));
-                        if(minmod < aa2) {
-                            minmod -= aa2 - (aa * aa) / 3.0f;
-                            minmod *= 3.0f / (aa * aa);
-                            const float f = mixf(aa / 10.0f, 1.0f, minmod);
-                            diffuse = diffuse * f; specular = specular * f; reflectivity *= f;
-                        }
-                        if(glmod((origin.x + 1000.0f) * 5.0f, 20.0f) < 10.0f && glmod((origin.z + 1000.0f) * 5.0f, 20.0f) < 10.0f) reflectivity *= 1.5f;
-                    }
-
-                    if(rayType == RT_SHADOW_INTERNAL) {  // :125-152
-                        const float thick = clampf(hit.t * (1.0f - transparency) * 10.0f, 0.0f, 1.0f);
-                        const V3 nd = normalize(v3(1.1f - diffuse.x, 1.1f - diffuse.y, 1.1f - diffuse.z));
-                        const V3 shadowCol = hv - mix3(v3(0, 0, 0), v3(nd.x + 0.1f, nd.y + 0.1f, nd.z + 0.1f), thick);
-                        if(recDepth < maxRec) {
-                            float* f = fr[sp++];
-                            f[F_ORG] = shadowCol.x; f[F_ORG + 1] = shadowCol.y; f[F_ORG + 2] = shadowCol.z;
-                            f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
-                            f[F_N] = n.x; f[F_N + 1] = n.y; f[F_N + 2] = n.z;
-                            f[F_IOR] = ior; f[F_FLAGS] = __int_as_float(FR_SHI); f[F_RECDEPTH] = __int_as_float(recDepth);
-                            rayType = RT_SHADOW_TRACE; recDepth++;
-                            ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 0; rayKind = CNT_SHADOW;   // rd unchanged (T3)
-                            issue = true;
-                        } else {
-                            hv = shadowCol * 0.4f;
-                        }
-                    } else if(rayType == RT_SHADOW_TRACE) {  // :153-166
-                        if(transparency > 0.0f) {
-                            if(recDepth < maxRec) {   // T2: nothing to do after the child returns except recDepth--, which every
-                                rayType = RT_SHADOW_INTERNAL; recDepth++;                 // resuming frame restores from its own copy
-                                ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
-                                issue = true;
-                            }
-                        } else {
-                            hv = hv * mixf(0.4f, 0.8f, clampf(logf(hit.t) / 8.0f, 0.0f, 1.0f));
-                        }
-                    } else {  // RT_GENERIC, :168-268
-                        if(COUNT) cnt[CNT_GENHIT]++;
-                        const bool frontFacing = dot(-rd, n) > 0.0f;
-                        if(!frontFacing) n = normalize(-n);
-                        const float ndl = dot(-L, n);
-                        V3 baseColor = diffuse * glmax(ndl, 0.2f);
-                        float* f = fr[sp++];
-                        f[F_ORG] = origin.x; f[F_ORG + 1] = origin.y; f[F_ORG + 2] = origin.z;
-                        f[F_DIR] = rd.x; f[F_DIR + 1] = rd.y; f[F_DIR + 2] = rd.z;
-                        f[F_N] = n.x; f[F_N + 1] = n.y; f[F_N + 2] = n.z;
-                        f[F_T] = hit.t;
-                        f[F_DIFF] = diffuse.x; f[F_DIFF + 1] = diffuse.y; f[F_DIFF + 2] = diffuse.z;
-                        f[F_SPEC] = specular.x; f[F_SPEC + 1] = specular.y; f[F_SPEC + 2] = specular.z;
-                        f[F_TRANSP] = transparency; f[F_REFL] = reflectivity; f[F_ROUGH] = roughness; f[F_IOR] = ior; f[F_EMIS] = emission;
-                        f[F_RECDEPTH] = __int_as_float(recDepth);
-                        int stage;
-                        bool shadowPending = false;
-                        if(ndl > 0.07f) {   // :188
-                            if(recDepth < maxRec) {
-                                hv = v3(1.0f, 1.0f, 1.0f);
-                                rayType = RT_SHADOW_TRACE; recDepth++;
-                                ro = origin; rd = -L; rtmin = 0.1f; rtmax = 1000.0f; missIndex = 1; rayKind = CNT_SHADOW;
-                                shadowPending = true;
-                            }
-                            // recDepth >= max: shadowColor stays 1
-                        } else {
-                            const float sm = transparency * transparency;   // pow(t, 2)
-                            const V3 sc = transparency < 1.0f ? mix3(v3(1, 1, 1), diffuse * sm, transparency) : v3(0.4f, 0.4f, 0.4f);
-                            baseColor = baseColor * sc;
-                        }
-                        if(shadowPending) { stage = ST_SHADOW_RET; issue = true; }
-                        else { baseColor = baseColor + diffuse * emission; stage = ST_TRY_REFLECT; }
-                        f[F_BASE] = baseColor.x; f[F_BASE + 1] = baseColor.y; f[F_BASE + 2] = baseColor.z;
-                        f[F_FLAGS] = __int_as_float(FR_GEN | (stage << 8) | ((frontFacing ? 1 : 0) << 16) | ((int)(rayConsumption & 0xffu) << 20));
-                    }
-                } else {
-                    if(missIndex == 0) {  // miss.rmiss:76-83
-                        const V3 sky = skyColor(rd, L, strictIeee);
-                        hv = sky; depth = 10000.0f;
-                        if(sp == 0 && recDepth == 0) { pRough = sky; pRoughA = 0.0f; }   // roughValue is only observable for a primary miss
-                    } else {              // shadowMiss.rmiss:33
-                        hv = v3(1.0f, 1.0f, 1.0f);
-                    }
-                }
-
-                // ---- resume suspended frames (the code after each traceRayEXT returns)
-                while(!issue) {
-                    if(sp == 0) {   // raygen.h:105-111: the sample's trace returned
-                        if(P.tileCost) atomicAdd(P.tileCost + slot, sampleRays);
-                        V3 accColor = hv, accNormal = pNormal, accRough = pRough;
-                        float accRoughA = pRoughA, accContrib = pContrib, accDepth = depth;
-                        bool last = true;
-                        if(S > 1u) {   // park this sample; the lane finishing the pixel's last sample sums all of them in order
-                            float4* rec = P.sampleScratch + 3 * ((size_t)pslot * S + (uint32_t)sample);
-                            __stcg(rec, make_float4(hv.x, hv.y, hv.z, pContrib));
-                            __stcg(rec + 1, make_float4(pNormal.x, pNormal.y, pNormal.z, depth));
-                            __stcg(rec + 2, make_float4(pRough.x, pRough.y, pRough.z, pRoughA));
-                            __threadfence();
-                            last = atomicAdd(P.sampleDone + pslot, 1u) == S - 1u;
-                            if(last) {
-                                __threadfence();
-                                P.sampleDone[pslot] = 0u;   // ready for the next frame
-                                accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
-                                const float4* all = P.sampleScratch + 3 * (size_t)pslot * S;
-                                for(uint32_t i = 0; i < S; ++i) {   // raygen.h:105-111 in the loop's order
-                                    const float4 a = __ldcg(all + 3 * i), b = __ldcg(all + 3 * i + 1), c = __ldcg(all + 3 * i + 2);
-                                    accColor = accColor + v3(a.x, a.y, a.z); accNormal = accNormal + v3(b.x, b.y, b.z);
-                                    accRough = accRough + v3(c.x, c.y, c.z); accRoughA += c.w; accContrib += a.w; accDepth += b.w;
-                                }
-                            }
-                        }
-                        if(last) {      // raygen.h:114 + raygen.rgen:35-38
-                            const float inv = (float)numSamples;
-                            const uint2 ob = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
-                            const uint2 on = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
-                            const uint2 orr = packHalf4(accRough.x / inv, accRough.y / inv, accRough.z / inv, accRoughA / inv);
-                            // the pixel goes to every GPU whose post-chain rectangle contains it (own images or peer memory over NVLink)
-        #pragma unroll
-                            for(int q = 0; q < (MULTI ? kMaxPeers : 1); ++q) {   // static indices: the targets stay in the constant bank
-                                if((uint32_t)q < P.nTargets) {
-                                    const int qx = (int)lx - P.targets[q].x0, qy = (int)ly - P.targets[q].y0;
-                                    if(qx >= 0 && qy >= 0 && qx < P.targets[q].w && qy < P.targets[q].h) {
-                                        const size_t o = (size_t)qy * P.targets[q].w + qx;
-                                        P.targets[q].base[o] = ob; P.targets[q].normal[o] = on; P.targets[q].rough[o] = orr;
-                                    }
-                                }
-                            }
-                        }
-                        active = false;
-                        break;
-                    }
-                    float* f = fr[sp - 1];
-                    const int flags = __float_as_int(f[F_FLAGS]);
-                    recDepth = __float_as_int(f[F_RECDEPTH]);   // undoes every recDepth++ / += rayConsumption below this frame
-                    if((flags & 0xff) == FR_SHI) {   // closesthit.rchit:136-146, after T3 returned
-                        V3 shadowCol = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]);
-                        if(depth < 1000.0f) {
-                            hv = hv * shadowCol;
-                        } else {
-                            const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                            const V3 dir = refract3(D, n, f[F_IOR]);
-                            const float dp = dot(L, dir);
-                            const float dp2 = dp * dp;
-                            shadowCol = shadowCol * (dp2 * dp2 * dp + 0.75f);   // pow(x, 5)
-                            cnt[CNT_SKY]++;   // T4: cull mask 0 -> always miss 0
-                            const V3 sky = skyColor(-dir, L, strictIeee);
-                            depth = 10000.0f;
-                            hv = shadowCol + sky * 0.1f;
-                        }
-                        sp--;
-                        continue;
-                    }
-                    int stage = (flags >> 8) & 0xff;
-                    const bool frontFacing = ((flags >> 16) & 1) != 0;
-                    const int rc = (flags >> 20) & 0xff;
-                    if(stage == ST_SHADOW_RET) {   // :196-197 then :254-255
-                        const V3 diffuse = v3(f[F_DIFF], f[F_DIFF + 1], f[F_DIFF + 2]);
-                        V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]) * hv + diffuse * f[F_EMIS];
-                        f[F_BASE] = base.x; f[F_BASE + 1] = base.y; f[F_BASE + 2] = base.z;
-                        stage = ST_TRY_REFLECT;
-                    }
-                    if(stage == ST_TRY_REFLECT) {  // :207-221
-                        if(recDepth < maxRec && f[F_REFL] > 0.0f) {
-                            const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                            recDepth += rc; refDepth += f[F_T];
-                            ro = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]); rd = reflect3(D, n); rtmin = 0.01f; rtmax = 1000.0f;
-                            rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFLECT;
-                            f[F_FLAGS] = __int_as_float((flags & ~0xff00) | (ST_REFLECT_RET << 8));
-                            issue = true;
-                            break;
-                        }
-                        f[F_RCOL] = 1.0f; f[F_RCOL + 1] = 1.0f; f[F_RCOL + 2] = 1.0f; f[F_RDEPTH] = 0.0f;
-                        stage = ST_TRY_REFRACT;
-                    }
-                    if(stage == ST_REFLECT_RET) {
-                        f[F_RCOL] = hv.x * f[F_SPEC]; f[F_RCOL + 1] = hv.y * f[F_SPEC + 1]; f[F_RCOL + 2] = hv.z * f[F_SPEC + 2];
-                        f[F_RDEPTH] = depth;
-                        stage = ST_TRY_REFRACT;
-                    }
-                    V3 refractColor = v3(1.0f, 1.0f, 1.0f);
-                    if(stage == ST_TRY_REFRACT) {  // :224-251
-                        if(recDepth < maxRec && f[F_TRANSP] > 0.0f) {
-                            const V3 D = v3(f[F_DIR], f[F_DIR + 1], f[F_DIR + 2]), n = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                            const float ior = f[F_IOR];
-                            const float eta = frontFacing ? curIOR / ior : ior / 1.0f;
-                            recDepth++;
-                            curIOR = frontFacing ? ior : 1.0f;
-                            ro = v3(f[F_ORG], f[F_ORG + 1], f[F_ORG + 2]); rd = refract3(D, n, eta); rtmin = 0.01f; rtmax = 1000.0f;
-                            rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFRACT;
-                            f[F_FLAGS] = __int_as_float((flags & ~0xff00) | ((frontFacing ? ST_REFRACT_RET_FRONT : ST_REFRACT_RET_BACK) << 8));
-                            issue = true;
-                            break;
-                        }
-                        stage = ST_COMBINE;
-                    } else if(stage == ST_REFRACT_RET_FRONT) {
-                        refractColor = hv;
-                    } else if(stage == ST_REFRACT_RET_BACK) {
-                        const V3 diffuse = v3(f[F_DIFF], f[F_DIFF + 1], f[F_DIFF + 2]);
-                        refractColor = mix3(v3(1, 1, 1), diffuse, logf(1.0f + f[F_T])) * hv;
-                    }
-                    // combine, :254-267
-                    {
-                        const V3 base = v3(f[F_BASE], f[F_BASE + 1], f[F_BASE + 2]);
-                        const V3 reflectColor = v3(f[F_RCOL], f[F_RCOL + 1], f[F_RCOL + 2]);
-                        const float transparency = f[F_TRANSP], reflectivity = f[F_REFL], roughness = f[F_ROUGH];
-                        const float totalContrib = glmax(transparency, reflectivity);
-                        float weight = reflectivity / (transparency + reflectivity);
-                        if(!strictIeee && (transparency + reflectivity) == 0.0f) weight = 0.0f;   // SURVEY hazard 8
-                        const V3 roughCol = mix3(refractColor, reflectColor, weight);
-                        hv = mix3(base, roughCol, totalContrib);
-                        if(recDepth == 0) {
-                            hv = base;
-                            pNormal = v3(f[F_N], f[F_N + 1], f[F_N + 2]);
-                            pRough = roughCol; pRoughA = glmin((f[F_RDEPTH] / 50.0f) * roughness, roughness / 2.1f);
-                            pContrib = totalContrib;
-                        }
-                        depth = f[F_T];
-                        sp--;
-                    }
-                }
-            storeCtx(k);
-            cStatus[k] = active ? CS_RAY : CS_IDLE;
+            Trav T;
+            const WorldRayRegs wr{{ro.x, ro.y, ro.z}, {rd.x, rd.y, rd.z}, rtmax};
+            travInit(P, T, hit, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmax);
+            while(!travStep<COUNT>(P, T, stack, hit, wr, rtmin, cntT)) {}
+            // ---- shade: hit / miss program, then the frames that resume, up to the next traceRayEXT
+            const int outcome = shadeContext<COUNT, MULTI>(P, K, hit, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp, frames,
+                                                           pix, &s_cnt[CNT_SKY][tid], cntT);
+            if(outcome == 1) { s_cnt[rayKind][tid]++; pix.rays++; }
+            else busy = false;
         }
     }
 
@@ -784,7 +993,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace(const TraceP
 #pragma unroll
     for(int k = 0; k < CNT_N; ++k) {
         if(!COUNT && k >= CNT_NODES) break;
-        unsigned long long v = cnt[k];
+        unsigned long long v = k < CNT_NODES ? (unsigned long long)s_cnt[k][tid] : (unsigned long long)cntT[k];
 #pragma unroll
         for(int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if(lane == 0 && v) atomicAdd(P.counters + k, v);
@@ -796,8 +1005,12 @@ __global__ void k_trace_rays(const TraceParams P, const float* __restrict__ rays
     if(i >= n) return;
     const float* q = rays8 + 8 * (size_t)i;
     Hit hit;
+    Trav T;
+    uint2 stack[kStackSize];
     uint32_t cnt[CNT_N];
-    traverse<false>(P, q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7], hit, cnt);
+    const WorldRayRegs wr{{q[0], q[1], q[2]}, {q[3], q[4], q[5]}, q[7]};
+    travInit(P, T, hit, q[0], q[1], q[2], q[3], q[4], q[5], q[7]);
+    while(!travStep<false>(P, T, stack, hit, wr, q[6], cnt)) {}
     tuv[3 * i] = hit.t; tuv[3 * i + 1] = hit.u; tuv[3 * i + 2] = hit.v;
     instPrim[2 * i] = hit.inst; instPrim[2 * i + 1] = hit.prim;
 }
@@ -845,22 +1058,33 @@ void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, cudaStre
     if(nSlots) k_order_tiles<<<1, 1024, 0, stream>>>(cost, nSlots, order);
 }
 
-template <bool COUNT, bool MULTI, int K>
-static void launchTraceK(const TraceParams& p, int numSms, cudaStream_t stream) {
-    // persistent grid: a multiple of the SM count; resident CTAs per SM limited by registers / local memory
-    int perSm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_trace<COUNT, MULTI, K>, 128, 0);
-    if(perSm < 1) perSm = 1;
-    k_trace<COUNT, MULTI, K><<<numSms * perSm, 128, 0, stream>>>(p);
+template <bool COUNT, bool MULTI, bool POOL>
+static int tracePerSm() {   // persistent grid: a multiple of the SM count; resident CTAs per SM limited by registers / shared memory
+    static int perSm = [] {
+        int v = 0;
+        if(POOL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_pool<COUNT, MULTI>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_lanes<COUNT, MULTI>, 128, 0);
+        return v < 1 ? 1 : v;
+    }();
+    return perSm;
 }
 
-void launchTrace(const TraceParams& p, int numSms, cudaStream_t stream) {
-    static int contexts = [] { const char* e = getenv("RGB200_LANE_CONTEXTS"); const int v = e ? atoi(e) : RG_LANE_CONTEXTS; return v == 2 || v == 4 ? v : 1; }();
-    if(p.flags & RG_COUNT_TRAVERSAL) { launchTraceK<true, true, 1>(p, numSms, stream); return; }
-    const bool multi = p.nTargets > 1;
-    if(contexts == 4) { if(multi) launchTraceK<false, true, 4>(p, numSms, stream); else launchTraceK<false, false, 4>(p, numSms, stream); }
-    else if(contexts == 2) { if(multi) launchTraceK<false, true, 2>(p, numSms, stream); else launchTraceK<false, false, 2>(p, numSms, stream); }
-    else { if(multi) launchTraceK<false, true, 1>(p, numSms, stream); else launchTraceK<false, false, 1>(p, numSms, stream); }
+template <bool COUNT, bool MULTI>
+static void launchTraceK(const TraceParams& p, int numSms, bool pool, cudaStream_t stream) {
+    if(pool) k_trace_pool<COUNT, MULTI><<<numSms * tracePerSm<COUNT, MULTI, true>(), 128, 0, stream>>>(p);
+    else k_trace_lanes<COUNT, MULTI><<<numSms * tracePerSm<COUNT, MULTI, false>(), 128, 0, stream>>>(p);
+}
+
+size_t tracePoolBytes(int numSms) {   // frames of every context of every warp of the largest persistent pool grid
+    int perSm = tracePerSm<false, false, true>();
+    if(tracePerSm<false, true, true>() > perSm) perSm = tracePerSm<false, true, true>();
+    if(tracePerSm<true, true, true>() > perSm) perSm = tracePerSm<true, true, true>();
+    return sizeof(float4) * (size_t)numSms * perSm * 4u * kPoolCtx * kCtxQuads;
+}
+
+void launchTrace(const TraceParams& p, int numSms, bool pool, cudaStream_t stream) {
+    if(p.flags & RG_COUNT_TRAVERSAL) { launchTraceK<true, true>(p, numSms, pool, stream); return; }
+    if(p.nTargets > 1) launchTraceK<false, true>(p, numSms, pool, stream); else launchTraceK<false, false>(p, numSms, pool, stream);
 }
 
 void launchTraceRays(const TraceParams& p, const float* rays8, uint32_t n, float* tuv, uint32_t* instPrim, cudaStream_t stream) {

@@ -6,9 +6,11 @@ namespace rg {
 
 constexpr int kMaxRecursions = 8;   // BASELINE config 3 uses 8; the reference UI allows 0..7 (render_system.cpp:264)
 constexpr int kMaxFrames = kMaxRecursions + 1;  // a generic hit entered at recDepth >= max still gets a frame
-constexpr int kStackSize = 40;
+constexpr int kStackSize = 48;     // traversal stack entries (uint2) per ray: TLAS + BLAS + postponed primitive groups
+constexpr int kPoolCtx = 64;       // ray-tree contexts (pixel samples in progress) per warp
+constexpr int kCtxQuads = kMaxFrames * 8 + 2;   // float4 per context in global memory: 8 per frame + the payload members only observable at recDepth 0
 constexpr int kMaxPeers = 8;        // GPUs of one node
-constexpr uint32_t kChunkTiles = 16; // tiles per round-robin chunk in partitioned mode      // traversal stack entries (uint2) per ray: TLAS + BLAS
+constexpr uint32_t kChunkTiles = 16; // tiles per round-robin chunk in partitioned mode
 
 struct TraceParams {
     const Node8* tlasNodes;
@@ -40,12 +42,15 @@ struct TraceParams {
     // Heavy-first scheduling: tiles are handed out in the order of tileOrder (built from last frame's per-tile ray counts,
     // most expensive first) so the long ray trees start early and overlap with the bulk; tileCost collects this frame's counts.
     const uint32_t* tileOrder; uint32_t* tileCost;
+    float4* ctxPool;   // tracePoolBytes(): frames of the per-warp context pools
     uint32_t* workCounter;
     unsigned long long* counters;  // 5 ray kinds + nodes, tris, instances
     uint32_t flags;
 };
 
-void launchTrace(const TraceParams& p, int numSms, cudaStream_t stream);
+// pool: per-warp context pools with ray / hit queues (incoherent bounces); otherwise one context per lane (coherent scenes)
+void launchTrace(const TraceParams& p, int numSms, bool pool, cudaStream_t stream);
+size_t tracePoolBytes(int numSms);
 // number of tile slots of this rank's share of the trace domain (sizes tileOrder / tileCost / sampleDone / sampleScratch)
 uint32_t traceShareTiles(uint32_t dw, uint32_t dh, uint32_t rank, uint32_t world);
 // order[] = tile slots sorted by descending cost class (8 classes relative to the mean); cost[] is cleared for the next frame

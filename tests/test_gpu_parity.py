@@ -90,10 +90,13 @@ def test_morton_sort_bit_exact_tlas_10k_instances(rgmod, O, S):
     assert np.array_equal(order, ref_order) and np.array_equal(keys, codes[ref_order])
 
 
+@pytest.mark.parametrize("sched", ["lanes", "pool"])
 @pytest.mark.parametrize("W,H,ns", [(640, 360, 1), (1920, 1080, 4), (100, 60, 2), (333, 187, 3)])
-def test_example_scene_frame_parity(rgmod, O, S, example_scene, oracle_example, W, H, ns):
+def test_example_scene_frame_parity(rgmod, O, S, example_scene, oracle_example, W, H, ns, sched):
+    """Both trace schedulers (one context per lane / per-warp context pools) against the oracle."""
     ubo = S.example_ubo(W, H, num_samples=ns, max_recursions=5)
     rt = rgmod.Raytracer(W, H)
+    rt.set_trace_scheduler(rgmod.RG_SCHED_POOL if sched == "pool" else rgmod.RG_SCHED_LANES)
     rt.load_scene(example_scene)
     rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
     ref = oracle_example.render(ubo, W, H, O.FXAA)
@@ -216,12 +219,34 @@ def test_sphere_grid_recursion_8_parity(rgmod, O, S):
         # look at the small grid
         cam = S.Transform(position=np.array([14, 9, -8], np.float32)); cam.look_at(np.array([6.25, 1, 6.25], np.float32))
         ubo = S.make_ubo(cam.to_mat4_colmajor(), S.proj_inverse(W, H), 1, 8)
-        rt = rgmod.Raytracer(W, H)
-        rt.load_scene(sd)
-        rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
         ref = O.OracleScene(sd).render(ubo, W, H, O.FXAA)
-        _check_frame(rt, ref, rgmod, f"spheres6 flat={flat}")
+        for sched in (rgmod.RG_SCHED_LANES, rgmod.RG_SCHED_POOL):
+            rt = rgmod.Raytracer(W, H)
+            rt.set_trace_scheduler(sched)
+            rt.load_scene(sd)
+            rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
+            _check_frame(rt, ref, rgmod, f"spheres6 flat={flat} sched={sched}")
+            assert rt.timings()["trace_scheduler"] == sched
+            rt.close()
         assert ref["counters"]["refract"] > 1000 and ref["counters"]["reflect"] > 10000
+
+
+def test_auto_scheduler_switches_without_changing_the_image(rgmod, S):
+    """RG_SCHED_AUTO times both trace kernels on consecutive frames and keeps the faster one: every frame must be bit-identical."""
+    W, H = 480, 270
+    sd, vi = S.sphere_grid_scene(8)
+    ubo = S.make_ubo(vi, S.proj_inverse(W, H), 2, 8)
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(sd)
+    frames, used = [], []
+    for _ in range(6):
+        rt.render_frame(ubo, rgmod.RG_FXAA)
+        frames.append(rt.read_rgba8().copy())
+        used.append(rt.timings()["trace_scheduler"])
+    assert set(used) == {rgmod.RG_SCHED_LANES, rgmod.RG_SCHED_POOL}, used   # both were probed
+    for f in frames[1:]:
+        assert np.array_equal(f, frames[0])
+    rt.close()
 
 
 def test_per_frame_tlas_rebuild_animated(rgmod, O, S):

@@ -19,7 +19,7 @@ for i in range(8):
     tm = rt.timings()
     if i >= 3: ts.append((tm["rt_only_ms"], tm["postproc_ms"], tm["as_build_ms"]))
 t = np.median(np.array(ts), axis=0)
-print(f"{os.environ.get('RGB200_LIB','default'):40s} {wl}: trace {t[0]:.3f} ms  post {t[1]:.3f} ms  as {t[2]:.3f} ms  rays {tm['rays']}  {tm['rays']/t[0]/1e3:.0f} Mrays/s")
+print(f"{os.environ.get('RGB200_LIB','default'):40s} sched={os.environ.get('RGB200_TRACE_SCHED','auto')}->{tm['trace_scheduler']} {wl}: trace {t[0]:.3f} ms  post {t[1]:.3f} ms  as {t[2]:.3f} ms  rays {tm['rays']}  {tm['rays']/t[0]/1e3:.0f} Mrays/s")
 
 rt.doRaytracing(rg.RG_FXAA | rg.RG_COUNT_TRAVERSAL)
 tc = rt.timings()
