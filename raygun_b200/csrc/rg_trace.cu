@@ -412,12 +412,33 @@ enum { Q_ORG_T = 0, Q_DIR_FLAGS = 1, Q_N_RECDEPTH = 2, Q_DIFF_TRANSP = 3, Q_SPEC
 // Shared by both trace kernels; they differ only in where the state lives.  h: closest hit of the ray (ro, rd).  On return 1 the
 // next ray is in (ro, rd, rtmin, rtmax) / (rayType, missIndex, rayKind); on return 2 the sample ended and its pixel share is stored.
 // fr: the context's frames, 8 float4 each, + 2 float4 for the payload members that are only observable at recDepth 0.
+// Where the frames of a context live: local memory (one context per lane) or the global pool, which is read and written
+// through L2 only (ld/st.global.cg) so that the frames of 64 contexts per warp do not evict the BVH from L1.
+struct FramesLocal {
+    float4* p;
+    __device__ __forceinline__ FramesLocal at(int i) const { return FramesLocal{p + i}; }
+    __device__ __forceinline__ const float4 ld(int i) const { return p[i]; }
+    __device__ __forceinline__ void st(int i, float4 v) const { p[i] = v; }
+};
+struct FramesPool {
+    float4* p;
+    __device__ __forceinline__ FramesPool at(int i) const { return FramesPool{p + i}; }
+#ifdef RG_POOL_FRAMES_L1
+    __device__ __forceinline__ const float4 ld(int i) const { return p[i]; }
+    __device__ __forceinline__ void st(int i, float4 v) const { p[i] = v; }
+#else
+    __device__ __forceinline__ const float4 ld(int i) const { return __ldcg(p + i); }
+    __device__ __forceinline__ void st(int i, float4 v) const { __stcg(p + i, v); }
+#endif
+};
 struct ShadeConsts { V3 L; int maxRec; bool strictIeee; int numSamples; uint32_t S; };
+constexpr uint32_t kMaxRaysPerSample = 1u << 20;   // watchdogs: far above anything a scene can need, they only turn a bug into a wrong
+constexpr uint32_t kMaxStepsPerRay = 1u << 18;     // image instead of a hung GPU
 struct PixInfo { uint32_t xy, pslot, sample, rays; };   // lx | ly << 16, pixel slot, sample index, rays traced for this sample so far
-template <bool COUNT, bool MULTI>
+template <bool COUNT, bool MULTI, class FR>
 __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeConsts& K, const Hit& h, V3& ro, V3& rd, float& rtmin, float& rtmax, V3& hv,
                                             float& depth, float& curIOR, float& refDepth, int& rayType, int& missIndex, int& rayKind, int& recDepth, int& sp,
-                                            float4* fr, const PixInfo& pix, uint32_t* skyLookups, uint32_t* cntT) {
+                                            const FR fr, const PixInfo& pix, uint32_t* skyLookups, uint32_t* cntT) {
     const bool found = h.inst != kInvalid;
     if(rayKind == CNT_PRIMARY && P.idInst && pix.sample == 0u) {
         const uint32_t xy = pix.xy;
@@ -466,11 +487,11 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             const V3 nd = normalize(v3(1.1f - diffuse.x, 1.1f - diffuse.y, 1.1f - diffuse.z));
             const V3 shadowCol = hv - mix3(v3(0, 0, 0), v3(nd.x + 0.1f, nd.y + 0.1f, nd.z + 0.1f), thick);
             if(recDepth < K.maxRec) {
-                float4* f = fr + 8 * sp++;
-                f[Q_ORG_T] = make_float4(shadowCol.x, shadowCol.y, shadowCol.z, 0.0f);
-                f[Q_DIR_FLAGS] = make_float4(rd.x, rd.y, rd.z, __int_as_float(FR_SHI));
-                f[Q_N_RECDEPTH] = make_float4(n.x, n.y, n.z, __int_as_float(recDepth));
-                f[Q_IOR_EMIS] = make_float4(ior, 0.0f, 0.0f, 0.0f);
+                const FR f = fr.at(8 * sp++);
+                f.st(Q_ORG_T, make_float4(shadowCol.x, shadowCol.y, shadowCol.z, 0.0f));
+                f.st(Q_DIR_FLAGS, make_float4(rd.x, rd.y, rd.z, __int_as_float(FR_SHI)));
+                f.st(Q_N_RECDEPTH, make_float4(n.x, n.y, n.z, __int_as_float(recDepth)));
+                f.st(Q_IOR_EMIS, make_float4(ior, 0.0f, 0.0f, 0.0f));
                 rayType = RT_SHADOW_TRACE; recDepth++;
                 ro = origin; rtmin = 0.01f; rtmax = 1000.0f; missIndex = 0; rayKind = CNT_SHADOW;   // rd unchanged (T3)
                 issue = true;
@@ -493,7 +514,7 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             if(!frontFacing) n = normalize(-n);
             const float ndl = dot(-K.L, n);
             V3 baseColor = diffuse * glmax(ndl, 0.2f);
-            float4* f = fr + 8 * sp++;
+            const FR f = fr.at(8 * sp++);
             const V3 rdIn = rd;
             int stage;
             bool shadowPending = false;
@@ -513,20 +534,20 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             if(shadowPending) { stage = ST_SHADOW_RET; issue = true; }
             else { baseColor = baseColor + diffuse * emission; stage = ST_TRY_REFLECT; }
             const int flags = FR_GEN | (stage << 8) | ((frontFacing ? 1 : 0) << 16) | ((int)(rayConsumption & 0xffu) << 20);
-            f[Q_ORG_T] = make_float4(origin.x, origin.y, origin.z, h.t);
-            f[Q_DIR_FLAGS] = make_float4(rdIn.x, rdIn.y, rdIn.z, __int_as_float(flags));
-            f[Q_N_RECDEPTH] = make_float4(n.x, n.y, n.z, __int_as_float(recDepth));
-            f[Q_DIFF_TRANSP] = make_float4(diffuse.x, diffuse.y, diffuse.z, transparency);
-            f[Q_SPEC_REFL] = make_float4(specular.x, specular.y, specular.z, reflectivity);
-            f[Q_BASE_ROUGH] = make_float4(baseColor.x, baseColor.y, baseColor.z, roughness);
-            f[Q_IOR_EMIS] = make_float4(ior, emission, 0.0f, 0.0f);
+            f.st(Q_ORG_T, make_float4(origin.x, origin.y, origin.z, h.t));
+            f.st(Q_DIR_FLAGS, make_float4(rdIn.x, rdIn.y, rdIn.z, __int_as_float(flags)));
+            f.st(Q_N_RECDEPTH, make_float4(n.x, n.y, n.z, __int_as_float(recDepth)));
+            f.st(Q_DIFF_TRANSP, make_float4(diffuse.x, diffuse.y, diffuse.z, transparency));
+            f.st(Q_SPEC_REFL, make_float4(specular.x, specular.y, specular.z, reflectivity));
+            f.st(Q_BASE_ROUGH, make_float4(baseColor.x, baseColor.y, baseColor.z, roughness));
+            f.st(Q_IOR_EMIS, make_float4(ior, emission, 0.0f, 0.0f));
             if(shadowPending) recDepth++;
         }
     } else {
         if(missIndex == 0) {  // miss.rmiss:76-83
             const V3 sky = skyColor(rd, K.L, K.strictIeee);
             hv = sky; depth = 10000.0f;
-            if(sp == 0 && recDepth == 0) fr[kMaxFrames * 8 + 1] = make_float4(sky.x, sky.y, sky.z, 0.0f);   // roughValue is only observable for a primary miss
+            if(sp == 0 && recDepth == 0) fr.st(kMaxFrames * 8 + 1, make_float4(sky.x, sky.y, sky.z, 0.0f));   // roughValue is only observable for a primary miss
         } else {              // shadowMiss.rmiss:33
             hv = v3(1.0f, 1.0f, 1.0f);
         }
@@ -534,12 +555,13 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
 
     // ---- resume suspended frames (the code after each traceRayEXT returns)
     bool ended = false;
+    if(pix.rays > kMaxRaysPerSample) { sp = 0; issue = false; }   // watchdog: state machine stuck (never happens); end the sample
     while(!issue) {
         if(sp == 0) {   // raygen.h:105-111: the sample's trace returned
             const uint32_t xy = pix.xy, pslot = pix.pslot, sample = pix.sample;
             const uint32_t lx = xy & 0xffffu, ly = xy >> 16;
             if(P.tileCost) atomicAdd(P.tileCost + (pslot >> 5), pix.rays);
-            const float4 cold0 = fr[kMaxFrames * 8], cold1 = fr[kMaxFrames * 8 + 1];   // normal + reflectContribution, roughValue
+            const float4 cold0 = fr.ld(kMaxFrames * 8), cold1 = fr.ld(kMaxFrames * 8 + 1);   // normal + reflectContribution, roughValue
             V3 accColor = hv, accNormal = v3(cold0.x, cold0.y, cold0.z), accRough = v3(cold1.x, cold1.y, cold1.z);
             float accRoughA = cold1.w, accContrib = cold0.w, accDepth = depth;
             bool last = true;
@@ -582,8 +604,8 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             ended = true;
             break;
         }
-        float4* f = fr + 8 * (sp - 1);
-        const float4 qDir = f[Q_DIR_FLAGS], qN = f[Q_N_RECDEPTH], qOrg = f[Q_ORG_T], qIor = f[Q_IOR_EMIS];
+        const FR f = fr.at(8 * (sp - 1));
+        const float4 qDir = f.ld(Q_DIR_FLAGS), qN = f.ld(Q_N_RECDEPTH), qOrg = f.ld(Q_ORG_T), qIor = f.ld(Q_IOR_EMIS);
         const int flags = __float_as_int(qDir.w);
         recDepth = __float_as_int(qN.w);   // undoes every recDepth++ / += rayConsumption below this frame
         if((flags & 0xff) == FR_SHI) {   // closesthit.rchit:136-146, after T3 returned
@@ -603,8 +625,8 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             sp--;
             continue;
         }
-        const float4 qDiff = f[Q_DIFF_TRANSP], qSpec = f[Q_SPEC_REFL];
-        float4 qBase = f[Q_BASE_ROUGH], qRcol = f[Q_RCOL_RDEPTH];
+        const float4 qDiff = f.ld(Q_DIFF_TRANSP), qSpec = f.ld(Q_SPEC_REFL);
+        float4 qBase = f.ld(Q_BASE_ROUGH), qRcol = f.ld(Q_RCOL_RDEPTH);
         int stage = (flags >> 8) & 0xff;
         const bool frontFacing = ((flags >> 16) & 1) != 0;
         const int rc = (flags >> 20) & 0xff;
@@ -620,8 +642,8 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
                 recDepth += rc; refDepth += qOrg.w;
                 ro = v3(qOrg.x, qOrg.y, qOrg.z); rd = reflect3(D, n); rtmin = 0.01f; rtmax = 1000.0f;
                 rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFLECT;
-                f[Q_DIR_FLAGS] = make_float4(qDir.x, qDir.y, qDir.z, __int_as_float((flags & ~0xff00) | (ST_REFLECT_RET << 8)));
-                f[Q_BASE_ROUGH] = qBase;
+                f.st(Q_DIR_FLAGS, make_float4(qDir.x, qDir.y, qDir.z, __int_as_float((flags & ~0xff00) | (ST_REFLECT_RET << 8))));
+                f.st(Q_BASE_ROUGH, qBase);
                 issue = true;
                 break;
             }
@@ -641,9 +663,9 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
                 curIOR = frontFacing ? ior : 1.0f;
                 ro = v3(qOrg.x, qOrg.y, qOrg.z); rd = refract3(D, n, eta); rtmin = 0.01f; rtmax = 1000.0f;
                 rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_REFRACT;
-                f[Q_DIR_FLAGS] = make_float4(qDir.x, qDir.y, qDir.z,
-                                             __int_as_float((flags & ~0xff00) | ((frontFacing ? ST_REFRACT_RET_FRONT : ST_REFRACT_RET_BACK) << 8)));
-                f[Q_BASE_ROUGH] = qBase; f[Q_RCOL_RDEPTH] = qRcol;
+                f.st(Q_DIR_FLAGS, make_float4(qDir.x, qDir.y, qDir.z,
+                                              __int_as_float((flags & ~0xff00) | ((frontFacing ? ST_REFRACT_RET_FRONT : ST_REFRACT_RET_BACK) << 8))));
+                f.st(Q_BASE_ROUGH, qBase); f.st(Q_RCOL_RDEPTH, qRcol);
                 issue = true;
                 break;
             }
@@ -666,8 +688,8 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             hv = mix3(base, roughCol, totalContrib);
             if(recDepth == 0) {
                 hv = base;
-                fr[kMaxFrames * 8] = make_float4(n.x, n.y, n.z, totalContrib);
-                fr[kMaxFrames * 8 + 1] = make_float4(roughCol.x, roughCol.y, roughCol.z, glmin((qRcol.w / 50.0f) * roughness, roughness / 2.1f));
+                fr.st(kMaxFrames * 8, make_float4(n.x, n.y, n.z, totalContrib));
+                fr.st(kMaxFrames * 8 + 1, make_float4(roughCol.x, roughCol.y, roughCol.z, glmin((qRcol.w / 50.0f) * roughness, roughness / 2.1f)));
             }
             depth = qOrg.w;
             sp--;
@@ -722,7 +744,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
     uint32_t rayHead = 0, rayCount = 0, hitHead = 0, hitCount = 0, freeHead = 0, freeCount = kPoolCtx;
     bool exhausted = false;
     // the lane's ray in flight
-    uint32_t myCtx = kNoCtx;
+    uint32_t myCtx = kNoCtx, steps = 0;
     float tmin = 0.0f;
     uint2 stack[kStackSize];
     Trav T;
@@ -779,7 +801,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
                     W.pay[0][c] = 0.0f; W.pay[1][c] = 0.0f; W.pay[2][c] = 0.0f; W.pay[3][c] = 0.0f; W.pay[4][c] = 1.0f; W.pay[5][c] = 0.0f;
                     W.sel[c] = (uint32_t)(RT_GENERIC | (0 << 2) | (CNT_PRIMARY << 4));   // recDepth 0, no frames
                     float4* cold = ctxMem + (size_t)c * kCtxQuads + kMaxFrames * 8;
-                    cold[0] = make_float4(0, 0, 0, 0); cold[1] = make_float4(0, 0, 0, 0);
+                    __stcg(cold, make_float4(0, 0, 0, 0)); __stcg(cold + 1, make_float4(0, 0, 0, 0));
                     s_cnt[CNT_PRIMARY][tid]++;
                 }
             }
@@ -812,8 +834,8 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
                 int sp = (int)((sel >> 16) & 255u);
                 PixInfo pix;
                 pix.xy = W.pix[0][c]; pix.pslot = W.pix[1][c]; pix.sample = W.pix[2][c]; pix.rays = W.pix[3][c];
-                const bool ended = shadeContext<COUNT, MULTI>(P, K, h, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp, fr,
-                                                              pix, &s_cnt[CNT_SKY][tid], cntT) == 2;
+                const bool ended = shadeContext<COUNT, MULTI>(P, K, h, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
+                                                              FramesPool{fr}, pix, &s_cnt[CNT_SKY][tid], cntT) == 2;
                 if(ended) {
                     outcome = 2;
                 } else {   // the next traceRayEXT of this sample
@@ -850,6 +872,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
                 if(myCtx == kNoCtx && r < take) {
                     myCtx = W.rayQ[(rayHead + r) & kQMask];
                     tmin = W.ray[6][myCtx];
+                    steps = 0;
                     travInit(P, T, hit, W.ray[0][myCtx], W.ray[1][myCtx], W.ray[2][myCtx], W.ray[3][myCtx], W.ray[4][myCtx], W.ray[5][myCtx], W.ray[7][myCtx]);
                 }
                 rayHead += take; rayCount -= take; nEmpty -= take;
@@ -858,7 +881,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
             if(rayCount == 0u && nEmpty >= RG_EXIT_THRESHOLD && hitCount) break;
             if(!exhausted && freeCount >= RG_REFILL_THRESHOLD && rayCount == 0u) break;
             bool done = false;
-            if(myCtx != kNoCtx) done = travStep<COUNT>(P, T, stack, hit, WorldRayPool{&W.ray[0][myCtx]}, tmin, cntT);
+            if(myCtx != kNoCtx) done = travStep<COUNT>(P, T, stack, hit, WorldRayPool{&W.ray[0][myCtx]}, tmin, cntT) || ++steps > kMaxStepsPerRay;
             const uint32_t mDone = __ballot_sync(0xffffffffu, done);
             if(mDone) {
                 if(done) {   // park the closest hit; the lane is free for the next ray
@@ -980,10 +1003,10 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
             Trav T;
             const WorldRayRegs wr{{ro.x, ro.y, ro.z}, {rd.x, rd.y, rd.z}, rtmax};
             travInit(P, T, hit, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmax);
-            while(!travStep<COUNT>(P, T, stack, hit, wr, rtmin, cntT)) {}
+            for(uint32_t steps = 0; !travStep<COUNT>(P, T, stack, hit, wr, rtmin, cntT) && steps < kMaxStepsPerRay; ++steps) {}
             // ---- shade: hit / miss program, then the frames that resume, up to the next traceRayEXT
-            const int outcome = shadeContext<COUNT, MULTI>(P, K, hit, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp, frames,
-                                                           pix, &s_cnt[CNT_SKY][tid], cntT);
+            const int outcome = shadeContext<COUNT, MULTI>(P, K, hit, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
+                                                           FramesLocal{frames}, pix, &s_cnt[CNT_SKY][tid], cntT);
             if(outcome == 1) { s_cnt[rayKind][tid]++; pix.rays++; }
             else busy = false;
         }
@@ -1010,7 +1033,7 @@ __global__ void k_trace_rays(const TraceParams P, const float* __restrict__ rays
     uint32_t cnt[CNT_N];
     const WorldRayRegs wr{{q[0], q[1], q[2]}, {q[3], q[4], q[5]}, q[7]};
     travInit(P, T, hit, q[0], q[1], q[2], q[3], q[4], q[5], q[7]);
-    while(!travStep<false>(P, T, stack, hit, wr, q[6], cnt)) {}
+    for(uint32_t steps = 0; !travStep<false>(P, T, stack, hit, wr, q[6], cnt) && steps < kMaxStepsPerRay; ++steps) {}
     tuv[3 * i] = hit.t; tuv[3 * i + 1] = hit.u; tuv[3 * i + 2] = hit.v;
     instPrim[2 * i] = hit.inst; instPrim[2 * i + 1] = hit.prim;
 }
