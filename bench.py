@@ -286,12 +286,13 @@ def main():
         alg_bytes = trace_algorithmic_bytes(tmc, px)
         trace_ms = sections["trace_kernel_ms"] / args.steps
         achieved = alg_bytes / (trace_ms * 1e-3) / 1e9
+        kernel = "k_trace_pool" if tm["trace_scheduler"] == rg.RG_SCHED_POOL else "k_trace_lanes"
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as fh:
-                traffic = json.load(fh).get(f"k_trace:{args.workload}:n{world}")
-        roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                traffic = json.load(fh).get(f"{kernel}:{args.workload}:n{world}")
+        roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": trace_ms,
                     "kernel_share_of_step": trace_ms / (dev_ms / args.steps),
                     "per_ray": {"nodes": tmc["nodes_visited"] / max(tmc["rays"], 1), "tris": tmc["tris_tested"] / max(tmc["rays"], 1)},
@@ -329,7 +330,8 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": desc, "width": W, "height": H, "split": (f"{world} {args.split} bands for the post chain; trace: 8x4 tiles dealt round-robin in chunks of 16, G-buffer pixels stored to their owners over NVLink"
                                      if args.mgpu == "partition" else f"{world} {args.split} bands, 40 px halo re-traced, overdraw x{overdraw(W, H, world, args.split):.3f}") if world > 1 else "none",
-                           "l2": "flushed before every timed frame (256 MiB memset)", "tlas": "rebuilt every frame"},
+                           "l2": "flushed before every timed frame (256 MiB memset)", "tlas": "rebuilt every frame",
+                           "trace_scheduler": ("pool" if tm["trace_scheduler"] == rg.RG_SCHED_POOL else "lanes") + " (RG_SCHED_AUTO: both timed during warm-up, faster kept)"},
                 "fps": 1e3 / ms_step, "rays_per_frame": rays_total / args.steps,
                 "sections_ms": {k: v / args.steps for k, v in sections.items()}, "wall_ms_per_step_incl_flush": wall_ms / args.steps,
                 "clocks": clocks,

@@ -193,137 +193,153 @@ __device__ __forceinline__ void travInit(const TraceParams& P, Trav& T, Hit& hit
     if(!none) setupRay(T.r, ox, oy, oz, dx, dy, dz);
 }
 
-// One step; true when the traversal is complete.  wray: the world-space ray given to travInit (needed again when an instance is entered or left).
-template <bool COUNT, class WR>
-__device__ __forceinline__ bool travStep(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
+// The three kinds of traversal work.  travNode: the 8 children of the next node of the lane's node group; leaves T.ng / T.tg = the hit
+// children / primitives of that node (primitives the lane still held are parked on its stack: postponed tests).
+template <bool COUNT>
+__device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* __restrict__ stack, const Hit& hit, float tmin, uint32_t* cnt) {
     RayCtx& r = T.r;
-    if((T.ng.y & 0xff000000u) && !T.tg.y) {   // one node per step, and only once this lane's pending primitives are done
-        uint2 ng = T.ng;
-        const int bit = 31 - __clz(ng.y);
-        ng.y &= ~(1u << bit);
-        const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
-        const uint32_t rel = __popc(ng.y & 0xffu & ((1u << slot) - 1u));
-        if((ng.y & 0xff000000u) && T.sp < kStackSize) stack[T.sp++] = ng;
-        const Node8* nodes = T.curInst != kInvalid ? P.blasNodes : P.tlasNodes;
-        const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
-        const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-        if(COUNT) cnt[CNT_NODES]++;
-        const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
-                    sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
-        const float px = __uint_as_float(n0.x) - r.ox, py = __uint_as_float(n0.y) - r.oy, pz = __uint_as_float(n0.z) - r.oz;
-        // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
-        // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.
-        // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
-        // byteF gives v = 1 + q / 32768, so t = v * A + (b - A) with A = 32768 * 2^e / d.  Rounding: ulp(A) = 1/256 of one
-        // quantisation step in t, plus the error of b = (p - o) / d; both are covered by the slack (relative to |b| and to a step).
-        const float ax = sx * r.ix * 32768.0f, ay = sy * r.iy * 32768.0f, az = sz * r.iz * 32768.0f;
-        const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
-        const float kSlack = 7.2e-7f, kStep = 1.0f / (32768.0f * 64.0f);   // 1/64 of a quantisation step
-        const float wx = fmaf(fabsf(bx), kSlack, fabsf(ax) * kStep), wy = fmaf(fabsf(by), kSlack, fabsf(ay) * kStep), wz = fmaf(fabsf(bz), kSlack, fabsf(az) * kStep);
-        const float onx = (bx - ax) - wx, ony = (by - ay) - wy, onz = (bz - az) - wz;
-        const float ofx = (bx - ax) + wx, ofy = (by - ay) + wy, ofz = (bz - az) + wz;
-        // near / far plane words by the sign of the direction: one LOP3 each on the packed words BEFORE the byte decode
-        // (a plain ?: lets the compiler select after decoding both, which doubles the PRMTs)
-        const uint32_t mx = (r.octinv & 4u) ? 0u : 0xffffffffu, my = (r.octinv & 2u) ? 0u : 0xffffffffu, mz = (r.octinv & 1u) ? 0u : 0xffffffffu;
-        const uint32_t octinv4 = r.octinv * 0x01010101u;
-        uint32_t hitmask = 0;
+    if(T.tg.y && T.sp < kStackSize) stack[T.sp++] = T.tg;
+    uint2 ng = T.ng;
+    const int bit = 31 - __clz(ng.y);
+    ng.y &= ~(1u << bit);
+    const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
+    const uint32_t rel = __popc(ng.y & 0xffu & ((1u << slot) - 1u));
+    if((ng.y & 0xff000000u) && T.sp < kStackSize) stack[T.sp++] = ng;
+    const Node8* nodes = T.curInst != kInvalid ? P.blasNodes : P.tlasNodes;
+    const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
+    const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+    if(COUNT) cnt[CNT_NODES]++;
+    const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
+                sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
+    const float px = __uint_as_float(n0.x) - r.ox, py = __uint_as_float(n0.y) - r.oy, pz = __uint_as_float(n0.z) - r.oz;
+    // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
+    // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.
+    // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
+    // byteF gives v = 1 + q / 32768, so t = v * A + (b - A) with A = 32768 * 2^e / d.  Rounding: ulp(A) = 1/256 of one
+    // quantisation step in t, plus the error of b = (p - o) / d; both are covered by the slack (relative to |b| and to a step).
+    const float ax = sx * r.ix * 32768.0f, ay = sy * r.iy * 32768.0f, az = sz * r.iz * 32768.0f;
+    const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
+    const float kSlack = 7.2e-7f, kStep = 1.0f / (32768.0f * 64.0f);   // 1/64 of a quantisation step
+    const float wx = fmaf(fabsf(bx), kSlack, fabsf(ax) * kStep), wy = fmaf(fabsf(by), kSlack, fabsf(ay) * kStep), wz = fmaf(fabsf(bz), kSlack, fabsf(az) * kStep);
+    const float onx = (bx - ax) - wx, ony = (by - ay) - wy, onz = (bz - az) - wz;
+    const float ofx = (bx - ax) + wx, ofy = (by - ay) + wy, ofz = (bz - az) + wz;
+    // near / far plane words by the sign of the direction: one LOP3 each on the packed words BEFORE the byte decode
+    // (a plain ?: lets the compiler select after decoding both, which doubles the PRMTs)
+    const uint32_t mx = (r.octinv & 4u) ? 0u : 0xffffffffu, my = (r.octinv & 2u) ? 0u : 0xffffffffu, mz = (r.octinv & 1u) ? 0u : 0xffffffffu;
+    const uint32_t octinv4 = r.octinv * 0x01010101u;
+    uint32_t hitmask = 0;
 #pragma unroll 1
-        for(int half = 0; half < 2; ++half) {   // slots 0..3, then 4..7: a rolled loop keeps the hot code small for the instruction cache
-            const uint32_t lx = half ? n2.y : n2.x, ly = half ? n2.w : n2.z, lz = half ? n3.y : n3.x;
-            const uint32_t hx = half ? n3.w : n3.z, hy = half ? n4.y : n4.x, hz = half ? n4.w : n4.z;
-            const uint32_t nx = bitsel(mx, hx, lx), fx = bitsel(mx, lx, hx), ny = bitsel(my, hy, ly), fy = bitsel(my, ly, hy), nz = bitsel(mz, hz, lz), fz = bitsel(mz, lz, hz);
-            uint32_t bits4, idx4;
-            decodeMeta4(half ? n1.w : n1.z, octinv4, bits4, idx4);
-            childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-            childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-            childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-            childTest<3>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-        }
-        T.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
-        T.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+    for(int half = 0; half < 2; ++half) {   // slots 0..3, then 4..7: a rolled loop keeps the hot code small for the instruction cache
+        const uint32_t lx = half ? n2.y : n2.x, ly = half ? n2.w : n2.z, lz = half ? n3.y : n3.x;
+        const uint32_t hx = half ? n3.w : n3.z, hy = half ? n4.y : n4.x, hz = half ? n4.w : n4.z;
+        const uint32_t nx = bitsel(mx, hx, lx), fx = bitsel(mx, lx, hx), ny = bitsel(my, hy, ly), fy = bitsel(my, ly, hy), nz = bitsel(mz, hz, lz), fz = bitsel(mz, lz, hz);
+        uint32_t bits4, idx4;
+        decodeMeta4(half ? n1.w : n1.z, octinv4, bits4, idx4);
+        childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+        childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+        childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+        childTest<3>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
     }
+    T.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
+    T.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+}
 
-    if(T.tg.y) {      // ONE primitive per step: lanes without pending primitives go on with their next node meanwhile
-        const int bit = __ffs(T.tg.y) - 1;
-        T.tg.y &= T.tg.y - 1u;
-        if(T.curInst == kInvalid) {
-            const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + (T.tg.x + bit));
-            const uint4 l3 = __ldg(lp + 3);
-            // instance of an empty mesh, or stack exhausted (never with sane scenes): skip
-            if(l3.x != kInvalid && T.sp + 6 <= kStackSize) {
-                if(COUNT) cnt[CNT_INST]++;
-                const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
-                const float ox = wray.ox(), oy = wray.oy(), oz = wray.oz();
-                bool enter = true;
-                if(l3.z) {
-                    // pure translation (flagged by the instance preparation): the direction and everything derived from it stay;
-                    // the oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t
+// travPrim: ONE primitive of the lane's primitive group -- a triangle test inside an instance, entering an instance in the TLAS.
+template <bool COUNT, class WR>
+__device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
+    RayCtx& r = T.r;
+    const int bit = __ffs(T.tg.y) - 1;
+    T.tg.y &= T.tg.y - 1u;
+    if(T.curInst == kInvalid) {
+        const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + (T.tg.x + bit));
+        const uint4 l3 = __ldg(lp + 3);
+        // instance of an empty mesh, or stack exhausted (never with sane scenes): skip
+        if(l3.x != kInvalid && T.sp + 6 <= kStackSize) {
+            if(COUNT) cnt[CNT_INST]++;
+            const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
+            const float ox = wray.ox(), oy = wray.oy(), oz = wray.oz();
+            bool enter = true;
+            if(l3.z) {
+                // pure translation (flagged by the instance preparation): the direction and everything derived from it stay;
+                // the oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t
+                if(T.tg.y) stack[T.sp++] = T.tg;
+                if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
+                stack[T.sp++] = make_uint2(kInvalid, 0x1000u);
+                r.ox = __fadd_rn(ox, __uint_as_float(l0.w)); r.oy = __fadd_rn(oy, __uint_as_float(l1.w)); r.oz = __fadd_rn(oz, __uint_as_float(l2.w));
+            } else {
+                // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
+                const float* w0 = reinterpret_cast<const float*>(&l0); const float* w1 = reinterpret_cast<const float*>(&l1);
+                const float* w2 = reinterpret_cast<const float*>(&l2);
+                const float dx = wray.dx(), dy = wray.dy(), dz = wray.dz();
+                const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0[0], ox), __fmul_rn(w0[1], oy)), __fmul_rn(w0[2], oz)), w0[3]);
+                const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1[0], ox), __fmul_rn(w1[1], oy)), __fmul_rn(w1[2], oz)), w1[3]);
+                const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2[0], ox), __fmul_rn(w2[1], oy)), __fmul_rn(w2[2], oz)), w2[3]);
+                const float odx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
+                const float ody = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
+                const float odz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
+                if(odx == 0.0f && ody == 0.0f && odz == 0.0f) {
+                    enter = false;
+                } else {
                     if(T.tg.y) stack[T.sp++] = T.tg;
                     if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
-                    stack[T.sp++] = make_uint2(kInvalid, 0x1000u);
-                    r.ox = __fadd_rn(ox, __uint_as_float(l0.w)); r.oy = __fadd_rn(oy, __uint_as_float(l1.w)); r.oz = __fadd_rn(oz, __uint_as_float(l2.w));
-                } else {
-                    // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
-                    const float* w0 = reinterpret_cast<const float*>(&l0); const float* w1 = reinterpret_cast<const float*>(&l1);
-                    const float* w2 = reinterpret_cast<const float*>(&l2);
-                    const float dx = wray.dx(), dy = wray.dy(), dz = wray.dz();
-                    const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0[0], ox), __fmul_rn(w0[1], oy)), __fmul_rn(w0[2], oz)), w0[3]);
-                    const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1[0], ox), __fmul_rn(w1[1], oy)), __fmul_rn(w1[2], oz)), w1[3]);
-                    const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2[0], ox), __fmul_rn(w2[1], oy)), __fmul_rn(w2[2], oz)), w2[3]);
-                    const float odx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
-                    const float ody = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
-                    const float odz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
-                    if(odx == 0.0f && ody == 0.0f && odz == 0.0f) {
-                        enter = false;
-                    } else {
-                        if(T.tg.y) stack[T.sp++] = T.tg;
-                        if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
-                        // the world-space slab / shear constants ride on the stack while the instance is traversed
-                        stack[T.sp++] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
-                        stack[T.sp++] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx));
-                        stack[T.sp++] = make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz));
-                        stack[T.sp++] = make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8));
-                        setupRay(r, oox, ooy, ooz, odx, ody, odz);
-                    }
-                }
-                if(enter) {
-                    T.curInst = l3.y;
-                    T.ng = make_uint2(l3.x, 0x80000000u);
-                    T.tg = make_uint2(0u, 0u);
+                    // the world-space slab / shear constants ride on the stack while the instance is traversed
+                    stack[T.sp++] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
+                    stack[T.sp++] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx));
+                    stack[T.sp++] = make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz));
+                    stack[T.sp++] = make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8));
+                    setupRay(r, oox, ooy, ooz, odx, ody, odz);
                 }
             }
-            return false;
-        } else {
-            const float4* tp = reinterpret_cast<const float4*>(P.tris + (T.tg.x + bit));
-            const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
-            if(COUNT) cnt[CNT_TRIS]++;
-            float t, u, v;
-            if(triTest(r, p0, p1, p2, tmin, t, u, v)) {
-                const uint32_t prim = __float_as_uint(p0.w);
-                if(t < hit.t || (t == hit.t && t < wray.tmax() && (T.curInst < hit.inst || (T.curInst == hit.inst && prim < hit.prim)))) {
-                    hit.t = t; hit.u = u; hit.v = v; hit.inst = T.curInst; hit.prim = prim;
-                }
+            if(enter) {
+                T.curInst = l3.y;
+                T.ng = make_uint2(l3.x, 0x80000000u);
+                T.tg = make_uint2(0u, 0u);
+            }
+        }
+        return;
+    } else {
+        const float4* tp = reinterpret_cast<const float4*>(P.tris + (T.tg.x + bit));
+        const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+        if(COUNT) cnt[CNT_TRIS]++;
+        float t, u, v;
+        if(triTest(r, p0, p1, p2, tmin, t, u, v)) {
+            const uint32_t prim = __float_as_uint(p0.w);
+            if(t < hit.t || (t == hit.t && t < wray.tmax() && (T.curInst < hit.inst || (T.curInst == hit.inst && prim < hit.prim)))) {
+                hit.t = t; hit.u = u; hit.v = v; hit.inst = T.curInst; hit.prim = prim;
             }
         }
     }
+}
 
-    if(!(T.ng.y & 0xff000000u) && !T.tg.y) {
-        while(true) {
-            if(T.sp == 0) return true;
-            T.ng = stack[--T.sp];
-            if(T.ng.x != kInvalid) break;
-            // leave the instance: back to the world-space ray
-            T.curInst = kInvalid;
-            r.ox = wray.ox(); r.oy = wray.oy(); r.oz = wray.oz();
-            if(!(T.ng.y & 0x1000u)) {   // a general instance: direction-derived constants come back from the stack
-                r.octinv = T.ng.y & 7u; r.kx = (int)((T.ng.y >> 4) & 3u); r.ky = (int)((T.ng.y >> 6) & 3u); r.kz = (int)((T.ng.y >> 8) & 3u);
-                const uint2 c2 = stack[--T.sp], c1 = stack[--T.sp], c0 = stack[--T.sp];
-                r.ix = __uint_as_float(c0.x); r.iy = __uint_as_float(c0.y); r.iz = __uint_as_float(c1.x);
-                r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
-            }
+// travPop: the lane has neither nodes nor primitives at hand: next entry of its stack.  True when the stack is empty (ray done).
+template <class WR>
+__device__ __forceinline__ bool travPop(Trav& T, const uint2* __restrict__ stack, const WR& wray) {
+    RayCtx& r = T.r;
+    while(true) {
+        if(T.sp == 0) return true;
+        T.ng = stack[--T.sp];
+        if(T.ng.x != kInvalid) break;
+        // leave the instance: back to the world-space ray
+        T.curInst = kInvalid;
+        r.ox = wray.ox(); r.oy = wray.oy(); r.oz = wray.oz();
+        if(!(T.ng.y & 0x1000u)) {   // a general instance: direction-derived constants come back from the stack
+            r.octinv = T.ng.y & 7u; r.kx = (int)((T.ng.y >> 4) & 3u); r.ky = (int)((T.ng.y >> 6) & 3u); r.kz = (int)((T.ng.y >> 8) & 3u);
+            const uint2 c2 = stack[--T.sp], c1 = stack[--T.sp], c0 = stack[--T.sp];
+            r.ix = __uint_as_float(c0.x); r.iy = __uint_as_float(c0.y); r.iz = __uint_as_float(c1.x);
+            r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
         }
-        if(!(T.ng.y & 0xff000000u)) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }   // a primitive group came off the stack
     }
+    if(!(T.ng.y & 0xff000000u)) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }   // a primitive group came off the stack
+    return false;
+}
+
+// One step of the fixed order node -> primitive -> pop (a lane goes on with nodes only once its pending primitives are done);
+// true when the traversal is complete.  wray: the world-space ray given to travInit (needed when an instance is entered or left).
+template <bool COUNT, class WR>
+__device__ __forceinline__ bool travStep(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
+    if((T.ng.y & 0xff000000u) && !T.tg.y) travNode<COUNT>(P, T, stack, hit, tmin, cnt);
+    if(T.tg.y) travPrim<COUNT>(P, T, stack, hit, wray, tmin, cnt);
+    if(!(T.ng.y & 0xff000000u) && !T.tg.y) return travPop(T, stack, wray);
     return false;
 }
 

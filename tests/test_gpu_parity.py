@@ -173,8 +173,8 @@ def test_band_split_is_bit_identical_to_full_frame(rgmod, S, example_scene, spli
     assert np.array_equal(full.read_gathered_rgba8(), want)
 
 
-@pytest.mark.parametrize("world,split", [(2, "columns"), (3, "rows"), (4, "columns")])
-def test_partitioned_mode_is_bit_identical_to_full_frame(rgmod, S, example_scene, world, split):
+@pytest.mark.parametrize("world,split,sched", [(2, "columns", "auto"), (3, "rows", "pool"), (4, "columns", "lanes"), (2, "rows", "pool")])
+def test_partitioned_mode_is_bit_identical_to_full_frame(rgmod, S, example_scene, world, split, sched):
     """Partitioned multi-GPU mode with `world` contexts on one GPU: every context traces its round-robin share of tiles and
     stores the pixels into the owners' G-buffers (peer pointers), device-side barriers order trace / post / next frame;
     the gathered frame must equal the single-context frame bit for bit, for two consecutive frames."""
@@ -187,11 +187,12 @@ def test_partitioned_mode_is_bit_identical_to_full_frame(rgmod, S, example_scene
     for r in range(world):
         rt = rgmod.Raytracer(W, H)
         rt.set_region(*band_region(W, H, r, world, split))
+        rt.set_trace_scheduler({"auto": rgmod.RG_SCHED_AUTO, "pool": rgmod.RG_SCHED_POOL, "lanes": rgmod.RG_SCHED_LANES}[sched])
         rt.load_scene(example_scene)
         rt.set_gather_target(target)
         rts.append(rt)
     attach_partition_in_process(rts)
-    for ns in (1, 2):
+    for ns in (1, 2, 2, 2) if sched == "auto" else (1, 2):   # auto: frames 3 and 4 are the two probe frames
         ubo = S.example_ubo(W, H, num_samples=ns)
         full.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_NO_GATHER)
         want = full.read_rgba8()
