@@ -37,14 +37,23 @@ __device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y 
 __device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ V3 normalize(V3 a) { const float r = 1.0f / sqrtf(dot(a, a)); return a * r; }
+#ifndef RG_INLINE_MATH
+__device__ __noinline__ float rsqrtIeee(float x) { return 1.0f / sqrtf(x); }   // ONE copy: the IEEE sqrt + divide expansion is large, and the
+__device__ __noinline__ float powShared(float x, float y) { return powf(x, y); }   // instruction caches are this kernel's bottleneck
+__device__ __noinline__ float divShared(float x, float y) { return x / y; }        // (same IEEE results as the inlined forms)
+#else
+__device__ __forceinline__ float rsqrtIeee(float x) { return 1.0f / sqrtf(x); }
+__device__ __forceinline__ float powShared(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ float divShared(float x, float y) { return x / y; }
+#endif
+__device__ __forceinline__ V3 normalize(V3 a) { const float r = rsqrtIeee(dot(a, a)); return a * r; }
 __device__ __forceinline__ V3 mix3(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 // GLSL min / max / clamp as GLM evaluates them ((y < x) ? y : x ...): NaN propagates exactly as in the oracle (RG_STRICT_IEEE)
 __device__ __forceinline__ float glmin(float x, float y) { return (y < x) ? y : x; }
 __device__ __forceinline__ float glmax(float x, float y) { return (x < y) ? y : x; }
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return glmin(glmax(x, lo), hi); }
-__device__ __forceinline__ float glmod(float x, float y) { return x - y * floorf(x / y); }
+__device__ __forceinline__ float glmod(float x, float y) { return x - y * floorf(divShared(x, y)); }
 __device__ __forceinline__ V3 reflect3(V3 I, V3 N) { return I - N * (dot(N, I) * 2.0f); }
 __device__ __forceinline__ V3 refract3(V3 I, V3 N, float eta) {
     const float d = dot(N, I);
@@ -360,26 +369,26 @@ __device__ __forceinline__ float2 aaOffset(int numSamples, int i) {
 __device__ __noinline__ V3 skyColor(V3 d, V3 lightDir, bool strict) {
     const bool zero = d.x == 0.0f && d.y == 0.0f && d.z == 0.0f;
     const V3 rayDir = (zero && !strict) ? v3(0, 0, 0) : normalize(d);
-    const float y = fabsf(d.y + 1.5f) / 3.0f;
+    const float y = divShared(fabsf(d.y + 1.5f), 3.0f);
     const V3 sd = normalize(-lightDir) - rayDir;
     float sun = 1.0f - sqrtf(dot(sd, sd));
     sun = clampf(sun, 0.0f, 2.0f);
     float glow = clampf(sun, 0.0f, 1.0f);
-    sun = powf(sun, 80.0f);
+    sun = powShared(sun, 80.0f);
     sun *= 1000.0f;
     sun = clampf(sun, 0.0f, 16.0f);
-    glow = powf(glow, 6.0f) * 1.0f;
-    glow = powf(glow, y);
+    glow = powShared(glow, 6.0f) * 1.0f;
+    glow = powShared(glow, y);
     glow = clampf(glow, 0.0f, 1.0f);
-    sun *= powf(y * y, 1.0f / 1.65f);
-    glow *= powf(y * y, 1.0f / 2.0f);
+    sun *= powShared(y * y, 1.0f / 1.65f);
+    glow *= powShared(y * y, 1.0f / 2.0f);
     sun += glow;
     const V3 sunColor = v3(1.0f, 0.6f, 0.05f) * sun;
     const float atmosphere = sqrtf(1.0f - y);
-    float scatter = powf(4.0f - lightDir.y, 1.0f / 15.0f);
+    float scatter = powShared(4.0f - lightDir.y, 1.0f / 15.0f);
     scatter = 1.0f - clampf(scatter, 0.8f, 1.0f);
     const V3 scatterColor = mix3(v3(1.0f, 1.0f, 1.0f), v3(1.0f, 0.3f, 0.0f) * 1.5f, scatter);
-    const V3 skyScatter = mix3(v3(0.2f, 0.4f, 0.8f), scatterColor, atmosphere / 1.3f);
+    const V3 skyScatter = mix3(v3(0.2f, 0.4f, 0.8f), scatterColor, divShared(atmosphere, 1.3f));
     return sunColor + skyScatter;
 }
 
@@ -486,13 +495,13 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
         V3 n = normalize(v3(o0.x * vn.x + o0.y * vn.y + o0.z * vn.z, o1.x * vn.x + o1.y * vn.y + o1.z * vn.z, o2.x * vn.x + o2.y * vn.y + o2.z * vn.z));  // :118-119
 
         if(effectId == 1u) {  // gridEffect, :74-91
-            const float aa = (refDepth + h.t + 8.0f) / 30.0f;
+            const float aa = divShared(refDepth + h.t + 8.0f, 30.0f);
             const float aa2 = aa / 2.0f;
             float minmod = glmin(fabsf(glmod((origin.x + 1000.0f) * 10.0f + aa2, 20.0f) - aa2), fabsf(glmod((origin.z + 1000.0f) * 10.0f + aa2, 20.0f) - aa2));
             if(minmod < aa2) {
-                minmod -= aa2 - (aa * aa) / 3.0f;
-                minmod *= 3.0f / (aa * aa);
-                const float f = mixf(aa / 10.0f, 1.0f, minmod);
+                minmod -= aa2 - divShared(aa * aa, 3.0f);
+                minmod *= divShared(3.0f, aa * aa);
+                const float f = mixf(divShared(aa, 10.0f), 1.0f, minmod);
                 diffuse = diffuse * f; specular = specular * f; reflectivity *= f;
             }
             if(glmod((origin.x + 1000.0f) * 5.0f, 20.0f) < 10.0f && glmod((origin.z + 1000.0f) * 5.0f, 20.0f) < 10.0f) reflectivity *= 1.5f;
@@ -602,9 +611,9 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             }
             if(last) {      // raygen.h:114 + raygen.rgen:35-38
                 const float inv = (float)K.numSamples;
-                const uint2 ob = packHalf4(accColor.x / inv, accColor.y / inv, accColor.z / inv, accContrib / inv);
-                const uint2 on = packHalf4(accNormal.x / inv, accNormal.y / inv, accNormal.z / inv, (logf(accDepth) * 0.25f) / inv);
-                const uint2 orr = packHalf4(accRough.x / inv, accRough.y / inv, accRough.z / inv, accRoughA / inv);
+                const uint2 ob = packHalf4(divShared(accColor.x, inv), divShared(accColor.y, inv), divShared(accColor.z, inv), divShared(accContrib, inv));
+                const uint2 on = packHalf4(divShared(accNormal.x, inv), divShared(accNormal.y, inv), divShared(accNormal.z, inv), divShared(logf(accDepth) * 0.25f, inv));
+                const uint2 orr = packHalf4(divShared(accRough.x, inv), divShared(accRough.y, inv), divShared(accRough.z, inv), divShared(accRoughA, inv));
                 // the pixel goes to every GPU whose post-chain rectangle contains it (own images or peer memory over NVLink)
 #pragma unroll
                 for(int q = 0; q < (MULTI ? kMaxPeers : 1); ++q) {   // static indices: the targets stay in the constant bank
@@ -674,7 +683,7 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
         if(stage == ST_TRY_REFRACT) {  // :224-251
             if(recDepth < K.maxRec && qDiff.w > 0.0f) {
                 const float ior = qIor.x;
-                const float eta = frontFacing ? curIOR / ior : ior / 1.0f;
+                const float eta = frontFacing ? divShared(curIOR, ior) : ior / 1.0f;
                 recDepth++;
                 curIOR = frontFacing ? ior : 1.0f;
                 ro = v3(qOrg.x, qOrg.y, qOrg.z); rd = refract3(D, n, eta); rtmin = 0.01f; rtmax = 1000.0f;
@@ -698,14 +707,14 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             const V3 reflectColor = v3(qRcol.x, qRcol.y, qRcol.z);
             const float transparency = qDiff.w, reflectivity = qSpec.w, roughness = qBase.w;
             const float totalContrib = glmax(transparency, reflectivity);
-            float weight = reflectivity / (transparency + reflectivity);
+            float weight = divShared(reflectivity, transparency + reflectivity);
             if(!K.strictIeee && (transparency + reflectivity) == 0.0f) weight = 0.0f;   // SURVEY hazard 8
             const V3 roughCol = mix3(refractColor, reflectColor, weight);
             hv = mix3(base, roughCol, totalContrib);
             if(recDepth == 0) {
                 hv = base;
                 fr.st(kMaxFrames * 8, make_float4(n.x, n.y, n.z, totalContrib));
-                fr.st(kMaxFrames * 8 + 1, make_float4(roughCol.x, roughCol.y, roughCol.z, glmin((qRcol.w / 50.0f) * roughness, roughness / 2.1f)));
+                fr.st(kMaxFrames * 8 + 1, make_float4(roughCol.x, roughCol.y, roughCol.z, glmin(divShared(qRcol.w, 50.0f) * roughness, divShared(roughness, 2.1f))));
             }
             depth = qOrg.w;
             sp--;
