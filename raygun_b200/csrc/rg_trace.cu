@@ -407,6 +407,12 @@ __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) {
 #ifndef RG_EXIT_THRESHOLD
 #define RG_EXIT_THRESHOLD 12     // lanes without a ray, with the ray queue empty, before the warp leaves the traversal loop to shade
 #endif
+#ifndef RG_POOL_LIVE
+#define RG_POOL_LIVE kPoolCtx    // contexts of a warp's pool that are actually used (<= kPoolCtx)
+#endif
+#ifndef RG_GRAB_MAX
+#define RG_GRAB_MAX 32           // consecutive work items (samples of one 8x4 tile) a warp takes per atomic
+#endif
 #ifndef RG_REFILL_THRESHOLD
 #define RG_REFILL_THRESHOLD 16   // free contexts before new work items are fetched (consecutive items = neighbouring pixels)
 #endif
@@ -766,7 +772,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
     for(uint32_t i = lane; i < (uint32_t)kPoolCtx; i += 32u) W.freeQ[i] = (uint8_t)i;
     __syncwarp();
     // warp-uniform scheduler state
-    uint32_t rayHead = 0, rayCount = 0, hitHead = 0, hitCount = 0, freeHead = 0, freeCount = kPoolCtx;
+    uint32_t rayHead = 0, rayCount = 0, hitHead = 0, hitCount = 0, freeHead = 0, freeCount = RG_POOL_LIVE;
     bool exhausted = false;
     // the lane's ray in flight
     uint32_t myCtx = kNoCtx, steps = 0;
@@ -792,7 +798,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
 
         // ---- REFILL: free contexts take new work items
         if(!exhausted && freeCount && (freeCount >= RG_REFILL_THRESHOLD || (rayCount == 0u && hitCount == 0u))) {
-            const uint32_t n = freeCount < 32u ? freeCount : 32u;
+            const uint32_t n = freeCount < (uint32_t)RG_GRAB_MAX ? freeCount : (uint32_t)RG_GRAB_MAX;
             uint32_t basew = 0;
             if(lane == 0) basew = atomicAdd(P.workCounter, n);
             basew = __shfl_sync(0xffffffffu, basew, 0);
@@ -985,14 +991,17 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
 
     while(true) {
         // ---- refill idle lanes (warp vote + prefix compaction over one atomic)
-        const uint32_t idle = __ballot_sync(0xffffffffu, !busy);
-        if(!exhausted && __popc(idle) >= 8) {
-            const int n = __popc(idle), leader = __ffs(idle) - 1;
+        uint32_t idle = __ballot_sync(0xffffffffu, !busy);
+        while(!exhausted && __popc(idle) >= 8) {
+            // at most RG_GRAB_MAX consecutive work items per grab: the samples of one (possibly very expensive) tile spread over several warps
+            const int nIdle = __popc(idle), n = nIdle < RG_GRAB_MAX ? nIdle : RG_GRAB_MAX, leader = __ffs(idle) - 1;
             uint32_t basew = 0;
             if((int)lane == leader) basew = atomicAdd(P.workCounter, (uint32_t)n);
             basew = __shfl_sync(0xffffffffu, basew, leader);
-            if(!busy) {
-                const uint32_t w = basew + __popc(idle & ((1u << lane) - 1u));
+            const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+            const bool served = !busy && rank < (uint32_t)n;
+            if(served) {
+                const uint32_t w = basew + rank;
                 if(w < total) {
                     const uint32_t l = w & 31u, pos = (w >> 5) / S;
                     const uint32_t sample = (w >> 5) % S;
@@ -1019,6 +1028,7 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
                 }
             }
             if(basew + (uint32_t)n >= total) exhausted = true;
+            idle &= ~__ballot_sync(0xffffffffu, served);   // padding pixels stay idle until the next round of the outer loop
         }
         if(!__any_sync(0xffffffffu, busy)) { if(exhausted) break; continue; }
 

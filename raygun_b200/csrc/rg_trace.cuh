@@ -7,7 +7,10 @@ namespace rg {
 constexpr int kMaxRecursions = 8;   // BASELINE config 3 uses 8; the reference UI allows 0..7 (render_system.cpp:264)
 constexpr int kMaxFrames = kMaxRecursions + 1;  // a generic hit entered at recDepth >= max still gets a frame
 constexpr int kStackSize = 48;     // traversal stack entries (uint2) per ray: TLAS + BLAS + postponed primitive groups
-constexpr int kPoolCtx = 64;       // ray-tree contexts (pixel samples in progress) per warp
+#ifndef RG_POOL_CTX
+#define RG_POOL_CTX 64
+#endif
+constexpr int kPoolCtx = RG_POOL_CTX;   // ray-tree contexts (pixel samples in progress) per warp
 constexpr int kCtxQuads = kMaxFrames * 8 + 2;   // float4 per context in global memory: 8 per frame + the payload members only observable at recDepth 0
 constexpr int kMaxPeers = 8;        // GPUs of one node
 constexpr uint32_t kChunkTiles = 16; // tiles per round-robin chunk in partitioned mode
