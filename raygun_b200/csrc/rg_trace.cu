@@ -402,10 +402,10 @@ __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) {
 #define RG_TRACE_MIN_BLOCKS 4
 #endif
 #ifndef RG_FETCH_THRESHOLD
-#define RG_FETCH_THRESHOLD 8     // lanes without a ray before the warp fetches from its ray queue
+#define RG_FETCH_THRESHOLD 4     // lanes without a ray before the warp fetches from its ray queue (swept 2..16 on C3)
 #endif
 #ifndef RG_EXIT_THRESHOLD
-#define RG_EXIT_THRESHOLD 12     // lanes without a ray, with the ray queue empty, before the warp leaves the traversal loop to shade
+#define RG_EXIT_THRESHOLD 28     // lanes without a ray, with the ray queue empty, before the warp leaves the traversal loop to shade (swept 12..31)
 #endif
 #ifndef RG_POOL_LIVE
 #define RG_POOL_LIVE kPoolCtx    // contexts of a warp's pool that are actually used (<= kPoolCtx)
