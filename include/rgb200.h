@@ -82,6 +82,21 @@ typedef struct rg_instance {
     uint32_t mat_off; /* materialBufferOffset */
 } rg_instance;
 
+/* One node of the scene graph for the device-side walk (rg_set_entities): what TopLevelAS::TopLevelAS reads of an Entity
+ * (raygun/render/acceleration_structure.cpp:55-85, raygun/entity.hpp:32-131): the LOCAL transform as TRS (raygun/transform.hpp:
+ * 108-112), visibility, and the model's BufferRef offsets.  Entities are listed in the order Entity::forEachEntity visits them
+ * (DFS pre-order, entity.hpp:67-84), so a parent always precedes its children.  64 bytes. */
+typedef struct rg_entity {
+    float position[3];
+    int32_t parent;      /* index of the parent entity, -1 for the root */
+    float rotation[4];   /* glm::quat as w, x, y, z */
+    float scaling[3];
+    uint32_t flags;      /* RG_ENTITY_VISIBLE | RG_ENTITY_HAS_MODEL */
+    uint32_t mesh, vtx_off, idx_off, mat_off;   /* as in rg_instance; ignored without RG_ENTITY_HAS_MODEL */
+} rg_entity;
+#define RG_ENTITY_VISIBLE 1u
+#define RG_ENTITY_HAS_MODEL 2u
+
 /* The five GPU sections of the reference profiler (raygun/profiler.def:6-10), from CUDA events,
  * plus the NVLink gather and device-side ray counters.  A "ray" is one traceRayEXT with a non-zero
  * cull mask; sky look-ups (cull mask 0, closesthit.rchit:144) are counted separately. */
@@ -138,6 +153,14 @@ int rg_refit_blas(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vertices);
  * called every frame; rebuilds the TLAS from scratch on the device.  The caller performs the entity
  * DFS of acceleration_structure.cpp:63-85 (raygun_b200/host does). */
 int rg_set_instances(rg_ctx* ctx, const rg_instance* instances, uint32_t n_instances);
+
+/* The same step with the scene-graph walk on the device: globalTransform = parent's global * local as TRS
+ * structs (raygun/entity.cpp:187-199, transform.hpp:99-106), subtrees of invisible or zero-volume entities pruned
+ * (acceleration_structure.cpp:65-67), instance = transpose(toMat4()) as 3x4 (:44-45), instance order = DFS order.  The records are
+ * bit-identical to the host walk.  rg_set_entities copies from host memory; rg_set_entities_device reads device memory (for
+ * simulations that live on the GPU).  Returns the number of instances through n_instances_out (may be NULL). */
+int rg_set_entities(rg_ctx* ctx, const rg_entity* entities, uint32_t n_entities, uint32_t* n_instances_out);
+int rg_set_entities_device(rg_ctx* ctx, const rg_entity* d_entities, uint32_t n_entities, uint32_t* n_instances_out);
 
 /* RenderSystem::updateUniformBuffer + Raytracer::updateRenderTarget (render_system.cpp:246-268, raytracer.cpp:149-171) */
 int rg_set_ubo(rg_ctx* ctx, const rg_ubo* ubo);
@@ -203,6 +226,8 @@ int rg_read_gathered_rgba8(rg_ctx* ctx, void* dst);
 /* Builder introspection for the parity tests (Morton / sort output must be bit-exact):
  * sorted Morton keys and the primitive order of one mesh's BLAS, and of the current TLAS. */
 int rg_debug_blas_sort(rg_ctx* ctx, uint32_t mesh, uint32_t* keys_sorted, uint32_t* prim_order, uint32_t capacity);
+/* The instance records of the current TLAS in instance order (what rg_set_instances received or rg_set_entities composed). */
+int rg_debug_read_instances(rg_ctx* ctx, rg_instance* out, uint32_t capacity, uint32_t* n_out);
 int rg_debug_tlas_sort(rg_ctx* ctx, uint32_t* keys_sorted, uint32_t* inst_order, uint32_t capacity);
 /* Closest-hit queries straight into the traversal kernel (n rays: org xyz, dir xyz, tmin, tmax = 8 floats each);
  * out: t,u,v (3 floats) + inst, prim (2 u32) per ray; inst = 0xffffffff on miss. */

@@ -23,6 +23,11 @@ LIB_PATH = os.environ.get("RGB200_LIB") or os.path.join(_HERE, "librgb200.so")  
 # rg_render flags (include/rgb200.h)
 RG_FXAA, RG_SRGB8, RG_STRICT_IEEE, RG_DEBUG_IDS, RG_COUNT_TRAVERSAL, RG_NO_GATHER = 1, 2, 4, 8, 16, 32
 RG_SCHED_LANES, RG_SCHED_POOL, RG_SCHED_AUTO = 0, 1, 2
+RG_ENTITY_VISIBLE, RG_ENTITY_HAS_MODEL = 1, 2
+# rg_entity (include/rgb200.h), 64 bytes: local TRS + parent + model references of one scene-graph node, DFS pre-order
+ENTITY_DTYPE = np.dtype([("position", np.float32, 3), ("parent", np.int32), ("rotation", np.float32, 4), ("scaling", np.float32, 3), ("flags", np.uint32),
+                         ("mesh", np.uint32), ("vtx_off", np.uint32), ("idx_off", np.uint32), ("mat_off", np.uint32)])
+assert ENTITY_DTYPE.itemsize == 64
 IMG_FINAL, IMG_BASE, IMG_NORMAL, IMG_ROUGH, IMG_TRANSITIONS, IMG_ROUGH_A, IMG_ROUGH_B = range(7)
 
 ABI_SYMBOLS = (
@@ -31,7 +36,7 @@ ABI_SYMBOLS = (
     "rg_set_instances_device", "rg_set_ubo_device", "rg_framebuffer_device_ptr", "rg_set_gather_target", "rg_gather_buffer_export",
     "rg_gather_buffer_open", "rg_gather_buffer_close", "rg_read_gathered_rgba8", "rg_debug_blas_sort", "rg_debug_tlas_sort", "rg_debug_trace_rays",
     "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2", "rg_debug_last_trace_rays_ms",
-    "rg_set_trace_scheduler", "rg_set_partition", "rg_peer_export", "rg_peer_attach", "rg_peer_detach_all", "rg_sync_error",
+    "rg_set_trace_scheduler", "rg_set_entities", "rg_set_entities_device", "rg_debug_read_instances", "rg_set_partition", "rg_peer_export", "rg_peer_attach", "rg_peer_detach_all", "rg_sync_error",
 )
 
 
@@ -150,6 +155,28 @@ class Raytracer:
     def setupTopLevelAS(self, instances_raw):
         raw = np.ascontiguousarray(instances_raw, np.uint32)
         self._ck(self.lib.rg_set_instances(self.h, _p(raw), C.c_uint32(len(raw))))
+
+    def set_entities(self, entities) -> int:
+        """Scene-graph walk on the device (TopLevelAS::TopLevelAS + Entity::globalTransform, acceleration_structure.cpp:55-85):
+        entities = ENTITY_DTYPE array in DFS pre-order.  Builds the TLAS; returns the number of instances."""
+        e = np.ascontiguousarray(entities, ENTITY_DTYPE)
+        n = C.c_uint32()
+        self._ck(self.lib.rg_set_entities(self.h, _p(e), C.c_uint32(len(e)), C.byref(n)))
+        return n.value
+
+    def set_entities_device(self, d_ptr: int, n_entities: int) -> int:
+        n = C.c_uint32()
+        self._ck(self.lib.rg_set_entities_device(self.h, C.c_void_p(d_ptr), C.c_uint32(n_entities), C.byref(n)))
+        return n.value
+
+    def debug_read_instances(self) -> np.ndarray:
+        """(I,16) uint32: the rg_instance records of the current TLAS."""
+        n = C.c_uint32()
+        self._ck(self.lib.rg_debug_read_instances(self.h, None, C.c_uint32(0), C.byref(n)))
+        out = np.zeros((n.value, 16), np.uint32)
+        if n.value:
+            self._ck(self.lib.rg_debug_read_instances(self.h, _p(out), C.c_uint32(n.value), C.byref(n)))
+        return out
 
     def updateRenderTarget(self, ubo):
         u = np.ascontiguousarray(ubo, np.uint32)

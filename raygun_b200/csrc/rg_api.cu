@@ -10,6 +10,7 @@
 #include "../../include/rgb200.h"
 #include "rg_build.cuh"
 #include "rg_post.cuh"
+#include "rg_scene.cuh"
 #include "rg_trace.cuh"
 
 using namespace rg;
@@ -75,6 +76,7 @@ struct rg_ctx {
 
     float* dUbo = nullptr; rg_ubo hUbo{}; rg_ubo* hUboPinned = nullptr; bool uboOnDevice = false;
     uint32_t* dWork = nullptr; unsigned long long* dCounters = nullptr; float4* ctxPool = nullptr;
+    rg_entity* dEntities = nullptr; rg_instance* dEntTmp = nullptr; uint32_t* dEntEmit = nullptr; uint32_t* dEntCount = nullptr; uint32_t entCap = 0;
     // trace scheduler (rg_trace.cu: k_trace_lanes / k_trace_pool).  RG_SCHED_AUTO times both on consecutive frames and keeps the
     // faster one; the comparison is repeated every kSchedReprobe frames so a changing scene can change the choice.
     int schedMode = RG_SCHED_AUTO, schedChosen = RG_SCHED_LANES, schedProbe = -1, schedLast = RG_SCHED_LANES;
@@ -337,6 +339,7 @@ void rg_destroy(rg_ctx* ctx) {
     cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes);
     cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->dMeshRoots); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
     cudaFree(ctx->dUbo); cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->ctxPool);
+    cudaFree(ctx->dEntities); cudaFree(ctx->dEntTmp); cudaFree(ctx->dEntEmit); cudaFree(ctx->dEntCount);
     cudaFreeHost(ctx->hInstPinned); cudaFreeHost(ctx->hUboPinned);
     for(auto& m: ctx->meshes) m.scratch.release();
     ctx->tlasScratch.release();
@@ -495,6 +498,49 @@ int rg_set_instances_device(rg_ctx* ctx, const rg_instance* d_instances, uint32_
     if(ensureInstanceCapacity(ctx, n_instances ? n_instances : 1)) return 1;
     if(n_instances) CK(cudaMemcpyAsync(ctx->dInstRaw, d_instances, sizeof(rg_instance) * (size_t)n_instances, cudaMemcpyDeviceToDevice, ctx->stream));
     return buildTlasFromRaw(ctx, n_instances);
+}
+
+static int setEntities(rg_ctx* ctx, const rg_entity* src, bool onHost, uint32_t n, uint32_t* nOut) {
+    if(!ctx) return 1;
+    if(n && !src) return fail(ctx, "rg_set_entities: null input");
+    if(!ctx->blasBuilt) return fail(ctx, "rg_set_entities: call rg_build_blas first");
+    USE_DEVICE();
+    if(onHost)
+        for(uint32_t i = 0; i < n; ++i)
+            if(src[i].parent >= (int32_t)i) return fail(ctx, "rg_set_entities: entity %u has parent %d; entities must be in DFS pre-order (parents first)", i, src[i].parent);
+    if(n > ctx->entCap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->dEntities); cudaFree(ctx->dEntTmp); cudaFree(ctx->dEntEmit);
+        ctx->entCap = n + n / 2 + 16;
+        CK(cudaMalloc(&ctx->dEntities, sizeof(rg_entity) * (size_t)ctx->entCap));
+        CK(cudaMalloc(&ctx->dEntTmp, sizeof(rg_instance) * (size_t)ctx->entCap));
+        CK(cudaMalloc(&ctx->dEntEmit, 4 * (size_t)ctx->entCap));
+    }
+    if(!ctx->dEntCount) CK(cudaMalloc(&ctx->dEntCount, 4));
+    if(ensureInstanceCapacity(ctx, n ? n : 1)) return 1;   // at most one instance per entity
+    if(n) CK(cudaMemcpyAsync(ctx->dEntities, src, sizeof(rg_entity) * (size_t)n, onHost ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    launchEntityInstances(ctx->dEntities, n, ctx->dEntTmp, ctx->dEntEmit, ctx->dInstRaw, ctx->dEntCount, ctx->stream);
+    ctx->launches += n ? 2 : 0;
+    uint32_t count = 0;   // the builder sizes its launches on the host: one 4-byte read-back per frame
+    CK(cudaMemcpyAsync(&count, ctx->dEntCount, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if(nOut) *nOut = count;
+    return buildTlasFromRaw(ctx, count);
+}
+int rg_set_entities(rg_ctx* ctx, const rg_entity* entities, uint32_t n_entities, uint32_t* n_instances_out) {
+    return setEntities(ctx, entities, true, n_entities, n_instances_out);
+}
+int rg_set_entities_device(rg_ctx* ctx, const rg_entity* d_entities, uint32_t n_entities, uint32_t* n_instances_out) {
+    return setEntities(ctx, d_entities, false, n_entities, n_instances_out);
+}
+int rg_debug_read_instances(rg_ctx* ctx, rg_instance* out, uint32_t capacity, uint32_t* n_out) {
+    if(!ctx || !n_out) return 1;
+    USE_DEVICE();
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_out = ctx->nInst;
+    const uint32_t n = ctx->nInst < capacity ? ctx->nInst : capacity;
+    if(n && out) CK(cudaMemcpy(out, ctx->dInstRaw, sizeof(rg_instance) * (size_t)n, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int rg_set_ubo(rg_ctx* ctx, const rg_ubo* ubo) {

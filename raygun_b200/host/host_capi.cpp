@@ -141,16 +141,24 @@ int rgh_render_entities(const void* vertices, uint32_t nVtx, const uint32_t* ind
         scene.camera->lookAt({camTarget[0], camTarget[1], camTarget[2]});
         render::RenderSystem rs(W, H, device);
         rs.ubo().num_samples = numSamples; rs.ubo().max_recursions = maxRecursions;
-        rs.useFXAA = useFXAA != 0;
+        rs.useFXAA = (useFXAA & 1) != 0;
+        rs.raytracer().deviceSceneWalk = (useFXAA & 2) != 0;   // bit 1: scene-graph walk on the GPU (rg_set_entities)
         rs.setupModelBuffers(mods);
         rs.raytracer().setupBottomLevelAS();
         rs.render(scene);
         std::vector<uint8_t> frame;
         rs.readFrame(frame);
         std::memcpy(rgba8, frame.data(), frame.size());
-        const auto& inst = rs.raytracer().instances;
-        if(instancesOut) std::memcpy(instancesOut, inst.data(), inst.size() * sizeof(rg_instance));
-        if(nInstancesOut) *nInstancesOut = (uint32_t)inst.size();
+        if(rs.raytracer().deviceSceneWalk) {   // what the device composed
+            uint32_t n = 0;
+            rg_debug_read_instances(rs.raytracer().ctx, nullptr, 0, &n);
+            if(instancesOut && n) rg_debug_read_instances(rs.raytracer().ctx, (rg_instance*)instancesOut, n, &n);
+            if(nInstancesOut) *nInstancesOut = n;
+        } else {
+            const auto& inst = rs.raytracer().instances;
+            if(instancesOut) std::memcpy(instancesOut, inst.data(), inst.size() * sizeof(rg_instance));
+            if(nInstancesOut) *nInstancesOut = (uint32_t)inst.size();
+        }
         if(timingsOut) { const rg_timings t = rs.timings(); timingsOut[0] = t.as_build_ms; timingsOut[1] = t.rt_total_ms; }
     });
 }

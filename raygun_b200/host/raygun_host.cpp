@@ -116,7 +116,41 @@ void Raytracer::gatherInstances(const Scene& scene, std::vector<rg_instance>& ou
         return true;
     });
 }
+// The same walk without the transform composition: every entity (pruning is the device's job too) as its LOCAL TRS + parent index,
+// in the order forEachEntity visits them.  rg_set_entities composes globalTransform and the 3x4 on the GPU (bit-identical records).
+void Raytracer::gatherEntities(const Scene& scene, std::vector<rg_entity>& out) {
+    out.clear();
+    std::vector<std::pair<const Entity*, int32_t>> stack;   // (entity, index of its parent in `out`)
+    stack.push_back({scene.root.get(), -1});
+    while(!stack.empty()) {
+        const auto [entity, parent] = stack.back();
+        stack.pop_back();
+        rg_entity e{};
+        const Transform& t = entity->transform();
+        e.position[0] = t.position.x; e.position[1] = t.position.y; e.position[2] = t.position.z;
+        e.rotation[0] = t.rotation.w; e.rotation[1] = t.rotation.x; e.rotation[2] = t.rotation.y; e.rotation[3] = t.rotation.z;
+        e.scaling[0] = t.scaling.x; e.scaling[1] = t.scaling.y; e.scaling[2] = t.scaling.z;
+        e.parent = parent;
+        e.flags = (entity->isVisible() ? RG_ENTITY_VISIBLE : 0u) | (entity->model ? RG_ENTITY_HAS_MODEL : 0u);
+        if(entity->model) {
+            e.mesh = entity->model->mesh->meshIndex;
+            e.vtx_off = entity->model->mesh->vertexBufferRef.offsetInElements();
+            e.idx_off = entity->model->mesh->indexBufferRef.offsetInElements();
+            e.mat_off = entity->model->materialBufferRef.offsetInElements();
+        }
+        const int32_t self = (int32_t)out.size();
+        out.push_back(e);
+        const auto& ch = entity->children();
+        for(auto it = ch.rbegin(); it != ch.rend(); ++it) stack.push_back({it->get(), self});   // reversed: pre-order pops the first child first
+    }
+}
 void Raytracer::setupTopLevelAS(const Scene& scene) {
+    if(deviceSceneWalk) {
+        gatherEntities(scene, entities);
+        uint32_t n = 0;
+        check(ctx, rg_set_entities(ctx, entities.data(), (uint32_t)entities.size(), &n), "rg_set_entities");
+        return;
+    }
     gatherInstances(scene, instances);
     check(ctx, rg_set_instances(ctx, instances.data(), (uint32_t)instances.size()), "rg_set_instances");
 }

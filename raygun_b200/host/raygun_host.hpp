@@ -212,6 +212,11 @@ struct Raytracer {
     rg_ctx* ctx = nullptr;
     std::vector<rg_instance> instances;   // the last TLAS input (also useful without a GPU)
     static void gatherInstances(const Scene& scene, std::vector<rg_instance>& out);
+    /// true: upload local TRS + parent links and let the GPU walk the scene graph (rg_set_entities) -- for scenes with
+    /// thousands of animated entities, where composing every globalTransform on the host dominates the frame.
+    bool deviceSceneWalk = false;
+    std::vector<rg_entity> entities;
+    static void gatherEntities(const Scene& scene, std::vector<rg_entity>& out);
 };
 
 /// Headless RenderSystem: same buffer packing and per-frame order as the reference, no swapchain / ImGui.

@@ -328,5 +328,24 @@ class AnimatedBalls:
         xf[-1, 0] = xf[-1, 5] = xf[-1, 10] = 1
         return xf
 
+    def entities(self, t: float) -> np.ndarray:
+        """The same frame as a scene graph for rg_set_entities: a root, the balls as its children (local TRS: bounce height, rotation
+        about Y as a quaternion) and the floor.  The device composes the transforms; the host only fills 10 floats per ball."""
+        from . import ENTITY_DTYPE, RG_ENTITY_VISIBLE, RG_ENTITY_HAS_MODEL
+        nb = self.n * self.n
+        e = np.zeros(nb + 2, ENTITY_DTYPE)
+        e["parent"][0] = -1; e["parent"][1:] = 0
+        e["rotation"][:, 0] = 1.0
+        e["scaling"][:] = 1.0
+        e["flags"][0] = RG_ENTITY_VISIBLE
+        e["flags"][1:] = RG_ENTITY_VISIBLE | RG_ENTITY_HAS_MODEL
+        y = 1.0 + 3.0 * np.abs(np.sin(2 * np.pi * (0.5 + self.u) * t + 2 * np.pi * self.v))
+        half = 0.5 * t * (1.0 + self.u)
+        e["position"][1:-1, 0] = self.gx; e["position"][1:-1, 1] = y; e["position"][1:-1, 2] = self.gz
+        e["rotation"][1:-1, 0] = np.cos(half); e["rotation"][1:-1, 2] = np.sin(half)
+        for k, name in enumerate(("mesh", "vtx_off", "idx_off", "mat_off")):
+            e[name][1:] = self.meta[:, k]
+        return e
+
     def scene(self, t: float) -> SceneData:
         return SceneData(self.vertices, self.indices, self.meshes, self.materials, self.instances(t), self.meta, name=f"balls{self.n}x{self.n}")

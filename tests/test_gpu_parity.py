@@ -332,3 +332,64 @@ def test_strict_ieee_switch_only_changes_diffuse_materials(rgmod, O, S, example_
     r = O.f16_to_f32(ref["rough"])
     assert np.isnan(r).any()
     assert float((np.isnan(g) == np.isnan(r)).mean()) >= 0.9999
+
+
+def _random_scene_graph(rng, n, n_models):
+    """Random tree flattened in DFS pre-order -> (ENTITY_DTYPE array, host-shim arrays)."""
+    import raygun_b200 as rg
+    children = {-1: []}
+    for k in range(n):
+        parent = -1 if k == 0 or rng.random() < 0.1 else int(rng.integers(0, k))
+        children.setdefault(parent, []).append(k); children.setdefault(k, [])
+    order = []
+    def visit(k):
+        order.append(k)
+        for c in children[k]:
+            visit(c)
+    for r in children[-1]:
+        visit(r)
+    new_index = {old: i for i, old in enumerate(order)}
+    parent_of = {c: p for p, cs in children.items() for c in cs}
+    ents = np.zeros(n, rg.ENTITY_DTYPE)
+    for i, old in enumerate(order):
+        p = parent_of[old]
+        q = rng.normal(size=4).astype(np.float32); q /= np.float32(np.sqrt((q * q).sum()))
+        e = ents[i]
+        e["parent"] = -1 if p < 0 else new_index[p]
+        e["position"] = rng.uniform(-5, 5, 3).astype(np.float32)
+        e["rotation"] = q
+        e["scaling"] = rng.uniform(0.3, 2.0, 3).astype(np.float32)
+        if rng.random() < 0.05:
+            e["scaling"][int(rng.integers(0, 3))] = 0.0      # zero volume: prunes the subtree
+        vis = rng.random() > 0.07
+        has = rng.random() < 0.7
+        e["flags"] = (rg.RG_ENTITY_VISIBLE if vis else 0) | (rg.RG_ENTITY_HAS_MODEL if has else 0)
+        m = int(rng.integers(0, n_models))
+        e["mesh"], e["vtx_off"], e["idx_off"], e["mat_off"] = m, 100 * m, 300 * m, 5 * m
+    return ents
+
+
+def test_device_scene_graph_walk_matches_host_walk(rgmod, example_scene):
+    """rg_set_entities (TRS composition, pruning, compaction on the device) against the C++ host shim's
+    Raytracer::gatherInstances over Scene / Entity / Transform (the mirror of acceleration_structure.cpp:55-85): bit-exact."""
+    import ctypes as C
+    import os
+    host = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(rgmod.__file__)), "libraygun_host.so"))
+    rng = np.random.default_rng(7)
+    rt = rgmod.Raytracer(64, 36)
+    rt.load_scene(example_scene)
+    for n in (1, 5, 300, 4000):
+        ents = _random_scene_graph(rng, n, 4)
+        models = np.array([[100 * m, 1, 300 * m, 3, 5 * m, 1] for m in range(4)], np.uint32)
+        he = np.stack([ents["parent"], np.where(ents["flags"] & rgmod.RG_ENTITY_HAS_MODEL, ents["mesh"].astype(np.int32), -1),
+                       (ents["flags"] & rgmod.RG_ENTITY_VISIBLE).astype(np.int32)], 1).astype(np.int32)
+        trs = np.concatenate([ents["position"], ents["rotation"], ents["scaling"]], 1).astype(np.float32)
+        want = np.zeros((n, 16), np.uint32); cnt = C.c_uint32()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        he = np.ascontiguousarray(he); trs = np.ascontiguousarray(trs)
+        assert host.rgh_gather_instances(p(models), 4, p(he), p(trs), n, p(want), C.byref(cnt)) == 0
+        got_n = rt.set_entities(ents)
+        got = rt.debug_read_instances()
+        assert got_n == cnt.value == len(got), (n, got_n, cnt.value)
+        assert np.array_equal(got, want[:cnt.value]), f"{n} entities: instance records differ"
+    rt.close()

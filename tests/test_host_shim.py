@@ -116,3 +116,9 @@ def test_render_through_entity_tree_equals_python_path(host, example_scene):
     want = rt.read_rgba8()
     d = np.abs(frame[..., :3].astype(int) - want[..., :3].astype(int)).max(axis=2)
     assert float((d <= 1).mean()) > 0.999   # camera matrices agree to ~1e-7: a handful of edge pixels may move
+    # the same scene with the scene-graph walk on the GPU (Raytracer::deviceSceneWalk -> rg_set_entities): identical instances and frame
+    frame2 = np.zeros_like(frame); inst2 = np.zeros_like(inst); n2 = C.c_uint32()
+    rc = host.rgh_render_entities(_p(v), len(v), _p(i), len(i), _p(m), len(m), _p(models), 4, _p(ents), _p(trs), len(ents), _p(cam_pos), _p(cam_tgt),
+                                  W, H, 2, 5, 1 | 2, 0, _p(frame2), _p(inst2), C.byref(n2), _p(tm))
+    assert rc == 0, host.rgh_last_error().decode()
+    assert n2.value == n.value and np.array_equal(inst2[:4], inst[:4]) and np.array_equal(frame2, frame)

@@ -22,6 +22,12 @@ for n in range(120):
     tm = rt.timings()
     if n >= 5:
         as_ms.append(tm["as_build_ms"]); tr_ms.append(tm["rt_only_ms"]); tot.append(tm["rt_total_ms"])
+# the same animation through the device-side scene-graph walk (rg_set_entities): host time per frame of both routes
+t_inst, t_ent = [], []
+for n in range(40):
+    t0 = time.perf_counter(); inst = rt.pack_instances(balls.instances(n / 60.0), balls.meta); rt.setupTopLevelAS(inst); rt.sync(); t_inst.append(time.perf_counter() - t0)
+    t0 = time.perf_counter(); ents = balls.entities(n / 60.0); ni = rt.set_entities(ents); rt.sync(); t_ent.append(time.perf_counter() - t0)
+res.update(host_ms_instances_route=float(np.median(t_inst)) * 1e3, host_ms_entities_route=float(np.median(t_ent)) * 1e3, entities_route_instances=int(ni))
 res.update(tlas_rebuild_ms=float(np.median(as_ms)), trace_ms=float(np.median(tr_ms)), rt_total_ms=float(np.median(tot)), rays=tm["rays"],
            mrays_s=tm["rays"] / float(np.median(tr_ms)) / 1e3, bvh=rt.debug_bvh_stats())
 # refit: vertex-wobbled copy of the flattened sphere grid (1 003 522 triangles)
