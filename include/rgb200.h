@@ -162,6 +162,19 @@ int rg_set_instances(rg_ctx* ctx, const rg_instance* instances, uint32_t n_insta
 int rg_set_entities(rg_ctx* ctx, const rg_entity* entities, uint32_t n_entities, uint32_t* n_instances_out);
 int rg_set_entities_device(rg_ctx* ctx, const rg_entity* d_entities, uint32_t n_entities, uint32_t* n_instances_out);
 
+/* Stand-in for PhysicsSystem::update (raygun/physics/physics_system.cpp:241-258): rigid spheres under gravity
+ * (0, -9.81, 0) (physics_system.cpp:68) over the plane y = floor_y, semi-implicit Euler, no sphere-sphere contacts.  Both arrays
+ * live in DEVICE memory and are updated in place: body i drives entity i (radius <= 0: no dynamic actor); the pose is written as
+ * the entity's local transform, as the reference does for actors under an identity parent.  Follow with rg_set_entities_device:
+ * an animated frame then needs no host data at all. */
+typedef struct rg_sphere_body {
+    float velocity[3];
+    float radius;
+    float angular_velocity[3];
+    float restitution;   /* default material: 0.6 (physics_system.cpp:40) */
+} rg_sphere_body;
+int rg_physics_step_spheres(rg_ctx* ctx, rg_entity* d_entities, rg_sphere_body* d_bodies, uint32_t n, float dt, float floor_y);
+
 /* RenderSystem::updateUniformBuffer + Raytracer::updateRenderTarget (render_system.cpp:246-268, raytracer.cpp:149-171) */
 int rg_set_ubo(rg_ctx* ctx, const rg_ubo* ubo);
 

@@ -141,3 +141,34 @@ def f16_to_f32(a):
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def step_spheres(entities, bodies, dt, floor_y=0.0):
+    """CPU restatement (numpy binary32, one rounded operation at a time, same order) of raygun_b200/csrc/rg_scene.cu:k_step_spheres --
+    the stand-in for PhysicsSystem::update (raygun/physics/physics_system.cpp:241-258; gravity :68, default restitution :40).
+    entities: ENTITY_DTYPE array, bodies: SPHERE_BODY_DTYPE array; returns updated copies."""
+    f = np.float32
+    e, b = entities.copy(), bodies.copy()
+    dyn = b["radius"] > 0
+    dt = f(dt)
+    vel = b["velocity"].copy(); pos = e["position"].copy()
+    vel[:, 1] = vel[:, 1] + f(-9.81) * dt
+    pos = pos + vel * dt
+    rest = f(floor_y) + b["radius"]
+    hit = (pos[:, 1] < rest) & (vel[:, 1] < 0)
+    pos[:, 1] = np.where(hit, rest + (rest - pos[:, 1]) * b["restitution"], pos[:, 1])
+    vel[:, 1] = np.where(hit, (-vel[:, 1]) * b["restitution"], vel[:, 1])
+    h = f(0.5) * dt
+    w = b["angular_velocity"] * h
+    wx, wy, wz = w[:, 0], w[:, 1], w[:, 2]
+    qw, qx, qy, qz = (e["rotation"][:, k] for k in range(4))
+    nw = qw + (((-wx) * qx - wy * qy) - wz * qz)
+    nx = qx + ((wx * qw + wy * qz) - wz * qy)
+    ny = qy + ((wy * qw - wx * qz) + wz * qx)
+    nz = qz + ((wz * qw + wx * qy) - wy * qx)
+    inv = f(1.0) / np.sqrt((nw * nw + nx * nx) + (ny * ny + nz * nz))
+    rot = np.stack([nw * inv, nx * inv, ny * inv, nz * inv], 1).astype(f)
+    e["position"] = np.where(dyn[:, None], pos, e["position"])
+    e["rotation"] = np.where(dyn[:, None], rot, e["rotation"])
+    b["velocity"] = np.where(dyn[:, None], vel, b["velocity"])
+    return e, b

@@ -28,6 +28,8 @@ RG_ENTITY_VISIBLE, RG_ENTITY_HAS_MODEL = 1, 2
 ENTITY_DTYPE = np.dtype([("position", np.float32, 3), ("parent", np.int32), ("rotation", np.float32, 4), ("scaling", np.float32, 3), ("flags", np.uint32),
                          ("mesh", np.uint32), ("vtx_off", np.uint32), ("idx_off", np.uint32), ("mat_off", np.uint32)])
 assert ENTITY_DTYPE.itemsize == 64
+SPHERE_BODY_DTYPE = np.dtype([("velocity", np.float32, 3), ("radius", np.float32), ("angular_velocity", np.float32, 3), ("restitution", np.float32)])
+assert SPHERE_BODY_DTYPE.itemsize == 32
 IMG_FINAL, IMG_BASE, IMG_NORMAL, IMG_ROUGH, IMG_TRANSITIONS, IMG_ROUGH_A, IMG_ROUGH_B = range(7)
 
 ABI_SYMBOLS = (
@@ -36,7 +38,7 @@ ABI_SYMBOLS = (
     "rg_set_instances_device", "rg_set_ubo_device", "rg_framebuffer_device_ptr", "rg_set_gather_target", "rg_gather_buffer_export",
     "rg_gather_buffer_open", "rg_gather_buffer_close", "rg_read_gathered_rgba8", "rg_debug_blas_sort", "rg_debug_tlas_sort", "rg_debug_trace_rays",
     "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2", "rg_debug_last_trace_rays_ms",
-    "rg_set_trace_scheduler", "rg_set_entities", "rg_set_entities_device", "rg_debug_read_instances", "rg_set_partition", "rg_peer_export", "rg_peer_attach", "rg_peer_detach_all", "rg_sync_error",
+    "rg_set_trace_scheduler", "rg_set_entities", "rg_set_entities_device", "rg_debug_read_instances", "rg_physics_step_spheres", "rg_set_partition", "rg_peer_export", "rg_peer_attach", "rg_peer_detach_all", "rg_sync_error",
 )
 
 
@@ -168,6 +170,10 @@ class Raytracer:
         n = C.c_uint32()
         self._ck(self.lib.rg_set_entities_device(self.h, C.c_void_p(d_ptr), C.c_uint32(n_entities), C.byref(n)))
         return n.value
+
+    def physics_step_spheres(self, d_entities: int, d_bodies: int, n: int, dt: float, floor_y: float = 0.0):
+        """One step of the rigid-sphere stand-in for PhysicsSystem::update on DEVICE arrays (ENTITY_DTYPE / SPHERE_BODY_DTYPE)."""
+        self._ck(self.lib.rg_physics_step_spheres(self.h, C.c_void_p(d_entities), C.c_void_p(d_bodies), C.c_uint32(n), C.c_float(dt), C.c_float(floor_y)))
 
     def debug_read_instances(self) -> np.ndarray:
         """(I,16) uint32: the rg_instance records of the current TLAS."""

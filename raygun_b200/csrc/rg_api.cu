@@ -533,6 +533,15 @@ int rg_set_entities(rg_ctx* ctx, const rg_entity* entities, uint32_t n_entities,
 int rg_set_entities_device(rg_ctx* ctx, const rg_entity* d_entities, uint32_t n_entities, uint32_t* n_instances_out) {
     return setEntities(ctx, d_entities, false, n_entities, n_instances_out);
 }
+int rg_physics_step_spheres(rg_ctx* ctx, rg_entity* d_entities, rg_sphere_body* d_bodies, uint32_t n, float dt, float floor_y) {
+    if(!ctx) return 1;
+    if(n && (!d_entities || !d_bodies)) return fail(ctx, "rg_physics_step_spheres: null input");
+    USE_DEVICE();
+    launchStepSpheres(d_entities, d_bodies, n, dt, floor_y, ctx->stream);
+    ctx->launches += n ? 1 : 0;
+    CK(cudaGetLastError());
+    return 0;
+}
 int rg_debug_read_instances(rg_ctx* ctx, rg_instance* out, uint32_t capacity, uint32_t* n_out) {
     if(!ctx || !n_out) return 1;
     USE_DEVICE();

@@ -142,7 +142,44 @@ __global__ void __launch_bounds__(1024) k_entity_compact(const rg_instance* __re
     if(tid == 0) *count = sCarry;
 }
 
+// Stand-in for PhysicsSystem::update (raygun/physics/physics_system.cpp:241-258; PhysX itself is out of scope): the contract of that
+// function is "after the step, write each dynamic actor's pose into its entity's transform".  Rigid spheres under gravity
+// (physics_system.cpp:68: (0, -9.81, 0)) over a floor plane, semi-implicit Euler, restitution per body (default material 0.6,
+// physics_system.cpp:40); orientation integrated from the angular velocity.  No sphere-sphere contacts.  Bodies must hang directly
+// under an identity-transform parent (the pose is written as the LOCAL transform).  Explicitly rounded operations in a fixed order:
+// the oracle's numpy restatement (oracle/oracle.py: step_spheres) reproduces the state bit for bit.
+__global__ void k_step_spheres(rg_entity* __restrict__ ents, rg_sphere_body* __restrict__ bodies, uint32_t n, float dt, float floorY) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i >= n) return;
+    rg_sphere_body b = bodies[i];
+    if(!(b.radius > 0.0f)) return;   // no dynamic actor
+    rg_entity e = ents[i];
+    b.velocity[1] = FA(b.velocity[1], FM(-9.81f, dt));
+    for(int k = 0; k < 3; ++k) e.position[k] = FA(e.position[k], FM(b.velocity[k], dt));
+    const float rest = FA(floorY, b.radius);
+    if(e.position[1] < rest && b.velocity[1] < 0.0f) {
+        e.position[1] = FA(rest, FM(FS(rest, e.position[1]), b.restitution));   // the part of the step below the floor comes back up
+        b.velocity[1] = FM(-b.velocity[1], b.restitution);
+    }
+    // q += dt/2 * (0, w) * q, then normalise
+    const float h = FM(0.5f, dt);
+    const float wx = FM(b.angular_velocity[0], h), wy = FM(b.angular_velocity[1], h), wz = FM(b.angular_velocity[2], h);
+    const float qw = e.rotation[0], qx = e.rotation[1], qy = e.rotation[2], qz = e.rotation[3];
+    float nw = FA(qw, FS(FS(FM(-wx, qx), FM(wy, qy)), FM(wz, qz)));
+    float nx = FA(qx, FS(FA(FM(wx, qw), FM(wy, qz)), FM(wz, qy)));
+    float ny = FA(qy, FA(FS(FM(wy, qw), FM(wx, qz)), FM(wz, qx)));
+    float nz = FA(qz, FS(FA(FM(wz, qw), FM(wx, qy)), FM(wy, qx)));
+    const float inv = __fdiv_rn(1.0f, __fsqrt_rn(FA(FA(FM(nw, nw), FM(nx, nx)), FA(FM(ny, ny), FM(nz, nz)))));
+    e.rotation[0] = FM(nw, inv); e.rotation[1] = FM(nx, inv); e.rotation[2] = FM(ny, inv); e.rotation[3] = FM(nz, inv);
+    ents[i] = e;
+    bodies[i] = b;
+}
+
 }  // namespace
+
+void launchStepSpheres(rg_entity* dEntities, rg_sphere_body* dBodies, uint32_t n, float dt, float floorY, cudaStream_t st) {
+    if(n) k_step_spheres<<<(n + 127) / 128, 128, 0, st>>>(dEntities, dBodies, n, dt, floorY);
+}
 
 void launchEntityInstances(const rg_entity* dEntities, uint32_t n, rg_instance* dTmp, uint32_t* dEmit, rg_instance* dOut, uint32_t* dCount, cudaStream_t st) {
     if(n == 0) { cudaMemsetAsync(dCount, 0, 4, st); return; }

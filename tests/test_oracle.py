@@ -273,3 +273,22 @@ def test_golden_frame_regression(oracle_example):
     assert np.array_equal(r["inst"], g["inst"]) and np.array_equal(r["prim"], g["prim"])
     d = np.abs(r["rgba8"].astype(int) - g["rgba8"].astype(int))
     assert d.max() <= 1   # libm differences between hosts may move a rounding
+
+
+def test_sphere_integrator_restatement_behaves():
+    """oracle.step_spheres (stand-in for PhysicsSystem::update): gravity, floor bounce with restitution, unit quaternions."""
+    import raygun_b200 as rg
+    from oracle import oracle as O
+    e = np.zeros(3, rg.ENTITY_DTYPE); b = np.zeros(3, rg.SPHERE_BODY_DTYPE)
+    e["rotation"][:, 0] = 1; e["scaling"][:] = 1
+    e["position"][:, 1] = (5.0, 5.0, 5.0)
+    b["radius"] = (1.0, 1.0, 0.0); b["restitution"] = (0.6, 1.0, 0.6); b["angular_velocity"][0] = (1, 2, 3)
+    peak, vmax = np.zeros(3), np.zeros(3)
+    for k in range(600):
+        e, b = O.step_spheres(e, b, 1 / 120.0)
+        if k > 300:
+            peak = np.maximum(peak, e["position"][:, 1])
+    assert e["position"][2, 1] == 5.0 and np.all(b["velocity"][2] == 0)          # no actor: untouched
+    assert e["position"][:2, 1].min() >= 1.0 - 1e-4                               # never below floor + radius
+    assert peak[0] < 2.5 < peak[1]                                                # restitution 0.6 loses energy, 1.0 keeps bouncing
+    assert abs(float((e["rotation"][0] ** 2).sum()) - 1.0) < 1e-5
