@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 TAG=$1; shift
 mkdir -p build/variants
 C=raygun_b200/csrc
-make -C $C -s >/dev/null
+make -C $C -s >/dev/null 2>&1
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 /usr/local/cuda/bin/nvcc $ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -fmad=false -Xptxas -v "$@" -c ${SRC:-$C/rg_trace.cu} -o build/variants/rg_trace_$TAG.o 2>&1 | grep -A2 "k_trace_poolILb0ELb0" | grep -E "spill|Used" || true
 /usr/local/cuda/bin/nvcc $ARCH -shared -o build/variants/librgb200_$TAG.so $C/_obj/rg_api.o $C/_obj/rg_build.o $C/_obj/rg_post.o $C/_obj/rg_scene.o build/variants/rg_trace_$TAG.o -lcudart
