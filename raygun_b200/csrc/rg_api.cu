@@ -214,7 +214,7 @@ constexpr uint32_t kSchedReprobe = 64;
 // Which trace kernel runs this frame.  AUTO: once the heavy-first tile order exists (second frame on), one frame is timed with
 // each scheduler (CUDA events around the kernel; the host waits for that one frame's kernel when it needs the number) and the
 // faster one is kept for the next kSchedReprobe frames.  Both produce bit-identical images, so switching is invisible.
-bool chooseScheduler(rg_ctx* c) {
+bool chooseScheduler(rg_ctx* c, uint32_t flags) {
     if(c->schedMode != RG_SCHED_AUTO) { c->schedProbe = -1; c->schedLast = c->schedMode; return c->schedMode == RG_SCHED_POOL; }
     if(c->schedProbe >= 0) {   // harvest the probe frame
         float ms = -1.0f;
@@ -224,7 +224,7 @@ bool chooseScheduler(rg_ctx* c) {
         if(c->schedMs[0] >= 0.0f && c->schedMs[1] >= 0.0f) { c->schedChosen = c->schedMs[1] < c->schedMs[0] ? RG_SCHED_POOL : RG_SCHED_LANES; c->schedFrames = 0; }
     }
     int mode = c->schedChosen;
-    if(c->haveTileHistory) {
+    if(c->haveTileHistory && !(flags & RG_COUNT_TRAVERSAL)) {   // the instrumented kernel is slower: never a probe frame
         if(c->schedMs[0] < 0.0f) mode = c->schedProbe = RG_SCHED_LANES;
         else if(c->schedMs[1] < 0.0f) mode = c->schedProbe = RG_SCHED_POOL;
         else if(++c->schedFrames >= kSchedReprobe) { c->schedMs[0] = c->schedMs[1] = -1.0f; mode = c->schedProbe = RG_SCHED_LANES; }
@@ -598,7 +598,7 @@ int rg_render(rg_ctx* ctx, uint32_t flags) {
         ctx->haveTileHistory = true;
     }
     TraceParams tp; fillTraceParams(ctx, tp, flags);
-    const bool pool = chooseScheduler(ctx);
+    const bool pool = chooseScheduler(ctx, flags);
     if(ctx->schedProbe >= 0) CK(cudaEventRecord(ctx->ev[EV_PROBE0], ctx->stream));
     launchTrace(tp, ctx->numSms, pool, ctx->stream);
     if(ctx->schedProbe >= 0) CK(cudaEventRecord(ctx->ev[EV_PROBE1], ctx->stream));
