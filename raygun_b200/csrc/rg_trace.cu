@@ -102,7 +102,8 @@ __device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t a, uint32_t b) {
 
 template <int J>
 __device__ __forceinline__ float byteF(uint32_t w) {  // 1 + b / 32768 for byte J of w: ONE PRMT puts b into mantissa bits 15..8 of 1.0f;
-    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u + (J << 4)));   // the affine map back to b is folded into the FFMA constants
+    // (the constant is the FIRST operand so that the selector is the instruction's immediate: PRMT Rd, Rconst, 0x32x0, Rw)
+    return __uint_as_float(__byte_perm(0x3F800000u, w, 0x3240u + (J << 4)));   // the affine map back to b is folded into the FFMA constants
 }
 
 // One child of a node: slab test on the quantised planes, then OR the child's bits into the hit mask.  Branch-free:
