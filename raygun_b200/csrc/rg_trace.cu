@@ -238,7 +238,11 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* _
     const uint32_t mx = (r.octinv & 4u) ? 0u : 0xffffffffu, my = (r.octinv & 2u) ? 0u : 0xffffffffu, mz = (r.octinv & 1u) ? 0u : 0xffffffffu;
     const uint32_t octinv4 = r.octinv * 0x01010101u;
     uint32_t hitmask = 0;
+#ifdef RG_UNROLL_HALVES
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for(int half = 0; half < 2; ++half) {   // slots 0..3, then 4..7: a rolled loop keeps the hot code small for the instruction cache
         const uint32_t lx = half ? n2.y : n2.x, ly = half ? n2.w : n2.z, lz = half ? n3.y : n3.x;
         const uint32_t hx = half ? n3.w : n3.z, hy = half ? n4.y : n4.x, hz = half ? n4.w : n4.z;
