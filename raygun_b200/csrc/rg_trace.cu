@@ -71,7 +71,14 @@ struct RayCtx {
     int kx, ky, kz;
 };
 
-__device__ __forceinline__ float sel3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
+// component k of (x, y, z) as two predicated selects: written in PTX because the compiler turns the ?: chain into divergent branches
+// (8 reconvergence barriers per triangle test; the axes differ from lane to lane)
+__device__ __forceinline__ float sel3(int k, float x, float y, float z) {
+    float r;
+    asm("{\n\t.reg .pred p0, p1;\n\tsetp.eq.s32 p0, %1, 0;\n\tsetp.eq.s32 p1, %1, 1;\n\tselp.f32 %0, %3, %4, p1;\n\tselp.f32 %0, %2, %0, p0;\n\t}"
+        : "=f"(r) : "r"(k), "f"(x), "f"(y), "f"(z));
+    return r;
+}
 __device__ __forceinline__ float __frcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 __device__ __forceinline__ void setupRay(RayCtx& r, float ox, float oy, float oz, float dx, float dy, float dz) {
