@@ -273,11 +273,10 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
     T.tg.y &= T.tg.y - 1u;
     if(T.curInst == kInvalid) {
         const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + (T.tg.x + bit));
-        const uint4 l3 = __ldg(lp + 3);
+        const uint4 l3 = __ldg(lp + 3), l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);   // all four in flight at once
         // instance of an empty mesh, or stack exhausted (never with sane scenes): skip
         if(l3.x != kInvalid && T.sp + 6 <= kStackSize) {
             if(COUNT) cnt[CNT_INST]++;
-            const uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);
             const float ox = wray.ox(), oy = wray.oy(), oz = wray.oz();
             bool enter = true;
             if(l3.z) {
