@@ -91,6 +91,49 @@ rgh_scene* rgh_example_scene_load(const char* resourcesDir, uint32_t W, uint32_t
        })) { delete s; return nullptr; }
     return s;
 }
+
+// ---- ray-traced text (ui/text.cpp): `text` laid out by TextGenerator with the font resources/fonts/<font>.obj and the material
+// resources/materials/<material>.rgmat.json, above the example scene's floor material as a ground quad; only the glyphs the text
+// uses are turned into models (the reference registers all 124; the fixture stays small).  widths128 receives Font::charWidth.
+rgh_scene* rgh_text_scene_load(const char* resourcesDir, const char* fontName, const char* materialName, const char* text, int align, uint32_t W, uint32_t H,
+                               float* widths128, uint32_t* glyphCount) {
+    auto* s = new rgh_scene();
+    if(guarded([&] {
+           s->rm = std::make_unique<ResourceManager>(resourcesDir);
+           s->scene = std::make_unique<Scene>(W, H);
+           auto font = s->rm->loadFont(fontName);
+           uint32_t n = 0;
+           for(size_t k = 0; k < font->charMap.size(); ++k) { if(widths128) widths128[k] = font->charWidth[k]; n += font->charMap[k] ? 1u : 0u; }
+           if(glyphCount) *glyphCount = n;
+           ui::Font used = *font;
+           for(size_t k = 0; k < used.charMap.size(); ++k)
+               if(!std::strchr(text, (int)k) || k == 0) used.charMap[k].reset();
+           ui::TextGenerator gen(used, s->rm->loadMaterial(materialName), [&](std::shared_ptr<render::Model> m) { s->rm->registerModel(std::move(m)); });
+           auto [ent, bounds] = gen.textWithBounds(text, (ui::Alignment)align);
+           ent->moveTo({0.0f, 1.0f, 0.0f});
+           s->scene->root->addChild(ent);
+           // ground: one quad with the floor material (grid effect, reflections of the glyphs)
+           auto ground = std::make_shared<render::Model>();
+           ground->mesh = std::make_shared<render::Mesh>();
+           const float e = 12.0f;
+           const float q[4][2] = {{-e, -e}, {e, -e}, {e, e}, {-e, e}};
+           for(auto& c: q) { render::Vertex v{}; v.position[0] = c[0]; v.position[2] = c[1]; v.normal[1] = 1.0f; ground->mesh->vertices.push_back(v); }
+           ground->mesh->indices = {0, 2, 1, 0, 3, 2};
+           ground->materials.push_back(s->rm->loadMaterial("floor"));
+           s->rm->registerModel(ground);
+           auto g = std::make_shared<Entity>("ground");
+           g->model = ground;
+           s->scene->root->addChild(g);
+           const float cx = 0.5f * (bounds.lower.x + bounds.upper.x);
+           s->scene->camera->moveTo({cx + 1.5f, 2.2f, 6.0f});
+           s->scene->camera->lookAt({cx, 1.2f, 0.0f});
+           render::RenderSystem::packModelBuffers(s->rm->models(), s->v, s->i, s->m, s->ranges);
+           render::Raytracer::gatherInstances(*s->scene, s->inst);
+           std::memset(&s->ubo, 0, sizeof s->ubo);
+           render::RenderSystem::fillUniformBuffer(s->ubo, *s->scene->camera);
+       })) { delete s; return nullptr; }
+    return s;
+}
 void rgh_scene_free(rgh_scene* s) { delete s; }
 void rgh_scene_counts(const rgh_scene* s, uint32_t* out5) {
     out5[0] = (uint32_t)s->v.size(); out5[1] = (uint32_t)s->i.size(); out5[2] = (uint32_t)s->m.size(); out5[3] = (uint32_t)s->ranges.size(); out5[4] = (uint32_t)s->inst.size();

@@ -223,4 +223,66 @@ rg_timings RenderSystem::timings() {
 }
 
 }  // namespace render
+
+// ------------------------------------------------------------------------------------------------ ui::TextGenerator (ui/text.cpp:30-138)
+namespace ui {
+TextGenerator::TextGenerator(const Font& font, std::shared_ptr<Material> material, const RegisterModel& registerModel, float letterPadding_, float lineSpacing_)
+    : m_charWidth(font.charWidth), letterPadding(letterPadding_), lineSpacing(lineSpacing_) {
+    for(size_t k = 0; k < font.charMap.size(); ++k) {
+        if(!font.charMap[k]) continue;
+        auto model = std::make_shared<render::Model>();
+        model->mesh = font.charMap[k];
+        model->materials.push_back(material);
+        if(registerModel) registerModel(model);
+        m_charMap[k] = model;
+    }
+}
+std::pair<std::shared_ptr<Entity>, render::Mesh::Bounds> TextGenerator::textInternal(string_view input) const {
+    auto result = std::make_shared<Entity>("char_group_" + string(input));
+    render::Mesh::Bounds bounds{};
+    vec2 offset{};
+    for(const char c: input) {
+        if(c == ' ') {
+            offset.x += 5 * letterPadding;
+        } else if(c == '\n') {
+            offset.x = 0;
+            offset.y -= lineSpacing;
+            continue;
+        }
+        const auto code = (unsigned char)c;
+        if(code >= m_charMap.size()) continue;
+        const auto& model = m_charMap[code];
+        if(!model) continue;
+        auto entity = result->emplaceChild(std::to_string((int)c));
+        entity->move({offset.x, offset.y, 0.0f});
+        entity->model = model;
+        offset.x += letterPadding + m_charWidth[code];
+        bounds.upper.x = offset.x - letterPadding;
+        bounds.upper.y = offset.y + lineSpacing * 0.66f;
+    }
+    return {result, bounds};
+}
+std::pair<std::shared_ptr<Entity>, render::Mesh::Bounds> TextGenerator::textWithBounds(string_view input, Alignment align) const {
+    auto [textEnt, bounds] = textInternal(input);
+    vec3 offset(0.0f);
+    switch(align) {
+    case Alignment::TopLeft: break;
+    case Alignment::TopCenter: offset = vec3(-bounds.upper.x / 2, 0, 0); break;
+    case Alignment::TopRight: offset = vec3(-bounds.upper.x, 0, 0); break;
+    case Alignment::MiddleLeft: offset = vec3(0, -bounds.upper.y / 2, 0); break;
+    case Alignment::MiddleCenter: offset = vec3(-bounds.upper.x / 2, -bounds.upper.y / 2, 0); break;
+    case Alignment::MiddleRight: offset = vec3(-bounds.upper.x, -bounds.upper.y / 2, 0); break;
+    case Alignment::BottomLeft: offset = vec3(0, -bounds.upper.y, 0); break;
+    case Alignment::BottomCenter: offset = vec3(-bounds.upper.x / 2, -bounds.upper.y, 0); break;
+    case Alignment::BottomRight: offset = vec3(-bounds.upper.x, -bounds.upper.y, 0); break;
+    }
+    textEnt->moveTo(offset);
+    bounds.upper += offset;
+    bounds.lower += offset;
+    auto result = std::make_shared<Entity>("string_" + string(input));
+    result->addChild(textEnt);
+    return {result, bounds};
+}
+}  // namespace ui
+
 }  // namespace raygun

@@ -10,6 +10,7 @@
 //   RenderSystem         raygun/render/render_system.hpp:39-95, render_system.cpp:88-162, :192-330 (headless: no swapchain / ImGui)
 // Physics, audio, window, Vulkan objects are out of scope and absent.
 #pragma once
+#include <array>
 #include <functional>
 #include <memory>
 #include <optional>
@@ -184,11 +185,40 @@ struct Scene {
 /// Asset ingestion the way the reference does it for this path (entity.cpp:60-122 on top of Assimp's Collada importer with
 /// aiProcess_Triangulate only, resource_manager.cpp:35-50 for materials): every child node of the file becomes a child entity
 /// with its own Model; one vertex per index tuple, sub-meshes merged per node in file order, every model carries all materials.
+namespace ui {
+
+/// raygun/ui/text.hpp:31-37: one mesh per ASCII code point, shifted so that its left edge is x = 0, and its width.
+struct Font {
+    string name;
+    std::array<std::shared_ptr<render::Mesh>, 128> charMap = {};
+    std::array<float, 128> charWidth = {};
+};
+
+enum class Alignment { TopLeft, TopCenter, TopRight, MiddleLeft, MiddleCenter, MiddleRight, BottomLeft, BottomCenter, BottomRight };
+
+/// raygun/ui/text.{hpp,cpp}: text as ordinary entities, one instance per glyph (the ray-traced UI of the reference).
+class TextGenerator {
+  public:
+    using RegisterModel = std::function<void(std::shared_ptr<render::Model>)>;
+    TextGenerator(const Font& font, std::shared_ptr<Material> material, const RegisterModel& registerModel, float letterPadding = 0.1f, float lineSpacing = 1.f);
+    std::shared_ptr<Entity> text(string_view input, Alignment align = Alignment::TopLeft) const { return textWithBounds(input, align).first; }
+    std::pair<std::shared_ptr<Entity>, render::Mesh::Bounds> textWithBounds(string_view input, Alignment align = Alignment::TopLeft) const;
+
+  private:
+    std::pair<std::shared_ptr<Entity>, render::Mesh::Bounds> textInternal(string_view input) const;
+    std::array<std::shared_ptr<render::Model>, 128> m_charMap = {};
+    std::array<float, 128> m_charWidth = {};
+    float letterPadding, lineSpacing;
+};
+
+}  // namespace ui
+
 class ResourceManager {
   public:
     explicit ResourceManager(string resourcesDir) : m_dir(std::move(resourcesDir)) {}
     std::shared_ptr<Entity> loadEntity(string_view name);          // resources/models/<name>.dae
     std::shared_ptr<Material> loadMaterial(const string& name);   // resources/materials/<name>.rgmat.json (+ underscore fallback)
+    std::shared_ptr<ui::Font> loadFont(string_view name);          // resources/fonts/<name>.obj (resource_manager.cpp:107-135)
     const std::vector<std::shared_ptr<render::Model>>& models() const { return m_models; }
     void registerModel(std::shared_ptr<render::Model> m) { m_models.push_back(std::move(m)); }
 
@@ -196,6 +226,7 @@ class ResourceManager {
     string m_dir;
     std::vector<std::shared_ptr<render::Model>> m_models;
     std::vector<std::pair<string, std::shared_ptr<Material>>> m_materials;
+    std::vector<std::pair<string, std::shared_ptr<ui::Font>>> m_fonts;
 };
 
 namespace render {

@@ -293,4 +293,75 @@ std::shared_ptr<Entity> ResourceManager::loadEntity(string_view name) {
     return entity;
 }
 
+
+// ---------------------------------------------------------------------------------------------- fonts
+// ResourceManager::loadFont (resource_manager.cpp:107-135): resources/fonts/<name>.obj holds one object per glyph, named by its
+// ASCII code ("o 65").  What Assimp's OBJ importer hands raygun::Entity for such a file (aiProcess_Triangulate only, entity.cpp:
+// 88-90): one node per object, one output vertex per face corner in face order (no welding), position + normal, default material
+// index 0.  The glyph mesh is then shifted so that its left edge is x = 0 and its width is recorded.
+std::shared_ptr<ui::Font> ResourceManager::loadFont(string_view nameView) {
+    const string name(nameView);
+    for(auto& f: m_fonts) if(f.first == name) return f.second;
+    const string text = readFile(m_dir + "/fonts/" + name + ".obj");
+    auto font = std::make_shared<ui::Font>();
+    font->name = name;
+    std::vector<vec3> pos, nrm;
+    std::shared_ptr<render::Mesh> mesh;
+    long glyph = -1;
+    auto finish = [&] {
+        if(!mesh || glyph < 0 || (size_t)glyph >= font->charMap.size() || mesh->vertices.empty()) return;
+        const auto b = mesh->bounds();
+        for(auto& v: mesh->vertices) v.position[0] -= b.lower.x;
+        font->charMap[(size_t)glyph] = mesh;
+        font->charWidth[(size_t)glyph] = mesh->width();
+    };
+    size_t i = 0;
+    while(i < text.size()) {
+        size_t e = text.find('\n', i);
+        if(e == string::npos) e = text.size();
+        const char* l = text.c_str() + i;
+        if(l[0] == 'o' && l[1] == ' ') {
+            finish();
+            mesh = std::make_shared<render::Mesh>();
+            char* end = nullptr;
+            glyph = std::strtol(l + 2, &end, 10);
+            if(end == l + 2) glyph = -1;   // not a number: std::stoul would throw in the reference; skipped here
+        } else if(l[0] == 'v' && (l[1] == ' ' || (l[1] == 'n' && l[2] == ' '))) {
+            char* q = const_cast<char*>(l + (l[1] == 'n' ? 3 : 2));
+            vec3 v;
+            v.x = (float)std::strtod(q, &q); v.y = (float)std::strtod(q, &q); v.z = (float)std::strtod(q, &q);
+            (l[1] == 'n' ? nrm : pos).push_back(v);
+        } else if(l[0] == 'f' && l[1] == ' ' && mesh) {
+            // "f v//vn v//vn v//vn" (also v, v/vt, v/vt/vn); polygons are fan-triangulated like aiProcess_Triangulate does for convex faces
+            std::vector<std::pair<long, long>> corners;
+            char* q = const_cast<char*>(l + 2);
+            const char* lineEnd = text.c_str() + e;
+            while(q < lineEnd) {
+                while(q < lineEnd && (*q == ' ' || *q == '\r')) ++q;
+                if(q >= lineEnd) break;
+                char* n0 = q;
+                const long vi = std::strtol(q, &q, 10);
+                if(q == n0) break;
+                long ni = 0;
+                if(*q == '/') { ++q; if(*q != '/') std::strtol(q, &q, 10); if(*q == '/') { ++q; ni = std::strtol(q, &q, 10); } }
+                corners.push_back({vi, ni});
+            }
+            auto emit = [&](const std::pair<long, long>& c) {
+                render::Vertex v{};
+                const long vi = c.first > 0 ? c.first - 1 : (long)pos.size() + c.first, ni = c.second > 0 ? c.second - 1 : (long)nrm.size() + c.second;
+                if(vi >= 0 && (size_t)vi < pos.size()) { v.position[0] = pos[(size_t)vi].x; v.position[1] = pos[(size_t)vi].y; v.position[2] = pos[(size_t)vi].z; }
+                if(c.second != 0 && ni >= 0 && (size_t)ni < nrm.size()) { v.normal[0] = nrm[(size_t)ni].x; v.normal[1] = nrm[(size_t)ni].y; v.normal[2] = nrm[(size_t)ni].z; }
+                v.mat_index = 0;
+                mesh->indices.push_back((uint32_t)mesh->vertices.size());
+                mesh->vertices.push_back(v);
+            };
+            for(size_t k = 2; k < corners.size(); ++k) { emit(corners[0]); emit(corners[k - 1]); emit(corners[k]); }
+        }
+        i = e + 1;
+    }
+    finish();
+    m_fonts.push_back({name, font});
+    return font;
+}
+
 }  // namespace raygun

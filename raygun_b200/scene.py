@@ -197,6 +197,17 @@ def load_example_scene() -> tuple[SceneData, dict]:
     return sd, cam
 
 
+def load_text_scene() -> tuple[SceneData, np.ndarray]:
+    """Ray-traced UI text (raygun/ui/text.cpp) over a ground quad: the committed snapshot tests/golden/text_scene.npz, made by
+    tools/make_text_scene.py with the C++ host shim's loadFont / TextGenerator from the reference's NotoSans.obj.  One instance per
+    glyph.  Returns the scene and the 48-word UBO prefix (view / projection inverse for 640x360) the shim's Camera produced."""
+    z = np.load(os.path.join(_GOLDEN, "text_scene.npz"))
+    inst = z["instances"]
+    sd = SceneData(vertices=z["vertices"].copy(), indices=z["indices"].copy(), meshes=z["meshes"].copy(), materials=z["materials"].copy(),
+                   inst_xform=inst[:, :12].copy().view(F32), inst_meta=inst[:, 12:].copy(), name="text")
+    return sd, z["ubo"].copy()
+
+
 def example_ubo(width, height, num_samples=1, max_recursions=5, **kw) -> np.ndarray:
     _, cam = load_example_scene()
     return make_ubo(cam["view_inverse"], proj_inverse(width, height), num_samples, max_recursions, cam["light_dir"], **kw)

@@ -122,3 +122,73 @@ def test_render_through_entity_tree_equals_python_path(host, example_scene):
                                   W, H, 2, 5, 1 | 2, 0, _p(frame2), _p(inst2), C.byref(n2), _p(tm))
     assert rc == 0, host.rgh_last_error().decode()
     assert n2.value == n.value and np.array_equal(inst2[:4], inst[:4]) and np.array_equal(frame2, frame)
+
+
+def test_text_layout_matches_text_generator_rules(host):
+    """ui/text.cpp:108-138 on the committed text snapshot: one instance per printable glyph, x advances by letterPadding + glyph
+    width, a space advances 5 paddings, a newline goes down one lineSpacing; MiddleCenter alignment shifts by half the bounds."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "text_scene.npz"))
+    text = bytes(z["text"]).decode()
+    widths = z["widths"].view(np.float32)
+    inst = z["instances"]
+    xf = inst[:, :12].view(np.float32).reshape(-1, 3, 4)
+    glyphs = [c for c in text if c not in " \n"]
+    assert len(inst) == len(glyphs) + 1                      # + the ground quad
+    pad, line = np.float32(0.1), np.float32(1.0)
+    x = np.float32(0); y = np.float32(0); want = []; ux = uy = np.float32(0)
+    for c in text:
+        if c == " ":
+            x = np.float32(x + np.float32(5) * pad)
+        elif c == "\n":
+            x = np.float32(0); y = np.float32(y - line); continue
+        if widths[ord(c)] == 0:
+            continue
+        want.append((x, y))
+        x = np.float32(x + np.float32(pad + widths[ord(c)]))
+        ux = np.float32(x - pad); uy = np.float32(y + np.float32(line * np.float32(0.66)))
+    off = np.array([-ux / 2, -uy / 2], np.float32)           # Alignment::MiddleCenter
+    got = xf[:len(glyphs), :2, 3] - np.array([0.0, 1.0], np.float32)   # the text entity sits at (0, 1, 0)
+    assert np.allclose(got, np.array(want, np.float32) + off, atol=2e-6)
+    assert np.allclose(xf[:len(glyphs), :, :3], np.eye(3, dtype=np.float32))   # glyph entities: translation only
+    # every glyph mesh starts at x = 0 (loadFont shifts it) and is as wide as charWidth says
+    v = z["vertices"].view(np.float32)
+    for k, c in enumerate(glyphs):
+        m = z["meshes"][inst[k, 12]]
+        px = v[m[0]:m[0] + m[1], 0]
+        assert px.min() == 0.0 and abs(px.max() - widths[ord(c)]) < 1e-6
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_RES), reason="reference resources not present (GPU box)")
+def test_font_loader_reproduces_the_snapshot(host):
+    sys_path = os.path.join(ROOT, "tools")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_text_scene", os.path.join(sys_path, "make_text_scene.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    host.rgh_text_scene_load.restype = C.c_void_p
+    d = mod.load(host)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "text_scene.npz"))
+    for k in ("vertices", "indices", "materials", "meshes", "instances", "ubo", "widths"):
+        assert np.array_equal(d[k], z[k]), k
+    assert int(d["glyphs"]) == 124                            # objects in NotoSans.obj
+
+
+@pytest.mark.gpu
+def test_text_scene_frame_parity():
+    """the ray-traced UI text (one tiny instance per glyph) rendered on the GPU against the oracle."""
+    import raygun_b200 as rg
+    from oracle import oracle as O
+    sd, ubo48 = S.load_text_scene()
+    W, H = 640, 360
+    ubo = S.make_ubo(ubo48[:16].view(np.float32), ubo48[16:32].view(np.float32), 2, 5)
+    ref = O.OracleScene(sd).render(ubo, W, H, O.FXAA)
+    for sched in (rg.RG_SCHED_LANES, rg.RG_SCHED_POOL):
+        rt = rg.Raytracer(W, H)
+        rt.set_trace_scheduler(sched)
+        rt.load_scene(sd)
+        rt.render_frame(ubo, rg.RG_FXAA | rg.RG_DEBUG_IDS)
+        img = rt.read_rgba8(); inst, prim = rt.read_ids()
+        assert float(((inst == ref["inst"]) & (prim == ref["prim"])).mean()) >= 0.9999
+        d = np.abs(img[..., :3].astype(int) - ref["rgba8"][..., :3].astype(int)).max(axis=2)
+        assert float((d <= 2).mean()) >= 0.999
+        assert (ref["inst"] < 20).mean() > 0.01               # the glyphs are actually on screen
+        rt.close()
