@@ -1133,6 +1133,7 @@ static int tracePerSm() {   // persistent grid: a multiple of the SM count; resi
         int v = 0;
         if(POOL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_pool<COUNT, MULTI>, 128, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_lanes<COUNT, MULTI>, 128, 0);
+        if(const char* e = getenv(POOL ? "RGB200_POOL_CTAS" : "RGB200_LANES_CTAS")) { const int w = atoi(e); if(w >= 1 && w < v) v = w; }   // developer knob: occupancy sweeps
         return v < 1 ? 1 : v;
     }();
     return perSm;
