@@ -320,6 +320,29 @@ def test_edge_cases(rgmod, O, S, example_scene):
         rt2.set_region(10, 10, 5, 20)
 
 
+@pytest.mark.parametrize("ns,mr", [(16, 5), (8, 5), (5, 3), (4, 0), (1, 8), (2, 1)])
+def test_sample_tables_and_recursion_limits(rgmod, O, S, example_scene, oracle_example, ns, mr):
+    """raygen.h:37-67: numSamples >= 5 uses the 8-offset table (16 = twice, BASELINE config 5), 3 and 4 the rotated grid; and the
+    recursion guard `recDepth < maxRecursions` from 0 (no secondary rays at all) to the library maximum 8.  Bit-exact image, exact
+    ray counters, both schedulers."""
+    W, H = 160, 90
+    ubo = S.example_ubo(W, H, num_samples=ns, max_recursions=mr)
+    ref = oracle_example.render(ubo, W, H, O.FXAA)
+    for sched in (rgmod.RG_SCHED_LANES, rgmod.RG_SCHED_POOL):
+        rt = rgmod.Raytracer(W, H)
+        rt.set_trace_scheduler(sched)
+        rt.load_scene(example_scene)
+        rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
+        _check_frame(rt, ref, rgmod, f"S={ns} maxRec={mr} sched={sched}")
+        tm, c = rt.timings(), ref["counters"]
+        assert tm["rays_primary"] == W * H * ns
+        for a, b in (("rays_shadow", "shadow"), ("rays_reflect", "reflect"), ("rays_refract", "refract")):
+            assert abs(tm[a] - c[b]) <= max(2, 2e-4 * c[b]), (a, tm[a], c[b])
+        if mr == 0:
+            assert tm["rays_shadow"] == tm["rays_reflect"] == tm["rays_refract"] == 0
+        rt.close()
+
+
 def test_strict_ieee_switch_only_changes_diffuse_materials(rgmod, O, S, example_scene, oracle_example):
     """SURVEY hazard 8: with the 0/0 kept, NaN appears exactly where the oracle (strict) has it."""
     W, H = 160, 90
