@@ -456,3 +456,29 @@ def test_rigid_sphere_integrator_bit_exact_and_device_resident_frame(rgmod, O, S
     rt.doRaytracing(rgmod.RG_FXAA)
     assert np.array_equal(rt.read_rgba8(), a)
     rt.close()
+
+
+@pytest.mark.parametrize("workload", ["c3", "c5"])
+def test_full_size_configs_schedulers_agree_and_frames_repeat(rgmod, workload):
+    """BASELINE configs 3 and 5 at FULL size, where the CPU oracle takes too long for the GPU suite: size-independent properties --
+    the two trace schedulers (different work order, different memory layout of the ray trees) must produce the same image bit for
+    bit and the same ray counters, a second frame must repeat the first (per-sample scratch, tile order and work counters reset
+    correctly), and every pixel is traced exactly numSamples times."""
+    import bench
+    desc, W, H, sd, ubo = bench.make_workload(workload)
+    ns = int(ubo[35])
+    frames, counters = [], []
+    for sched in (rgmod.RG_SCHED_LANES, rgmod.RG_SCHED_POOL):
+        rt = rgmod.Raytracer(W, H)
+        rt.set_trace_scheduler(sched)
+        rt.load_scene(sd)
+        for _ in range(2):
+            rt.render_frame(ubo, rgmod.RG_FXAA)
+            frames.append(rt.read_rgba8().copy())
+            tm = rt.timings()
+            counters.append(tuple(tm[k] for k in ("rays_primary", "rays_shadow", "rays_reflect", "rays_refract", "sky_lookups")))
+        rt.close()
+    assert all(np.array_equal(f, frames[0]) for f in frames[1:])
+    assert all(c == counters[0] for c in counters[1:]), counters
+    assert counters[0][0] == W * H * ns
+    assert len(np.unique(frames[0].reshape(-1, 4), axis=0)) > 1000      # a real image, not a constant
