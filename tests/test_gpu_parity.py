@@ -482,3 +482,31 @@ def test_full_size_configs_schedulers_agree_and_frames_repeat(rgmod, workload):
     assert all(c == counters[0] for c in counters[1:]), counters
     assert counters[0][0] == W * H * ns
     assert len(np.unique(frames[0].reshape(-1, 4), axis=0)) > 1000      # a real image, not a constant
+
+
+def test_resize_sample_change_and_material_edit_equal_a_fresh_context(rgmod, S, example_scene):
+    """RenderSystem::reload (render_system.cpp:77-78: a new Raytracer at the new window size), numSamples changed from the UI
+    (render_system.cpp:264) and the material editor's re-upload (gpu_material.cpp:91-93) on a LIVE context must give exactly what a
+    fresh context gives."""
+    def fresh(W, H, ns, sd):
+        rt = rgmod.Raytracer(W, H)
+        rt.load_scene(sd)
+        rt.render_frame(S.example_ubo(W, H, num_samples=ns), rgmod.RG_FXAA)
+        img = rt.read_rgba8().copy()
+        rt.close()
+        return img
+    rt = rgmod.Raytracer(64, 36)
+    rt.load_scene(example_scene)
+    rt.render_frame(S.example_ubo(64, 36), rgmod.RG_FXAA)
+    assert np.array_equal(rt.read_rgba8(), fresh(64, 36, 1, example_scene))
+    rt.resize(200, 120)
+    for ns in (1, 4, 2):
+        rt.render_frame(S.example_ubo(200, 120, num_samples=ns), rgmod.RG_FXAA)
+        assert np.array_equal(rt.read_rgba8(), fresh(200, 120, ns, example_scene)), ns
+    mats = example_scene.materials.copy()
+    mats[:, 0:3] = np.array([0.2, 0.7, 0.3], np.float32).view(np.uint32)      # every material turns green
+    rt.updateMaterialBuffer(mats)
+    rt.render_frame(S.example_ubo(200, 120, num_samples=2), rgmod.RG_FXAA)
+    edited = S.SceneData(example_scene.vertices, example_scene.indices, example_scene.meshes, mats, example_scene.inst_xform, example_scene.inst_meta)
+    assert np.array_equal(rt.read_rgba8(), fresh(200, 120, 2, edited))
+    rt.close()
