@@ -1,5 +1,6 @@
 // rg_api.cu -- the C ABI of librgb200.so (include/rgb200.h): context, uploads, per-frame command stream.
 // Mirrors raygun::render::Raytracer (raygun/render/raytracer.{hpp,cpp}) for the one path this library replaces.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -252,6 +253,15 @@ void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
     p.workCounter = c->dWork; p.counters = c->dCounters; p.flags = flags; p.ctxPool = c->ctxPool;
     p.sampleScratch = c->sampleScratch; p.sampleDone = c->sampleDone;
     p.tileOrder = c->haveTileHistory ? c->tileOrder : nullptr; p.tileCost = c->tileCost;
+    // miss.rmiss:63-66 (oracle/orc_shade.cpp skyMix): scatter = 1 - clamp(pow(4 - lightDir.y, 1/15), .8, 1);
+    // scatterColor = mix(vec3(1), vec3(1, .3, 0) * 1.5, scatter) -- per frame, not per ray
+    {
+        float scatter = std::pow(4.0f - c->hUbo.light_dir[1], 1.0f / 15.0f);
+        scatter = scatter < 0.8f ? 0.8f : (scatter > 1.0f ? 1.0f : scatter);
+        scatter = 1.0f - scatter;
+        const float tone[3] = {1.0f * 1.5f, 0.3f * 1.5f, 0.0f * 1.5f};
+        for(int k = 0; k < 3; ++k) p.scatterColor[k] = 1.0f * (1.0f - scatter) + tone[k] * scatter;
+    }
 }
 
 void fillPostParams(rg_ctx* c, PostParams& p, uint32_t flags) {

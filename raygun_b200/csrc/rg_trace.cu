@@ -376,8 +376,11 @@ __device__ __forceinline__ float2 aaOffset(int numSamples, int i) {
     return c_aaOffsets[n == 2 ? 0 : (n <= 4 ? 1 : 2)][i & 7];
 }
 
-// miss.rmiss:38-74 with the constants of :78; normalize(0) is kept 0 (SURVEY hazard 7)
-__device__ __noinline__ V3 skyColor(V3 d, V3 lightDir, bool strict) {
+// miss.rmiss:38-74 with the constants of :78; normalize(0) is kept 0 (SURVEY hazard 7).  Of the shader's six pow() calls four need
+// no pow: the integer powers are multiplication chains (x^80 = x^64 * x^16: 7 products, within 40 ulp of the exact power where the
+// sun term is not clamped away, far below the binary16 store), pow(x, 0.5) is the correctly rounded square root, and the scatter
+// colour depends on the light direction only -- the host evaluates it once per frame with the oracle's own libm (TraceParams).
+__device__ __noinline__ V3 skyColor(V3 d, V3 lightDir, V3 scatterColor, bool strict) {
     const bool zero = d.x == 0.0f && d.y == 0.0f && d.z == 0.0f;
     const V3 rayDir = (zero && !strict) ? v3(0, 0, 0) : normalize(d);
     const float y = divShared(fabsf(d.y + 1.5f), 3.0f);
@@ -385,20 +388,19 @@ __device__ __noinline__ V3 skyColor(V3 d, V3 lightDir, bool strict) {
     float sun = 1.0f - sqrtf(dot(sd, sd));
     sun = clampf(sun, 0.0f, 2.0f);
     float glow = clampf(sun, 0.0f, 1.0f);
-    sun = powShared(sun, 80.0f);
+    const float s2 = sun * sun, s4 = s2 * s2, s8 = s4 * s4, s16 = s8 * s8, s32 = s16 * s16, s64 = s32 * s32;
+    sun = s64 * s16;               // pow(sun, 80)
     sun *= 1000.0f;
     sun = clampf(sun, 0.0f, 16.0f);
-    glow = powShared(glow, 6.0f) * 1.0f;
+    const float g2 = glow * glow, g4 = g2 * g2;
+    glow = (g4 * g2) * 1.0f;       // pow(glow, 6)
     glow = powShared(glow, y);
     glow = clampf(glow, 0.0f, 1.0f);
     sun *= powShared(y * y, 1.0f / 1.65f);
-    glow *= powShared(y * y, 1.0f / 2.0f);
+    glow *= sqrtf(y * y);          // pow(y * y, 1 / 2)
     sun += glow;
     const V3 sunColor = v3(1.0f, 0.6f, 0.05f) * sun;
     const float atmosphere = sqrtf(1.0f - y);
-    float scatter = powShared(4.0f - lightDir.y, 1.0f / 15.0f);
-    scatter = 1.0f - clampf(scatter, 0.8f, 1.0f);
-    const V3 scatterColor = mix3(v3(1.0f, 1.0f, 1.0f), v3(1.0f, 0.3f, 0.0f) * 1.5f, scatter);
     const V3 skyScatter = mix3(v3(0.2f, 0.4f, 0.8f), scatterColor, divShared(atmosphere, 1.3f));
     return sunColor + skyScatter;
 }
@@ -587,7 +589,7 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
         }
     } else {
         if(missIndex == 0) {  // miss.rmiss:76-83
-            const V3 sky = skyColor(rd, K.L, K.strictIeee);
+            const V3 sky = skyColor(rd, K.L, v3(P.scatterColor[0], P.scatterColor[1], P.scatterColor[2]), K.strictIeee);
             hv = sky; depth = 10000.0f;
             if(sp == 0 && recDepth == 0) fr.st(kMaxFrames * 8 + 1, make_float4(sky.x, sky.y, sky.z, 0.0f));   // roughValue is only observable for a primary miss
         } else {              // shadowMiss.rmiss:33
@@ -660,7 +662,7 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
                 const float dp2 = dp * dp;
                 shadowCol = shadowCol * (dp2 * dp2 * dp + 0.75f);   // pow(x, 5)
                 (*skyLookups)++;   // T4: cull mask 0 -> always miss 0
-                const V3 sky = skyColor(-dir, K.L, K.strictIeee);
+                const V3 sky = skyColor(-dir, K.L, v3(P.scatterColor[0], P.scatterColor[1], P.scatterColor[2]), K.strictIeee);
                 depth = 10000.0f;
                 hv = shadowCol + sky * 0.1f;
             }

@@ -49,6 +49,7 @@ struct TraceParams {
     uint32_t* workCounter;
     unsigned long long* counters;  // 5 ray kinds + nodes, tris, instances
     uint32_t flags;
+    float scatterColor[3];   // miss.rmiss:63-66 scatterColor: a function of lightDir alone, evaluated by the host once per frame
 };
 
 // pool: per-warp context pools with ray / hit queues (incoherent bounces); otherwise one context per lane (coherent scenes)
