@@ -273,7 +273,7 @@ def main():
     dev_ms, e2e_ms, wall_ms = (float(v) for v in stats.tolist())
     rays_total, launches_total = (float(v) for v in sums.tolist())
 
-    # ---------------- roofline of the dominant kernel (k_trace) from one instrumented, untimed frame (rank 0, N = 1 only)
+    # ---------------- roofline of the dominant kernel (the trace kernel the scheduler picked) from one instrumented, untimed frame (rank 0, N = 1 only)
     roofline = None
     # (every rank renders it: in partitioned mode a frame is a collective operation)
     rt.set_instances_device(d_inst.data_ptr(), len(inst_raw))

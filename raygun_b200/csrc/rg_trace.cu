@@ -9,7 +9,7 @@
 // depth-first in the reference's order (shadow -> reflection -> refraction), with ONE mutable payload, so every
 // stale-state effect of the GLSL (SURVEY.md 8a hazards 1-6) is reproduced.  Every warp of the persistent grid runs a pool
 // of contexts with ray / hit queues in shared memory: lanes take the next ray the moment theirs is done (warp vote +
-// prefix rank), and hits are shaded 32 at a time -- see k_trace.
+// prefix rank), and hits are shaded 32 at a time (k_trace_pool); coherent scenes use one context per lane (k_trace_lanes).
 //
 // Ray / triangle arithmetic is bit-identical to the oracle (explicitly rounded operations, never contracted):
 // watertight Woop test, t preserved across the instance transform, ties resolved to the smallest (instance, primitive).

@@ -1,4 +1,4 @@
-"""Developer experiment: k_trace time of each rank's share in partitioned mode, all contexts on one GPU (run sequentially)."""
+"""Developer experiment: trace-kernel time of each rank's share in partitioned mode, all contexts on one GPU (run sequentially)."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
