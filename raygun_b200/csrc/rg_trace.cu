@@ -629,10 +629,14 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
                 }
             }
             if(last) {      // raygen.h:114 + raygen.rgen:35-38
+                // x / numSamples: for a power of two the product with the reciprocal is the same correctly rounded value
                 const float inv = (float)K.numSamples;
-                const uint2 ob = packHalf4(divShared(accColor.x, inv), divShared(accColor.y, inv), divShared(accColor.z, inv), divShared(accContrib, inv));
-                const uint2 on = packHalf4(divShared(accNormal.x, inv), divShared(accNormal.y, inv), divShared(accNormal.z, inv), divShared(logf(accDepth) * 0.25f, inv));
-                const uint2 orr = packHalf4(divShared(accRough.x, inv), divShared(accRough.y, inv), divShared(accRough.z, inv), divShared(accRoughA, inv));
+                const bool pow2 = (K.S & (K.S - 1u)) == 0u;
+                const float rinv = pow2 ? 1.0f / inv : 0.0f;
+                auto divN = [&](float x) { return pow2 ? x * rinv : divShared(x, inv); };
+                const uint2 ob = packHalf4(divN(accColor.x), divN(accColor.y), divN(accColor.z), divN(accContrib));
+                const uint2 on = packHalf4(divN(accNormal.x), divN(accNormal.y), divN(accNormal.z), divN(logf(accDepth) * 0.25f));
+                const uint2 orr = packHalf4(divN(accRough.x), divN(accRough.y), divN(accRough.z), divN(accRoughA));
                 // the pixel goes to every GPU whose post-chain rectangle contains it (own images or peer memory over NVLink)
 #pragma unroll
                 for(int q = 0; q < (MULTI ? kMaxPeers : 1); ++q) {   // static indices: the targets stay in the constant bank
