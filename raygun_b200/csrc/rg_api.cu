@@ -18,6 +18,7 @@ using namespace rg;
 
 static_assert(sizeof(rg_vertex) == 32 && sizeof(rg_material) == 64 && sizeof(rg_ubo) == 192 && sizeof(rg_instance) == 64 && sizeof(rg_mesh_range) == 16,
               "POD layouts must match the reference's .def files");
+static_assert(sizeof(rg_entity) == 64 && sizeof(rg_sphere_body) == 32 && sizeof(rg_timings) % 8 == 0, "extension records of include/rgb200.h");
 
 namespace {
 
