@@ -321,17 +321,27 @@ int rg_create(rg_ctx** out, int cuda_device, uint32_t width, uint32_t height) {
     cudaGetDeviceProperties(&prop, cuda_device);
     ctx->numSms = prop.multiProcessorCount;
     if(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 5; }
-    for(auto& e: ctx->ev) cudaEventCreate(&e);
-    cudaMalloc(&ctx->dUbo, 192); cudaMemset(ctx->dUbo, 0, 192);
-    cudaMalloc(&ctx->dWork, 4); cudaMalloc(&ctx->dCounters, 16 * 8); cudaMemset(ctx->dCounters, 0, 128);
-    cudaMalloc(&ctx->ctxPool, tracePoolBytes(ctx->numSms));
     if(const char* e = getenv("RGB200_TRACE_SCHED"))   // developer override for A/B timing: lanes | pool | auto
         ctx->schedMode = !strcmp(e, "lanes") ? RG_SCHED_LANES : (!strcmp(e, "pool") ? RG_SCHED_POOL : RG_SCHED_AUTO);
-    cudaMallocHost(&ctx->hUboPinned, sizeof(rg_ubo));
-    cudaMalloc(&ctx->arriveTrace, 4 * kMaxPeers); cudaMalloc(&ctx->arrivePost, 4 * kMaxPeers); cudaMalloc(&ctx->dSyncErr, 4);
-    cudaMemset(ctx->arriveTrace, 0, 4 * kMaxPeers); cudaMemset(ctx->arrivePost, 0, 4 * kMaxPeers); cudaMemset(ctx->dSyncErr, 0, 4);
-    cudaMalloc(&ctx->dPeerTraceFlags, sizeof(void*) * kMaxPeers); cudaMalloc(&ctx->dPeerPostFlags, sizeof(void*) * kMaxPeers);
-    cudaMemset(ctx->dPeerTraceFlags, 0, sizeof(void*) * kMaxPeers); cudaMemset(ctx->dPeerPostFlags, 0, sizeof(void*) * kMaxPeers);
+    // every allocation is checked: a half-initialised context must not reach the caller
+    bool ok = true;
+    auto good = [&](cudaError_t e) { ok = ok && e == cudaSuccess; };
+    for(auto& e: ctx->ev) good(cudaEventCreate(&e));
+    good(cudaMalloc(&ctx->dUbo, 192)); good(cudaMalloc(&ctx->dWork, 4)); good(cudaMalloc(&ctx->dCounters, 16 * 8));
+    good(cudaMalloc(&ctx->ctxPool, tracePoolBytes(ctx->numSms)));
+    good(cudaMallocHost(&ctx->hUboPinned, sizeof(rg_ubo)));
+    good(cudaMalloc(&ctx->arriveTrace, 4 * kMaxPeers)); good(cudaMalloc(&ctx->arrivePost, 4 * kMaxPeers)); good(cudaMalloc(&ctx->dSyncErr, 4));
+    good(cudaMalloc(&ctx->dPeerTraceFlags, sizeof(void*) * kMaxPeers)); good(cudaMalloc(&ctx->dPeerPostFlags, sizeof(void*) * kMaxPeers));
+    if(ok) {
+        good(cudaMemset(ctx->dUbo, 0, 192)); good(cudaMemset(ctx->dCounters, 0, 128));
+        good(cudaMemset(ctx->arriveTrace, 0, 4 * kMaxPeers)); good(cudaMemset(ctx->arrivePost, 0, 4 * kMaxPeers)); good(cudaMemset(ctx->dSyncErr, 0, 4));
+        good(cudaMemset(ctx->dPeerTraceFlags, 0, sizeof(void*) * kMaxPeers)); good(cudaMemset(ctx->dPeerPostFlags, 0, sizeof(void*) * kMaxPeers));
+    }
+    if(!ok) {
+        fprintf(stderr, "rgb200: rg_create: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        rg_destroy(ctx);
+        return 7;
+    }
     ctx->W = width; ctx->H = height; ctx->ix0 = 0; ctx->iy0 = 0; ctx->ix1 = (int)width; ctx->iy1 = (int)height;
     if(allocImages(ctx)) { fprintf(stderr, "rgb200: %s\n", ctx->err.c_str()); rg_destroy(ctx); return 6; }
     *out = ctx;
@@ -516,9 +526,14 @@ static int setEntities(rg_ctx* ctx, const rg_entity* src, bool onHost, uint32_t 
     if(n && !src) return fail(ctx, "rg_set_entities: null input");
     if(!ctx->blasBuilt) return fail(ctx, "rg_set_entities: call rg_build_blas first");
     USE_DEVICE();
-    if(onHost)
-        for(uint32_t i = 0; i < n; ++i)
+    if(onHost) {   // validate the order and the nesting depth (the device walk keeps kMaxEntityDepth ancestors)
+        std::vector<uint16_t> depth(n);
+        for(uint32_t i = 0; i < n; ++i) {
             if(src[i].parent >= (int32_t)i) return fail(ctx, "rg_set_entities: entity %u has parent %d; entities must be in DFS pre-order (parents first)", i, src[i].parent);
+            depth[i] = src[i].parent < 0 ? 1 : (uint16_t)(depth[(size_t)src[i].parent] + 1);
+            if(depth[i] > kMaxEntityDepth) return fail(ctx, "rg_set_entities: entity %u is nested %u deep; the device walk supports %d levels", i, (unsigned)depth[i], kMaxEntityDepth);
+        }
+    }
     if(n > ctx->entCap) {
         CK(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->dEntities); cudaFree(ctx->dEntTmp); cudaFree(ctx->dEntEmit);

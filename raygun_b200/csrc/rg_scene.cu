@@ -94,7 +94,7 @@ __global__ void k_entity_instances(const rg_entity* __restrict__ ents, uint32_t 
         const rg_entity& e = ents[cur];
         // Entity::isVisible (acceleration_structure.cpp:65); Transform::isZeroVolume on the LOCAL transform (:67, transform.hpp:65)
         if(!(e.flags & RG_ENTITY_VISIBLE) || FM(FM(e.scaling[0], e.scaling[1]), e.scaling[2]) == 0.0f) { alive = false; break; }
-        if(depth == kMaxEntityDepth) { alive = false; break; }   // deeper than the library supports: dropped (reported by rg_set_entities)
+        if(depth == kMaxEntityDepth) { alive = false; break; }   // deeper than the library supports: dropped (rg_set_entities rejects such input from host memory)
         chain[depth++] = cur;
         if(e.parent < 0 || (uint32_t)e.parent >= cur) break;     // the root (parents precede their children in DFS pre-order)
         cur = (uint32_t)e.parent;

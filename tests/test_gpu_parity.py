@@ -312,6 +312,12 @@ def test_edge_cases(rgmod, O, S, example_scene):
     inst2, prim2 = rt2.read_ids()
     assert np.array_equal(inst2, ref2["inst"]) and np.array_equal(prim2, ref2["prim"]) and (inst2 == 1).sum() > 50
     # invalid arguments are rejected with a message, not a crash
+    bad = np.zeros(3, rgmod.ENTITY_DTYPE); bad["parent"] = (-1, 2, 0)          # child listed before its parent
+    with pytest.raises(rgmod.RaygunError):
+        rt2.set_entities(bad)
+    deep = np.zeros(80, rgmod.ENTITY_DTYPE); deep["parent"] = np.arange(-1, 79)  # a chain 80 levels deep
+    with pytest.raises(rgmod.RaygunError):
+        rt2.set_entities(deep)
     with pytest.raises(rgmod.RaygunError):
         rt2.updateRenderTarget(S.make_ubo(np.zeros(16), np.zeros(16), num_samples=0))
     with pytest.raises(rgmod.RaygunError):
