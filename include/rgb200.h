@@ -184,7 +184,7 @@ int rg_sync(rg_ctx* ctx);
 
 /* Scheduler of the trace kernel (no reference counterpart: traceRaysKHR leaves scheduling to the driver).  LANES: one pixel sample
  * per lane, fastest on coherent scenes.  POOL: per-warp context pools with shared-memory ray / hit queues, fastest on incoherent
- * bounces.  AUTO (default): times both on consecutive frames, keeps the faster, re-checks every 64 frames.  Images are
+ * bounces.  AUTO (default): times both on consecutive frames, keeps the faster, re-checks every 256 frames.  Images are
  * bit-identical either way. */
 #define RG_SCHED_LANES 0
 #define RG_SCHED_POOL 1

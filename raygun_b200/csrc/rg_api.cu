@@ -211,7 +211,7 @@ int ensureSchedule(rg_ctx* ctx) {
     return 0;
 }
 
-constexpr uint32_t kSchedReprobe = 64;
+constexpr uint32_t kSchedReprobe = 256;   // two probe frames (one per kernel) every 256: < 0.5 % even when the loser is 60 % slower
 
 // Which trace kernel runs this frame.  AUTO: once the heavy-first tile order exists (second frame on), one frame is timed with
 // each scheduler (CUDA events around the kernel; the host waits for that one frame's kernel when it needs the number) and the
