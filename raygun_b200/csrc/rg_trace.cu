@@ -956,6 +956,9 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
 }
 
 
+#ifndef RG_LANES_REFILL
+#define RG_LANES_REFILL 32       // idle lanes before a warp of the lanes kernel fetches new work items (swept 2..32: C2 7.9 ms at 2, 6.6 at 8, 5.4 at 20-28, 5.2 at 32)
+#endif
 #ifndef RG_LANES_MIN_BLOCKS
 #define RG_LANES_MIN_BLOCKS 8
 #endif
@@ -1009,7 +1012,7 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
     while(true) {
         // ---- refill idle lanes (warp vote + prefix compaction over one atomic)
         uint32_t idle = __ballot_sync(0xffffffffu, !busy);
-        while(!exhausted && __popc(idle) >= 8) {
+        while(!exhausted && __popc(idle) >= RG_LANES_REFILL) {
             // at most RG_GRAB_MAX consecutive work items per grab: the samples of one (possibly very expensive) tile spread over several warps
             const int nIdle = __popc(idle), n = nIdle < RG_GRAB_MAX ? nIdle : RG_GRAB_MAX, leader = __ffs(idle) - 1;
             uint32_t basew = 0;
