@@ -73,21 +73,27 @@ __global__ void k_rough_prepare(const uint2* __restrict__ rough, const uint2* __
 
 // rough_blur.h:23-40; (ox, oy) = (1,0) for the H pass, (0,1) for the V pass.  Most pixels are inactive (transition weight < 0.001,
 // i.e. SNORM8 <= 0) and a pass is bound by block scheduling, not bandwidth: one thread owns 4 horizontally adjacent pixels and leaves
-// after one 32-bit load when none of them is active.
+// after one 32-bit load when none of them is active (PX = 4); PX = 1 for small images.
+template <int PX>
 __global__ void k_rough_blur(const uint2* __restrict__ in, uint2* __restrict__ out, const signed char* __restrict__ trans, int W, int H, int ox, int oy) {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
     if(x0 >= W || y >= H) return;
     const size_t row = (size_t)y * W;
-    signed char t4[4] = {0, 0, 0, 0};
-    if(((row + x0) & 3) == 0 && x0 + 3 < W) {
+    signed char t4[PX];
+    if(PX == 4 && ((row + x0) & 3) == 0 && x0 + 3 < W) {
         const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(trans + row + x0));
-        t4[0] = (signed char)(w & 0xffu); t4[1] = (signed char)((w >> 8) & 0xffu); t4[2] = (signed char)((w >> 16) & 0xffu); t4[3] = (signed char)(w >> 24);
-    } else {
-        for(int k = 0; k < 4; ++k) if(x0 + k < W) t4[k] = trans[row + x0 + k];
-    }
-    if(t4[0] <= 0 && t4[1] <= 0 && t4[2] <= 0 && t4[3] <= 0) return;
 #pragma unroll
-    for(int k = 0; k < 4; ++k) {
+        for(int k = 0; k < PX; ++k) t4[k] = (signed char)((w >> (8 * k)) & 0xffu);
+    } else {
+#pragma unroll
+        for(int k = 0; k < PX; ++k) t4[k] = x0 + k < W ? trans[row + x0 + k] : (signed char)0;
+    }
+    bool any = false;
+#pragma unroll
+    for(int k = 0; k < PX; ++k) any |= t4[k] > 0;
+    if(!any) return;
+#pragma unroll
+    for(int k = 0; k < PX; ++k) {
         const int x = x0 + k;
         if(x >= W) break;
         const float t = fromSnorm8(t4[k]);
@@ -295,10 +301,19 @@ void launchRoughPrepare(const PostParams& p, cudaStream_t st) {
     k_rough_prepare<<<grid2d(p.rw, p.rh, b), b, 0, st>>>(p.rough, p.normal, p.rw, p.rh, p.trans, p.roughA, p.roughB);
 }
 void launchRoughBlur(const PostParams& p, cudaStream_t st) {
-    const dim3 b(32, 8), g(((p.rw + 3) / 4 + b.x - 1) / b.x, (p.rh + b.y - 1) / b.y);   // 4 pixels per thread
+    const dim3 b(32, 8);
+    // large images: 4 pixels per thread (a pass is bound by block scheduling); small ones (640x360, the bands of an 8-GPU frame): 1 pixel
+    // per thread, there the pass is bound by the latency of a thread and wants all the parallelism it can get
+    const bool wide = (size_t)p.rw * p.rh >= (size_t)800000;
+    const dim3 g(((wide ? (p.rw + 3) / 4 : p.rw) + b.x - 1) / b.x, (p.rh + b.y - 1) / b.y);
     for(int i = 0; i < 10; ++i) {
-        k_rough_blur<<<g, b, 0, st>>>(p.roughA, p.roughB, p.trans, p.rw, p.rh, 1, 0);
-        k_rough_blur<<<g, b, 0, st>>>(p.roughB, p.roughA, p.trans, p.rw, p.rh, 0, 1);
+        if(wide) {
+            k_rough_blur<4><<<g, b, 0, st>>>(p.roughA, p.roughB, p.trans, p.rw, p.rh, 1, 0);
+            k_rough_blur<4><<<g, b, 0, st>>>(p.roughB, p.roughA, p.trans, p.rw, p.rh, 0, 1);
+        } else {
+            k_rough_blur<1><<<g, b, 0, st>>>(p.roughA, p.roughB, p.trans, p.rw, p.rh, 1, 0);
+            k_rough_blur<1><<<g, b, 0, st>>>(p.roughB, p.roughA, p.trans, p.rw, p.rh, 0, 1);
+        }
     }
 }
 void launchPostprocess(const PostParams& p, cudaStream_t st) {
