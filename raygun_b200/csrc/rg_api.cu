@@ -162,7 +162,7 @@ int ensureInstanceCapacity(rg_ctx* ctx, uint32_t n) {
     CK(cudaMalloc(&ctx->dInstTrav, sizeof(InstTrav) * (size_t)cap));
     CK(cudaMalloc(&ctx->dInstShade, sizeof(InstShade) * (size_t)cap));
     CK(cudaMalloc(&ctx->tlasNodes, sizeof(Node8) * (size_t)cap));
-    CK(cudaMalloc(&ctx->tlasLeaves, sizeof(InstTrav) * (size_t)cap));
+    CK(cudaMalloc(&ctx->tlasLeaves, sizeof(InstTrav) * (size_t)cap * kLeafStride));   // kLeafStride elements per TLAS leaf child
     ctx->instCap = cap;
     ctx->tlasScratch.reserve(cap);
     return 0;
@@ -441,7 +441,9 @@ int rg_build_blas(rg_ctx* ctx) {
     USE_DEVICE();
     uint64_t totalTris = 0;
     for(auto& m: ctx->meshes) totalTris += m.range.idx_cnt / 3;
-    const uint32_t needNodes = (uint32_t)(totalTris + ctx->meshes.size() + 1), needTris = (uint32_t)(totalTris + 1);
+    // every leaf child of a wide node reserves kLeafStride elements of the primitive array (rg_types.cuh); at worst one triangle per leaf
+    if(totalTris * kLeafStride + 1 >= 0x7fffffffull) return fail(ctx, "rg_build_blas: %llu triangles exceed the primitive index range", (unsigned long long)totalTris);
+    const uint32_t needNodes = (uint32_t)(totalTris + ctx->meshes.size() + 1), needTris = (uint32_t)(kLeafStride * totalTris + 1);
     bool rebuildAll = false;
     if(needNodes > ctx->nodeCap || needTris > ctx->triCap) {
         CK(cudaStreamSynchronize(ctx->stream));

@@ -327,7 +327,7 @@ __device__ __forceinline__ void writeLeafPrim(const LeafSourceInst& src, uint32_
 
 // Quantise one wide node from its children's boxes.  Conservative in exact arithmetic: the decoded
 // planes p + q * 2^e (exact in binary64) never cut into a child box.
-__device__ void quantizeNode(Node8& nd, const float (*clo)[3], const float (*chi)[3], const int* slotOfChild, int nChildren) {
+__device__ void quantizeNode(Node8& nd, const float (*clo)[3], const float (*chi)[3], const int* posOfChild, int nChildren) {
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for(int c = 0; c < nChildren; ++c)
         for(int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], clo[c][a]); hi[a] = fmaxf(hi[a], chi[c][a]); }
@@ -350,7 +350,7 @@ __device__ void quantizeNode(Node8& nd, const float (*clo)[3], const float (*chi
     for(int s = 0; s < 8; ++s)
         for(int a = 0; a < 3; ++a) { qlo[a][s] = 255; qhi[a][s] = 0; }  // empty: inverted box
     for(int c = 0; c < nChildren; ++c) {
-        const int s = slotOfChild[c];
+        const int s = posOfChild[c];
         for(int a = 0; a < 3; ++a) {
             const float inv = 1.0f / scale[a];
             int ql = (int)floorf((clo[c][a] - lo[a]) * inv), qh = (int)ceilf((chi[c][a] - lo[a]) * inv);
@@ -426,40 +426,52 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
         }
     }
 
-    Node8 nd;
-    quantizeNode(nd, clo, chi, slotOfChild, n);
-
-    uint32_t refOfSlot[8];
-    for(int s = 0; s < 8; ++s) { refOfSlot[s] = kInvalid; nd.meta[s] = 0; }
-    uint32_t imask = 0, nInternal = 0, nPrims = 0;
+    // positions: leaves first, then internal children (the traversal tests positions pairwise and stops at the first empty pair)
+    bool isInner[8];
+    int posOfChild[8], childOfSlot[8];
+    uint32_t nLeaf = 0, nInternal = 0;
+    for(int s = 0; s < 8; ++s) childOfSlot[s] = -1;
     for(int k = 0; k < n; ++k) {
-        refOfSlot[slotOfChild[k]] = c[k];
-        const uint32_t cnt = refCount(c[k], range);
-        if(cnt > (uint32_t)kMaxLeafPrims) { imask |= 1u << slotOfChild[k]; ++nInternal; } else nPrims += cnt;
+        isInner[k] = refCount(c[k], range) > (uint32_t)kMaxLeafPrims;
+        if(!isInner[k]) posOfChild[k] = (int)nLeaf++;
+        childOfSlot[slotOfChild[k]] = k;
     }
+    for(int k = 0; k < n; ++k)
+        if(isInner[k]) posOfChild[k] = (int)(nLeaf + nInternal++);
+
+    Node8 nd;
+    quantizeNode(nd, clo, chi, posOfChild, n);
+
     const uint32_t childBase = nInternal ? atomicAdd(nodeCounter, nInternal) : 0u;
-    const uint32_t primBase = nPrims ? atomicAdd(primCounter, nPrims) : 0u;
+    const uint32_t primBase = nLeaf ? atomicAdd(primCounter, kLeafStride * nLeaf) : 0u;
     const uint32_t qBase = nInternal ? atomicAdd(nOutPtr, nInternal) : 0u;
-    uint32_t ci = 0, po = 0;
-    for(int s = 0; s < 8; ++s) {
-        const uint32_t r = refOfSlot[s];
-        if(wideRef) wideRef[(size_t)wide * 8 + s] = r;
-        if(r == kInvalid) continue;
-        const uint32_t cnt = refCount(r, range);
-        if(cnt > (uint32_t)kMaxLeafPrims) {
-            nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
-            queueOut[qBase + ci] = make_uint2(r, childBase + ci);
+    uint32_t refOfPos[8];
+    for(int j = 0; j < 8; ++j) refOfPos[j] = kInvalid;
+    uint32_t imask = 0, codes = 0x88888888u, vm = 0, ci = 0;
+    for(int s = 0; s < 8; ++s) {   // code order: the order of the child nodes in memory
+        const int k = childOfSlot[s];
+        if(k < 0) continue;
+        const int j = posOfChild[k];
+        refOfPos[j] = c[k];
+        if(isInner[k]) {
+            imask |= 1u << s;
+            codes = (codes & ~(0xFu << (4 * j))) | ((uint32_t)s << (4 * j));
+            vm |= 8u << (4 * j);
+            queueOut[qBase + ci] = make_uint2(c[k], childBase + ci);
             ++ci;
         } else {
-            nd.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | po);
-            const uint32_t first = refFirst(r, range);
-            for(uint32_t k = 0; k < cnt; ++k) writeLeafPrim(leafSrc, primOffset + primBase + po + k, vals[first + k]);
-            po += cnt;
+            const uint32_t cnt = refCount(c[k], range), first = refFirst(c[k], range);
+            vm |= ((1u << cnt) - 1u) << (4 * j);
+            for(uint32_t kk = 0; kk < cnt; ++kk) writeLeafPrim(leafSrc, primOffset + primBase + kLeafStride * (uint32_t)j + kk, vals[first + kk]);
         }
     }
+    if(wideRef)
+        for(int j = 0; j < 8; ++j) wideRef[(size_t)wide * 8 + j] = refOfPos[j];
     nd.imask = (uint8_t)imask;
     nd.childBase = nodeOffset + childBase;
-    nd.primBase = primOffset + primBase;
+    nd.primBase = (primOffset + primBase) | kPrimGroupBit;
+    nd.codes = codes;
+    nd.vm = vm;
     nodes[nodeOffset + wide] = nd;
 }
 
@@ -624,26 +636,24 @@ __global__ void k_requantize(uint32_t nWide, Node8* __restrict__ nodes, uint32_t
     if(w >= nWide) return;
     Node8 nd = nodes[nodeOffset + w];
     float clo[8][3], chi[8][3];
-    int slotOfChild[8];
+    int posOfChild[8];
     int n = 0;
-    for(int s = 0; s < 8; ++s) {
-        const uint32_t r = wideRef[(size_t)w * 8 + s];
+    const uint32_t pb = nd.primBase & ~kPrimGroupBit;
+    for(int j = 0; j < 8; ++j) {
+        const uint32_t r = wideRef[(size_t)w * 8 + j];
         if(r == kInvalid) continue;
         loadRefBox(r, bnodes, primBox, vals, clo[n], chi[n]);
-        slotOfChild[n++] = s;
+        posOfChild[n++] = j;
         const uint32_t cnt = refCount(r, range);
         if(cnt <= (uint32_t)kMaxLeafPrims) {
-            const uint32_t first = refFirst(r, range), off = nd.meta[s] & 31u;
-            for(uint32_t k = 0; k < cnt; ++k) writeLeafPrim(leafSrc, nd.primBase + off + k, vals[first + k]);
+            const uint32_t first = refFirst(r, range);
+            for(uint32_t k = 0; k < cnt; ++k) writeLeafPrim(leafSrc, pb + kLeafStride * (uint32_t)j + k, vals[first + k]);
         }
     }
     const uint8_t imask = nd.imask;
-    uint8_t meta[8];
-    for(int s = 0; s < 8; ++s) meta[s] = nd.meta[s];
-    const uint32_t cb = nd.childBase, pb = nd.primBase;
-    quantizeNode(nd, clo, chi, slotOfChild, n);
-    nd.imask = imask; nd.childBase = cb; nd.primBase = pb;
-    for(int s = 0; s < 8; ++s) nd.meta[s] = meta[s];
+    const uint32_t cb = nd.childBase, pbFlag = nd.primBase, codes = nd.codes, vm = nd.vm;
+    quantizeNode(nd, clo, chi, posOfChild, n);
+    nd.imask = imask; nd.childBase = cb; nd.primBase = pbFlag; nd.codes = codes; nd.vm = vm;
     nodes[nodeOffset + w] = nd;
     (void)primOffset;
 }

@@ -113,27 +113,35 @@ __device__ __forceinline__ float byteF(uint32_t w) {  // 1 + b / 32768 for byte 
     return __uint_as_float(__byte_perm(0x3F800000u, w, 0x3240u + (J << 4)));   // the affine map back to b is folded into the FFMA constants
 }
 
-// One child of a node: slab test on the quantised planes, then OR the child's bits into the hit mask.  Branch-free:
-// bits4 / idx4 hold, per child byte, the bits to insert (0 for an empty slot) and where (see decodeMeta4).
-template <int J>
-__device__ __forceinline__ void childTest(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, uint32_t bits4, uint32_t idx4,
-                                          float ax, float ay, float az, float onx, float ony, float onz, float ofx, float ofy, float ofz, float tmin,
-                                          float tmax, uint32_t& hitmask) {
-    const float tnx = fmaf(byteF<J>(nx), ax, onx), tny = fmaf(byteF<J>(ny), ay, ony), tnz = fmaf(byteF<J>(nz), az, onz);
-    const float tfx = fmaf(byteF<J>(fx), ax, ofx), tfy = fmaf(byteF<J>(fy), ay, ofy), tfz = fmaf(byteF<J>(fz), az, ofz);
-    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-    const uint32_t b = (bits4 >> (8 * J)) & 0xffu, i = (idx4 >> (8 * J)) & 0xffu;
-    hitmask |= (tn <= tf) ? (b << i) : 0u;
+// d = a * b + c on two binary32 values at once (sm_100a FFMA2; b is broadcast): near and far plane of one axis share the multiplier
+__device__ __forceinline__ void fma2(float a0, float a1, float b, float c0, float c1, float& d0, float& d1) {
+    asm("{\n\t.reg .b64 va, vb, vc, vd;\n\tmov.b64 va, {%2, %3};\n\tmov.b64 vb, {%4, %4};\n\tmov.b64 vc, {%5, %6};\n\t"
+        "fma.rn.f32x2 vd, va, vb, vc;\n\tmov.b64 {%0, %1}, vd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
 }
 
-// Four meta bytes at once (after Ylitie et al. 2017): inner children (bits 3 and 4 set) get bit index 24 + (slot ^ octinv),
-// leaves keep their primitive offset; the bits to insert are meta >> 5 (1 for inner nodes, unary count for leaves).
-__device__ __forceinline__ void decodeMeta4(uint32_t meta4, uint32_t octinv4, uint32_t& bits4, uint32_t& idx4) {
-    const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t innerMask4 = (isInner4 >> 4) * 0xffu;
-    idx4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
-    bits4 = (meta4 >> 5) & 0x07070707u;
+// One child of a node: slab test on the quantised planes; a hit sets nibble POS of the hit mask.  J: byte of the plane words.
+template <int J, int POS>
+__device__ __forceinline__ void childTest(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float ax, float ay, float az, float onx,
+                                          float ony, float onz, float ofx, float ofy, float ofz, float tmin, float tmax, uint32_t& hn) {
+#ifdef RG_FFMA2
+    float tnx, tny, tnz, tfx, tfy, tfz;
+    fma2(byteF<J>(nx), byteF<J>(fx), ax, onx, ofx, tnx, tfx);
+    fma2(byteF<J>(ny), byteF<J>(fy), ay, ony, ofy, tny, tfy);
+    fma2(byteF<J>(nz), byteF<J>(fz), az, onz, ofz, tnz, tfz);
+#else
+    const float tnx = fmaf(byteF<J>(nx), ax, onx), tny = fmaf(byteF<J>(ny), ay, ony), tnz = fmaf(byteF<J>(nz), az, onz);
+    const float tfx = fmaf(byteF<J>(fx), ax, ofx), tfy = fmaf(byteF<J>(fy), ay, ofy), tfz = fmaf(byteF<J>(fz), az, ofz);
+#endif
+    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+    if(tn <= tf) hn |= 0xFu << (4 * POS);
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // default mode: nibble bit 3 = replicate the byte's sign
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
 }
 
 // Watertight ray / triangle test (Woop, Benthin, Wald 2013), no culling; operation order == oracle/orc_scene.cpp intersectTri.
@@ -243,36 +251,49 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* _
     // near / far plane words by the sign of the direction: one LOP3 each on the packed words BEFORE the byte decode
     // (a plain ?: lets the compiler select after decoding both, which doubles the PRMTs)
     const uint32_t mx = (r.octinv & 4u) ? 0u : 0xffffffffu, my = (r.octinv & 2u) ? 0u : 0xffffffffu, mz = (r.octinv & 1u) ? 0u : 0xffffffffu;
-    const uint32_t octinv4 = r.octinv * 0x01010101u;
-    uint32_t hitmask = 0;
-#ifdef RG_UNROLL_HALVES
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-    for(int half = 0; half < 2; ++half) {   // slots 0..3, then 4..7: a rolled loop keeps the hot code small for the instruction cache
-        const uint32_t lx = half ? n2.y : n2.x, ly = half ? n2.w : n2.z, lz = half ? n3.y : n3.x;
-        const uint32_t hx = half ? n3.w : n3.z, hy = half ? n4.y : n4.x, hz = half ? n4.w : n4.z;
-        const uint32_t nx = bitsel(mx, hx, lx), fx = bitsel(mx, lx, hx), ny = bitsel(my, hy, ly), fy = bitsel(my, ly, hy), nz = bitsel(mz, hz, lz), fz = bitsel(mz, lz, hz);
-        uint32_t bits4, idx4;
-        decodeMeta4(half ? n1.w : n1.z, octinv4, bits4, idx4);
-        childTest<0>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-        childTest<1>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-        childTest<2>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
-        childTest<3>(nx, ny, nz, fx, fy, fz, bits4, idx4, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hitmask);
+    const uint32_t vm = n1.w;
+    // The children sit in positions 0..n-1 (rg_types.cuh): two at a time, stop at the first empty pair (vm nibbles of
+    // occupied positions are non-zero).  A hit child sets its nibble of hn.
+    uint32_t hn = 0;
+    {
+        const uint32_t nx = bitsel(mx, n3.z, n2.x), fx = bitsel(mx, n2.x, n3.z), ny = bitsel(my, n4.x, n2.z), fy = bitsel(my, n2.z, n4.x),
+                       nz = bitsel(mz, n4.z, n3.x), fz = bitsel(mz, n3.x, n4.z);
+        childTest<0, 0>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
+        childTest<1, 1>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
+        if(vm >= 0x100u) {
+            childTest<2, 2>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
+            childTest<3, 3>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
+        }
     }
-    T.ng = make_uint2(n1.x, (hitmask & 0xff000000u) | (n0.w >> 24));
-    T.tg = make_uint2(n1.y, hitmask & 0x00ffffffu);
+    if(vm >= 0x10000u) {
+        const uint32_t nx = bitsel(mx, n3.w, n2.y), fx = bitsel(mx, n2.y, n3.w), ny = bitsel(my, n4.y, n2.w), fy = bitsel(my, n2.w, n4.y),
+                       nz = bitsel(mz, n4.w, n3.y), fz = bitsel(mz, n3.y, n4.w);
+        childTest<0, 4>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
+        childTest<1, 5>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
+        if(vm >= 0x1000000u) {
+            childTest<2, 6>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
+            childTest<3, 7>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
+        }
+    }
+    // Internal children that were hit -> bits 24 + (code ^ octant) of the node group, so that the highest bit is the nearest child:
+    // ONE table look-up per four children (PRMT: selector nibble = code ^ octant picks the byte 1 << nibble; nibble 8 yields 0),
+    // then the eight distinct one-hot bytes are summed into the top byte by a multiplication.
+    const uint32_t innerNib = ((vm >> 3) & 0x11111111u) * 15u;
+    const uint32_t sel = bitsel(hn & innerNib, n1.z ^ (r.octinv * 0x11111111u), 0x88888888u);
+    const uint32_t onehot = prmt(0x08040201u, 0x80402010u, sel) | prmt(0x08040201u, 0x80402010u, sel >> 16);
+    T.ng = make_uint2(n1.x, ((onehot * 0x01010101u) & 0xff000000u) | (n0.w >> 24));
+    T.tg = make_uint2(n1.y, hn & vm & 0x77777777u);   // primitive k of position j: bit 4 j + k
 }
 
 // travPrim: ONE primitive of the lane's primitive group -- a triangle test inside an instance, entering an instance in the TLAS.
 template <bool COUNT, class WR>
 __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
     RayCtx& r = T.r;
-    const int bit = __ffs(T.tg.y) - 1;
+    const uint32_t bit = (uint32_t)(__ffs(T.tg.y) - 1);
     T.tg.y &= T.tg.y - 1u;
+    const uint32_t primIdx = (T.tg.x & ~kPrimGroupBit) + bit - (bit >> 2);   // bit 4 j + k -> element 3 j + k of the group (rg_types.cuh)
     if(T.curInst == kInvalid) {
-        const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + (T.tg.x + bit));
+        const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + primIdx);
         const uint4 l3 = __ldg(lp + 3), l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);   // all four in flight at once
         // instance of an empty mesh, or stack exhausted (never with sane scenes): skip
         if(l3.x != kInvalid && T.sp + 6 <= kStackSize) {
@@ -318,7 +339,7 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
         }
         return;
     } else {
-        const float4* tp = reinterpret_cast<const float4*>(P.tris + (T.tg.x + bit));
+        const float4* tp = reinterpret_cast<const float4*>(P.tris + primIdx);
         const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
         if(COUNT) cnt[CNT_TRIS]++;
         float t, u, v;
@@ -349,7 +370,7 @@ __device__ __forceinline__ bool travPop(Trav& T, const uint2* __restrict__ stack
             r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
         }
     }
-    if(!(T.ng.y & 0xff000000u)) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }   // a primitive group came off the stack
+    if(T.ng.x & kPrimGroupBit) { T.tg = T.ng; T.ng = make_uint2(0u, 0u); }   // a primitive group came off the stack
     return false;
 }
 

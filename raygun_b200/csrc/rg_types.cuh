@@ -16,18 +16,25 @@
 namespace rg {
 
 // Compressed 8-wide node (after Ylitie, Karras, Laine 2017).  Child boxes are quantised to 8 bits
-// relative to the node origin p with per-axis power-of-two scale 2^e.  Slot s of a node sits on the
-// (s&4 ? +x : -x, s&2 ? +y : -y, s&1 ? +z : -z) side of the node centre where possible, so XOR-ing the
-// slot with the ray's direction octant yields a front-to-back order without sorting.
-//   meta[s] == 0                    empty slot
-//   meta[s] == 0x20 | (24 + s)      internal child; children are stored contiguously from childBase in slot order
-//   meta[s] == unary(n) << 5 | off  leaf with n in 1..3 primitives starting at primBase + off (off < 24)
+// relative to the node origin p with per-axis power-of-two scale 2^e.  The n children of a node sit in
+// POSITIONS 0..n-1 (leaves first, then internal children, empty positions last with an inverted box), so
+// the traversal tests them two at a time and stops at the first empty pair.  Every internal child also has
+// an octant CODE c (bit 2/1/0 = +x/+y/+z side of the node centre where possible): XOR-ing the code with the
+// ray's direction octant yields a front-to-back order without sorting.
+//   codes  nibble j = code of the internal child at position j (8 for a leaf / empty position)
+//   vm     nibble j = bit 3: internal child; bits 0..2: valid primitives of the leaf at position j
+//          (primitive k of position j is element (primBase & 0x7fffffff) + 3 j + k of the primitive array: stride 3,
+//          unused elements are never read)
+//   imask  bit c = an internal child with code c exists; child nodes are stored contiguously from childBase
+//          in code order
+//   primBase carries bit 31 (marks primitive groups on the traversal stack)
 struct alignas(16) Node8 {
     float px, py, pz;
     uint8_t ex, ey, ez, imask;
     uint32_t childBase;
     uint32_t primBase;
-    uint8_t meta[8];
+    uint32_t codes;
+    uint32_t vm;
     uint8_t qlox[8], qloy[8];
     uint8_t qloz[8], qhix[8];
     uint8_t qhiy[8], qhiz[8];
@@ -67,6 +74,8 @@ static_assert(sizeof(BNode) == 32, "BNode");
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kInvalid = 0xffffffffu;
 constexpr int kMaxLeafPrims = 3;
+constexpr uint32_t kPrimGroupBit = 0x80000000u;   // Node8::primBase / traversal stack entries
+constexpr uint32_t kLeafStride = 3;               // primitive array elements reserved per leaf child
 
 struct Hit { float t, u, v; uint32_t inst, prim; };
 
