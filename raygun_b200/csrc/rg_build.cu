@@ -338,13 +338,14 @@ __device__ void quantizeNode(Node8& nd, const float (*clo)[3], const float (*chi
         const float ext = hi[a] - lo[a];
         int k = 0;
         if(ext > 0.0f) (void)frexpf(ext / 255.0f, &k); else k = -120;
-        k = max(-120, min(120, k));
+        k = max(-120, min(100, k));
         // fl(hi - lo) may round down: make sure 255 steps really reach hi
         while((double)lo[a] + 255.0 * (double)__uint_as_float((uint32_t)(k + 127) << 23) < (double)hi[a]) ++k;
         eb[a] = (uint8_t)(k + 127);
         scale[a] = __uint_as_float((uint32_t)eb[a] << 23);
     }
-    nd.ex = eb[0]; nd.ey = eb[1]; nd.ez = eb[2];
+    // stored with the bias of the traversal's byte decode (1 + q / 32768, rg_trace.cu byteF): 2^(e + 15)
+    nd.ex = (uint8_t)(eb[0] + kExpBias); nd.ey = (uint8_t)(eb[1] + kExpBias); nd.ez = (uint8_t)(eb[2] + kExpBias);
     uint8_t* qlo[3] = {nd.qlox, nd.qloy, nd.qloz};
     uint8_t* qhi[3] = {nd.qhix, nd.qhiy, nd.qhiz};
     for(int s = 0; s < 8; ++s)

@@ -64,11 +64,11 @@ __device__ __forceinline__ V3 refract3(V3 I, V3 N, float eta) {
 
 // ------------------------------------------------------------------------------------------------ traversal
 struct RayCtx {
-    float ox, oy, oz, dx, dy, dz;
+    float ox, oy, oz;
     float ix, iy, iz;     // 1/d (zero components clamped to +-1e-30)
     float Sx, Sy, Sz;     // Woop shear
     uint32_t octinv;      // bit 2/1/0 set when d.x/d.y/d.z >= 0
-    int kx, ky, kz;
+    int kx, ky, kz;       // kz == kNoShear: shear constants not computed yet
 };
 
 // component k of (x, y, z) as two predicated selects: written in PTX because the compiler turns the ?: chain into divergent branches
@@ -81,14 +81,21 @@ __device__ __forceinline__ float sel3(int k, float x, float y, float z) {
 }
 __device__ __forceinline__ float __frcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-__device__ __forceinline__ void setupRay(RayCtx& r, float ox, float oy, float oz, float dx, float dy, float dz) {
-    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+// The ray constants of the slab test (every node) ...
+__device__ __forceinline__ void setupSlab(RayCtx& r, float ox, float oy, float oz, float dx, float dy, float dz) {
+    r.ox = ox; r.oy = oy; r.oz = oz;
     const float eps = 1e-30f;
     // approximate reciprocal (1 ulp): only the conservative slab test uses it; the slack below covers it
     r.ix = __frcp_approx(fabsf(dx) > eps ? dx : copysignf(eps, dx));
     r.iy = __frcp_approx(fabsf(dy) > eps ? dy : copysignf(eps, dy));
     r.iz = __frcp_approx(fabsf(dz) > eps ? dz : copysignf(eps, dz));
     r.octinv = (dx >= 0.0f ? 4u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 1u : 0u);
+}
+// ... and those of the triangle test (Woop shear; two IEEE divisions).  Only needed inside an instance, so they are computed when
+// the first instance is entered (kz == kNoShear until then): rays that miss every instance box never pay for them, and a ray that
+// enters a rotated / scaled instance pays once (for the object-space direction) instead of twice.
+constexpr int kNoShear = 3;
+__device__ __forceinline__ void setupShear(RayCtx& r, float dx, float dy, float dz) {
     const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
     const int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
     int kx = kz == 2 ? 0 : kz + 1;
@@ -207,6 +214,9 @@ struct Trav {
 };
 
 // Closest hit in (tmin, tmax).  hit.inst == kInvalid on miss.
+// LAZY: leave the triangle-test constants to the first instance entry (setupShear); otherwise compute them for the world-space direction now
+// (the pool scheduler starts rays with more lanes than it has at an instance entry)
+template <bool LAZY>
 __device__ __forceinline__ void travInit(const TraceParams& P, Trav& T, Hit& hit, float ox, float oy, float oz, float dx, float dy, float dz, float tmax) {
     hit.t = tmax; hit.u = 0.0f; hit.v = 0.0f; hit.inst = kInvalid; hit.prim = kInvalid;
     T.sp = 0;
@@ -215,7 +225,8 @@ __device__ __forceinline__ void travInit(const TraceParams& P, Trav& T, Hit& hit
     // nothing to traverse (the first travStep reports a miss): empty scene, zero direction (refract on total internal reflection), NaN ray
     const bool none = P.nInst == 0 || (dx == 0.0f && dy == 0.0f && dz == 0.0f) || !(dx == dx && dy == dy && dz == dz && ox == ox && oy == oy && oz == oz);
     T.ng = make_uint2(0u, none ? 0u : 0x80000000u);
-    if(!none) setupRay(T.r, ox, oy, oz, dx, dy, dz);
+    T.r.kx = 0; T.r.ky = 0; T.r.kz = kNoShear; T.r.Sx = 0.0f; T.r.Sy = 0.0f; T.r.Sz = 0.0f;
+    if(!none) { setupSlab(T.r, ox, oy, oz, dx, dy, dz); if(!LAZY) setupShear(T.r, dx, dy, dz); }
 }
 
 // The three kinds of traversal work.  travNode: the 8 children of the next node of the lane's node group; leaves T.ng / T.tg = the hit
@@ -242,7 +253,7 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* _
     // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
     // byteF gives v = 1 + q / 32768, so t = v * A + (b - A) with A = 32768 * 2^e / d.  Rounding: ulp(A) = 1/256 of one
     // quantisation step in t, plus the error of b = (p - o) / d; both are covered by the slack (relative to |b| and to a step).
-    const float ax = sx * r.ix * 32768.0f, ay = sy * r.iy * 32768.0f, az = sz * r.iz * 32768.0f;
+    const float ax = sx * r.ix, ay = sy * r.iy, az = sz * r.iz;   // the node's exponents carry the factor 32768 (kExpBias)
     const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
     const float kSlack = 7.2e-7f, kStep = 1.0f / (32768.0f * 64.0f);   // 1/64 of a quantisation step
     const float wx = fmaf(fabsf(bx), kSlack, fabsf(ax) * kStep), wy = fmaf(fabsf(by), kSlack, fabsf(ay) * kStep), wz = fmaf(fabsf(bz), kSlack, fabsf(az) * kStep);
@@ -299,7 +310,8 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
         if(l3.x != kInvalid && T.sp + 6 <= kStackSize) {
             if(COUNT) cnt[CNT_INST]++;
             const float ox = wray.ox(), oy = wray.oy(), oz = wray.oz();
-            bool enter = true;
+            bool enter = true, shear;
+            float sdx = wray.dx(), sdy = wray.dy(), sdz = wray.dz();   // direction inside the instance
             if(l3.z) {
                 // pure translation (flagged by the instance preparation): the direction and everything derived from it stay;
                 // the oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t
@@ -307,18 +319,20 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
                 if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
                 stack[T.sp++] = make_uint2(kInvalid, 0x1000u);
                 r.ox = __fadd_rn(ox, __uint_as_float(l0.w)); r.oy = __fadd_rn(oy, __uint_as_float(l1.w)); r.oz = __fadd_rn(oz, __uint_as_float(l2.w));
+                shear = r.kz == kNoShear;   // first instance of this ray
             } else {
                 // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
                 const float* w0 = reinterpret_cast<const float*>(&l0); const float* w1 = reinterpret_cast<const float*>(&l1);
                 const float* w2 = reinterpret_cast<const float*>(&l2);
-                const float dx = wray.dx(), dy = wray.dy(), dz = wray.dz();
+                const float dx = sdx, dy = sdy, dz = sdz;
                 const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w0[0], ox), __fmul_rn(w0[1], oy)), __fmul_rn(w0[2], oz)), w0[3]);
                 const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1[0], ox), __fmul_rn(w1[1], oy)), __fmul_rn(w1[2], oz)), w1[3]);
                 const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w2[0], ox), __fmul_rn(w2[1], oy)), __fmul_rn(w2[2], oz)), w2[3]);
-                const float odx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
-                const float ody = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
-                const float odz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
-                if(odx == 0.0f && ody == 0.0f && odz == 0.0f) {
+                sdx = __fadd_rn(__fadd_rn(__fmul_rn(w0[0], dx), __fmul_rn(w0[1], dy)), __fmul_rn(w0[2], dz));
+                sdy = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
+                sdz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
+                shear = true;
+                if(sdx == 0.0f && sdy == 0.0f && sdz == 0.0f) {
                     enter = false;
                 } else {
                     if(T.tg.y) stack[T.sp++] = T.tg;
@@ -328,9 +342,10 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
                     stack[T.sp++] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx));
                     stack[T.sp++] = make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz));
                     stack[T.sp++] = make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8));
-                    setupRay(r, oox, ooy, ooz, odx, ody, odz);
+                    setupSlab(r, oox, ooy, ooz, sdx, sdy, sdz);
                 }
             }
+            if(enter && shear) setupShear(r, sdx, sdy, sdz);
             if(enter) {
                 T.curInst = l3.y;
                 T.ng = make_uint2(l3.x, 0x80000000u);
@@ -942,7 +957,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
                     myCtx = W.rayQ[(rayHead + r) & kQMask];
                     tmin = W.ray[6][myCtx];
                     steps = 0;
-                    travInit(P, T, hit, W.ray[0][myCtx], W.ray[1][myCtx], W.ray[2][myCtx], W.ray[3][myCtx], W.ray[4][myCtx], W.ray[5][myCtx], W.ray[7][myCtx]);
+                    travInit<false>(P, T, hit, W.ray[0][myCtx], W.ray[1][myCtx], W.ray[2][myCtx], W.ray[3][myCtx], W.ray[4][myCtx], W.ray[5][myCtx], W.ray[7][myCtx]);
                 }
                 rayHead += take; rayCount -= take; nEmpty -= take;
             }
@@ -1078,7 +1093,7 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
             Hit hit;
             Trav T;
             const WorldRayRegs wr{{ro.x, ro.y, ro.z}, {rd.x, rd.y, rd.z}, rtmax};
-            travInit(P, T, hit, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmax);
+            travInit<true>(P, T, hit, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmax);
             for(uint32_t steps = 0; !travStep<COUNT>(P, T, stack, hit, wr, rtmin, cntT) && steps < kMaxStepsPerRay; ++steps) {}
             // ---- shade: hit / miss program, then the frames that resume, up to the next traceRayEXT
             const int outcome = shadeContext<COUNT, MULTI>(P, K, hit, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
@@ -1108,7 +1123,7 @@ __global__ void k_trace_rays(const TraceParams P, const float* __restrict__ rays
     uint2 stack[kStackSize];
     uint32_t cnt[CNT_N];
     const WorldRayRegs wr{{q[0], q[1], q[2]}, {q[3], q[4], q[5]}, q[7]};
-    travInit(P, T, hit, q[0], q[1], q[2], q[3], q[4], q[5], q[7]);
+    travInit<true>(P, T, hit, q[0], q[1], q[2], q[3], q[4], q[5], q[7]);
     for(uint32_t steps = 0; !travStep<false>(P, T, stack, hit, wr, q[6], cnt) && steps < kMaxStepsPerRay; ++steps) {}
     tuv[3 * i] = hit.t; tuv[3 * i + 1] = hit.u; tuv[3 * i + 2] = hit.v;
     instPrim[2 * i] = hit.inst; instPrim[2 * i + 1] = hit.prim;

@@ -75,6 +75,7 @@ constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kInvalid = 0xffffffffu;
 constexpr int kMaxLeafPrims = 3;
 constexpr uint32_t kPrimGroupBit = 0x80000000u;   // Node8::primBase / traversal stack entries
+constexpr uint32_t kExpBias = 15;                 // Node8::ex/ey/ez hold e + 127 + kExpBias: the plane of byte q is p + q * 2^e
 constexpr uint32_t kLeafStride = 3;               // primitive array elements reserved per leaf child
 
 struct Hit { float t, u, v; uint32_t inst, prim; };
