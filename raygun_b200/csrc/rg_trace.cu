@@ -143,6 +143,9 @@ __device__ __forceinline__ void childTest(uint32_t nx, uint32_t ny, uint32_t nz,
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
     const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
     if(tn <= tf) hn |= 0xFu << (4 * POS);
+#ifdef RG_EXP_EXTRA_ALU   // experiment: sensitivity of the kernel to ALU-pipe instructions in the child test (3 more per child; results unchanged)
+    if(__byte_perm(nx, fx, 0x5140 + J) == 0xdeadbeefu) hn ^= 1u;
+#endif
 }
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // default mode: nibble bit 3 = replicate the byte's sign
@@ -996,7 +999,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
 #define RG_LANES_REFILL 32       // idle lanes before a warp of the lanes kernel fetches new work items (swept 2..32: C2 7.9 ms at 2, 6.6 at 8, 5.4 at 20-28, 5.2 at 32)
 #endif
 #ifndef RG_LANES_MIN_BLOCKS
-#define RG_LANES_MIN_BLOCKS 8
+#define RG_LANES_MIN_BLOCKS 5   // 96 registers, no spills; swept 4..8 with the round-2 node step: C2 4.75 / 4.48 / 4.56 / 4.49 / 4.68 ms
 #endif
 // The second scheduler, for COHERENT workloads: one context per lane, state in registers, frames in local memory.  A warp takes 32
 // consecutive work items (one sample index of one 8x4 tile), so its lanes trace neighbouring rays and then run the same shader
@@ -1179,6 +1182,10 @@ static int tracePerSm() {   // persistent grid: a multiple of the SM count; resi
         if(POOL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_pool<COUNT, MULTI>, 128, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_lanes<COUNT, MULTI>, 128, 0);
         if(const char* e = getenv(POOL ? "RGB200_POOL_CTAS" : "RGB200_LANES_CTAS")) { const int w = atoi(e); if(w >= 1 && w < v) v = w; }   // developer knob: occupancy sweeps
+        if(const char* e = getenv(POOL ? "RGB200_POOL_CARVEOUT" : "RGB200_LANES_CARVEOUT")) {   // developer knob: shared-memory carve-out in percent (the rest is L1)
+            if(POOL) cudaFuncSetAttribute(k_trace_pool<COUNT, MULTI>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+            else cudaFuncSetAttribute(k_trace_lanes<COUNT, MULTI>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+        }
         return v < 1 ? 1 : v;
     }();
     return perSm;
