@@ -148,6 +148,9 @@ int rg_build_blas(rg_ctx* ctx);
 /* Extension (BASELINE config 4; the reference never refits): new vertex records for one mesh
  * (same count), topology kept, boxes refitted bottom-up and re-quantised. */
 int rg_refit_blas(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vertices);
+/* The same with the new vertex records already in DEVICE memory (written by a skinning / physics kernel of the caller on any stream
+ * it has synchronised with): device-to-device copy on the library's stream, then the refit; no host round trip. */
+int rg_refit_blas_device(rg_ctx* ctx, uint32_t mesh, const rg_vertex* d_new_vertices);
 
 /* Raytracer::setupTopLevelAS (raytracer.cpp:76-85; TopLevelAS acceleration_structure.cpp:55-138):
  * called every frame; rebuilds the TLAS from scratch on the device.  The caller performs the entity

@@ -34,7 +34,7 @@ IMG_FINAL, IMG_BASE, IMG_NORMAL, IMG_ROUGH, IMG_TRANSITIONS, IMG_ROUGH_A, IMG_RO
 
 ABI_SYMBOLS = (
     "rg_create", "rg_destroy", "rg_resize", "rg_last_error", "rg_set_region", "rg_upload_geometry", "rg_upload_materials", "rg_build_blas",
-    "rg_refit_blas", "rg_set_instances", "rg_set_ubo", "rg_render", "rg_sync", "rg_read_rgba8", "rg_read_image", "rg_read_ids", "rg_get_timings",
+    "rg_refit_blas", "rg_refit_blas_device", "rg_set_instances", "rg_set_ubo", "rg_render", "rg_sync", "rg_read_rgba8", "rg_read_image", "rg_read_ids", "rg_get_timings",
     "rg_set_instances_device", "rg_set_ubo_device", "rg_framebuffer_device_ptr", "rg_set_gather_target", "rg_gather_buffer_export",
     "rg_gather_buffer_open", "rg_gather_buffer_close", "rg_read_gathered_rgba8", "rg_debug_blas_sort", "rg_debug_tlas_sort", "rg_debug_trace_rays",
     "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2", "rg_debug_last_trace_rays_ms",
@@ -143,6 +143,10 @@ class Raytracer:
     def refitBottomLevelAS(self, mesh: int, new_vertices):
         v = np.ascontiguousarray(new_vertices, np.uint32)
         self._ck(self.lib.rg_refit_blas(self.h, C.c_uint32(mesh), _p(v)))
+
+    def refitBottomLevelAS_device(self, mesh: int, d_ptr: int):
+        """new vertex records (32 B each, same count as the mesh) already in device memory"""
+        self._ck(self.lib.rg_refit_blas_device(self.h, C.c_uint32(mesh), C.c_void_p(d_ptr)))
 
     # ------------------------------------------------------------------ per frame (render_system.cpp:88-162)
     @staticmethod

@@ -475,13 +475,13 @@ int rg_build_blas(rg_ctx* ctx) {
     return 0;
 }
 
-int rg_refit_blas(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vertices) {
+static int refitBlasCommon(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vertices, cudaMemcpyKind kind, const char* who) {
     if(!ctx) return 1;
-    if(mesh >= ctx->meshes.size() || !ctx->meshes[mesh].built) return fail(ctx, "rg_refit_blas: mesh %u has no BLAS", mesh);
-    if(!new_vertices) return fail(ctx, "rg_refit_blas: null input");
+    if(mesh >= ctx->meshes.size() || !ctx->meshes[mesh].built) return fail(ctx, "%s: mesh %u has no BLAS", who, mesh);
+    if(!new_vertices) return fail(ctx, "%s: null input", who);
     USE_DEVICE();
     MeshBlas& mb = ctx->meshes[mesh];
-    CK(cudaMemcpyAsync((char*)ctx->dVertices + (size_t)mb.range.vtx_off * 32, new_vertices, (size_t)mb.range.vtx_cnt * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync((char*)ctx->dVertices + (size_t)mb.range.vtx_off * 32, new_vertices, (size_t)mb.range.vtx_cnt * 32, kind, ctx->stream));
     TriSource src{ctx->dVertices, ctx->dIndices, mb.range.vtx_off, mb.range.idx_off, mb.range.idx_cnt / 3};
     const uint64_t before = mb.scratch.launches;
     CK(cudaEventRecord(ctx->ev[EV_AS0], ctx->stream));
@@ -490,6 +490,16 @@ int rg_refit_blas(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vertices) {
     ctx->launches += mb.scratch.launches - before;
     CK(cudaGetLastError());
     return 0;
+}
+
+int rg_refit_blas(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vertices) {
+    return refitBlasCommon(ctx, mesh, new_vertices, cudaMemcpyHostToDevice, "rg_refit_blas");
+}
+
+// The animated vertices already live in device memory (a skinning / physics kernel wrote them): no host round trip, the copy into the
+// library's vertex buffer (which the closest-hit shading reads) is device to device on the library's stream.
+int rg_refit_blas_device(rg_ctx* ctx, uint32_t mesh, const rg_vertex* d_new_vertices) {
+    return refitBlasCommon(ctx, mesh, d_new_vertices, cudaMemcpyDeviceToDevice, "rg_refit_blas_device");
 }
 
 int rg_set_instances(rg_ctx* ctx, const rg_instance* instances, uint32_t n_instances) {

@@ -490,6 +490,81 @@ def test_full_size_configs_schedulers_agree_and_frames_repeat(rgmod, workload):
     assert len(np.unique(frames[0].reshape(-1, 4), axis=0)) > 1000      # a real image, not a constant
 
 
+@pytest.mark.parametrize("n", [50, 100])
+def test_large_tlas_frame_parity(rgmod, O, S, n):
+    """BASELINE config 4's acceleration-structure path: 2 501 and 10 001 instances are above kTlasFusedMax (1 024), so the TLAS is built
+    by the multi-kernel builder (k_prepare_instances, k_inst_boxes, radix sort, k_hierarchy, k_refit_binary, k_collapse_all) and then
+    TRAVERSED: primary ids and the image are compared with the oracle for two animation frames, under both trace schedulers
+    (replaces TopLevelAS, raygun/render/acceleration_structure.cpp:55-138, called every frame from raytracer.cpp:76-85)."""
+    W, H = 480, 270
+    balls = S.AnimatedBalls(n)
+    sd0 = balls.scene(0.0)
+    assert len(sd0.inst_xform) > 1024
+    ubo = S.make_ubo(balls.view_inverse, S.proj_inverse(W, H), 1, 3)
+    osc = O.OracleScene(sd0)
+    for sched in (rgmod.RG_SCHED_LANES, rgmod.RG_SCHED_POOL):
+        rt = rgmod.Raytracer(W, H)
+        rt.set_trace_scheduler(sched)
+        rt.load_scene(sd0)
+        for frame in (3, 11):
+            xf = balls.instances(frame / 60.0)
+            rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS, rt.pack_instances(xf, balls.meta))
+            osc.set_instances(xf, balls.meta)
+            ref = osc.render(ubo, W, H, O.FXAA)
+            _check_frame(rt, ref, rgmod, f"balls {n}x{n} frame {frame} sched {sched}")
+            inst, _ = rt.read_ids()
+            assert len(np.unique(inst)) > 200      # the frame really shows hundreds of different instances
+        rt.close()
+
+
+@pytest.mark.parametrize("workload", ["c3", "c5"])
+def test_full_size_frames_against_the_oracle(rgmod, O, workload):
+    """BASELINE configs 3 (785 instances, 1 003 522 triangles, maxRecursions 8, 1920x1080) and 5 (3840x2160, numSamples 4) at FULL
+    size against the CPU oracle (a few seconds per frame on the box's host cores): ids, PSNR, error bar and every ray counter."""
+    import bench
+    desc, W, H, sd, ubo = bench.make_workload(workload)
+    ref = O.OracleScene(sd).render(ubo, W, H, O.FXAA)
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(sd)
+    rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
+    _check_frame(rt, ref, rgmod, f"full-size {workload}")
+    tm, c = rt.timings(), ref["counters"]
+    for k, o in (("rays_primary", "primary"), ("rays_shadow", "shadow"), ("rays_reflect", "reflect"), ("rays_refract", "refract")):
+        assert abs(tm[k] - c[o]) <= 2e-4 * max(c[o], 1), (k, tm[k], c[o])
+    rt.close()
+
+
+def test_blas_refit_from_device_memory(rgmod, O, S, example_scene):
+    """rg_refit_blas_device: the animated vertices are already in HBM (no 32 B / vertex host copy per frame); same result as the
+    host-pointer refit and as a fresh build (the oracle)."""
+    import torch
+    W, H = 256, 144
+    sd = example_scene
+    ubo = S.example_ubo(W, H)
+    vo, vc = int(sd.meshes[3, 0]), int(sd.meshes[3, 1])     # the ball
+    v = sd.vertices[vo:vo + vc].copy()
+    p = v.view(np.float32)
+    p[:, 0:3] *= (1.0 + 0.25 * np.sin(7.0 * p[:, 1:2])).astype(np.float32)
+    frames = []
+    for device_ptr in (False, True):
+        rt = rgmod.Raytracer(W, H)
+        rt.load_scene(sd)
+        if device_ptr:
+            dv = torch.from_numpy(v.view(np.int32).copy()).cuda()
+            torch.cuda.synchronize()
+            rt.refitBottomLevelAS_device(3, dv.data_ptr())
+        else:
+            rt.refitBottomLevelAS(3, v)
+        rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS, rt.pack_instances(sd.inst_xform, sd.inst_meta))
+        frames.append(rt.read_rgba8().copy())
+        if device_ptr:
+            sd2 = S.SceneData(sd.vertices.copy(), sd.indices, sd.meshes, sd.materials, sd.inst_xform, sd.inst_meta)
+            sd2.vertices[vo:vo + vc] = v
+            _check_frame(rt, O.OracleScene(sd2).render(ubo, W, H, O.FXAA), rgmod, "refit ball (device pointer)")
+        rt.close()
+    assert np.array_equal(frames[0], frames[1])
+
+
 def test_resize_sample_change_and_material_edit_equal_a_fresh_context(rgmod, S, example_scene):
     """RenderSystem::reload (render_system.cpp:77-78: a new Raytracer at the new window size), numSamples changed from the UI
     (render_system.cpp:264) and the material editor's re-upload (gpu_material.cpp:91-93) on a LIVE context must give exactly what a
