@@ -213,6 +213,8 @@ int rg_framebuffer_device_ptr(rg_ctx* ctx, void** d_ptr);
  * whole frame; the trace kernel stores each finished pixel's G-buffer straight into the images of every rank whose
  * region + halo contains it (own memory or peer memory over NVLink).  Two device-side flag barriers per frame (after the
  * trace, after the post chain) keep the ranks in step without host round trips; a wait gives up after 4 s (rg_sync_error).
+ * rg_set_region / rg_resize re-allocate the images a peer stores into, so they FAIL while the context is partitioned (world > 1):
+ * leave the mode on every rank first (rg_peer_detach_all, rg_set_partition(ctx, 0, 1)), resize, then attach again.
  * Order of calls: rg_set_region, rg_set_partition, then on every rank rg_peer_export -> exchange the descriptors ->
  * rg_peer_attach for every other rank (open_ipc = 1 across processes, 0 for contexts of one process). */
 typedef struct rg_peer_desc {
@@ -230,7 +232,7 @@ int rg_sync_error(rg_ctx* ctx);
 /* Tile gather over NVLink: the final kernel (FXAA + 8-bit convert) stores this context's region
  * straight into `d_target` (a width x height RGBA8 frame that may live on a PEER GPU: either a
  * pointer in the same process with peer access enabled, or one opened from a CUDA IPC handle). */
-int rg_set_gather_target(rg_ctx* ctx, void* d_target_rgba8);
+int rg_set_gather_target(rg_ctx* ctx, void* d_target_rgba8);   /* rg_resize clears it: the buffer has the old frame's stride */
 /* 64-byte cudaIpcMemHandle_t of this context's full-frame gather buffer (allocated on demand) and
  * its opening on another process' context. */
 int rg_gather_buffer_export(rg_ctx* ctx, void* handle64, void** d_ptr);

@@ -141,6 +141,8 @@ void closestHit(Ctx& c, Payload& payload, vec3 worldRayOrigin, vec3 worldRayDire
     const Material& gm = s.materials[inst.matOff + v0.matIndex];
     Mat mat{vec3(gm.diffuse[0], gm.diffuse[1], gm.diffuse[2]), gm.transparency, vec3(gm.specular[0], gm.specular[1], gm.specular[2]),
             gm.reflectivity, gm.roughness, gm.ior, gm.effectId, gm.rayConsumption, gm.emission};
+    // gpu_material.def documents rayConsumption as 1..5; the kernels clamp it to 1..8 so that every reflection advances recDepth (same here)
+    mat.rayConsumption = mat.rayConsumption < 1u ? 1u : (mat.rayConsumption > 8u ? 8u : mat.rayConsumption);
 
     // :111-114
     const float tmin = 0.01f;

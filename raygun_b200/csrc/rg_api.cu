@@ -376,14 +376,18 @@ int rg_resize(rg_ctx* ctx, uint32_t width, uint32_t height) {
     if(!ctx || !width || !height) return fail(ctx, "rg_resize: bad size");
     USE_DEVICE();
     CK(cudaStreamSynchronize(ctx->stream));
+    if(ctx->world > 1) return fail(ctx, "rg_resize: the context is in partitioned mode; peers hold pointers into its images -- call rg_peer_detach_all and rg_set_partition(ctx, 0, 1) on every rank first");
     ctx->W = width; ctx->H = height; ctx->ix0 = 0; ctx->iy0 = 0; ctx->ix1 = (int)width; ctx->iy1 = (int)height;
-    cudaFree(ctx->gatherOwn); ctx->gatherOwn = nullptr;
+    // the gather buffer (own or a peer's) has the old frame's stride: the caller sets a target for the new size again
+    cudaFree(ctx->gatherOwn); ctx->gatherOwn = nullptr; ctx->gatherTarget = nullptr;
     return allocImages(ctx);
 }
 
 int rg_set_region(rg_ctx* ctx, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
     if(!ctx) return 1;
     if(x0 >= x1 || y0 >= y1 || x1 > ctx->W || y1 > ctx->H) return fail(ctx, "rg_set_region: bad rectangle");
+    // The images are re-allocated: ranks that attached this one (rg_peer_attach) would keep storing G-buffer pixels into freed memory.
+    if(ctx->world > 1) return fail(ctx, "rg_set_region: the context is in partitioned mode; peers hold pointers into its images -- call rg_peer_detach_all and rg_set_partition(ctx, 0, 1) on every rank first");
     USE_DEVICE();
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->ix0 = (int)x0; ctx->iy0 = (int)y0; ctx->ix1 = (int)x1; ctx->iy1 = (int)y1;
@@ -609,7 +613,15 @@ int rg_set_ubo_device(rg_ctx* ctx, const rg_ubo* d_ubo) {
     // fade / showAlpha are kernel parameters of the post passes: fetch the tail of the UBO
     CK(cudaMemcpyAsync(ctx->hUboPinned, d_ubo, 192, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->hUbo = *ctx->hUboPinned;
+    const rg_ubo& u = *ctx->hUboPinned;
+    if(u.num_samples < 1 || u.num_samples > 64 || u.max_recursions < 0 || u.max_recursions > kMaxRecursions) {   // same bars as rg_set_ubo
+        const int ns = u.num_samples, mr = u.max_recursions;
+        *ctx->hUboPinned = ctx->hUbo;   // put the previous (valid) block back: the kernels divide by numSamples
+        CK(cudaMemcpyAsync(ctx->dUbo, ctx->hUboPinned, 192, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return fail(ctx, "rg_set_ubo_device: numSamples %d (1..64) or maxRecursions %d (0..%d) out of range", ns, mr, kMaxRecursions);
+    }
+    ctx->hUbo = u;
     return 0;
 }
 
@@ -730,8 +742,25 @@ int rg_framebuffer_device_ptr(rg_ctx* ctx, void** d_ptr) {
     return 0;
 }
 
+// A pointer handed over inside ONE process may live on another GPU: enable peer access to its device (CUDA IPC mappings come with it).
+static int ensurePeerAccess(rg_ctx* ctx, const void* p, const char* who) {
+    if(!p) return 0;
+    cudaPointerAttributes a{};
+    if(cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if(a.type != cudaMemoryTypeDevice || a.device == ctx->device) return 0;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, ctx->device, a.device));
+    if(!can) return fail(ctx, "%s: device %d cannot access memory of device %d", who, ctx->device, a.device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+    if(e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    if(e != cudaSuccess) return fail(ctx, "%s: cudaDeviceEnablePeerAccess(%d) failed: %s", who, a.device, cudaGetErrorString(e));
+    return 0;
+}
+
 int rg_set_gather_target(rg_ctx* ctx, void* d_target_rgba8) {
     if(!ctx) return 1;
+    USE_DEVICE();
+    if(ensurePeerAccess(ctx, d_target_rgba8, "rg_set_gather_target")) return 1;
     ctx->gatherTarget = (uint32_t*)d_target_rgba8;
     return 0;
 }
@@ -829,6 +858,8 @@ int rg_peer_attach(rg_ctx* ctx, uint32_t peer_rank, const rg_peer_desc* desc, in
             CK(cudaIpcOpenMemHandle(&ptrs[k], h, cudaIpcMemLazyEnablePeerAccess));
             ctx->peerIpcOpened[peer_rank][k] = ptrs[k];
         }
+    } else {
+        for(int k = 0; k < 5; ++k) if(ensurePeerAccess(ctx, ptrs[k], "rg_peer_attach")) return 1;
     }
     ctx->peers[peer_rank] = TraceParams::Target{(uint2*)ptrs[0], (uint2*)ptrs[1], (uint2*)ptrs[2], desc->x0, desc->y0, desc->w, desc->h};
     ctx->peerArriveTrace[peer_rank] = (uint32_t*)ptrs[3]; ctx->peerArrivePost[peer_rank] = (uint32_t*)ptrs[4];

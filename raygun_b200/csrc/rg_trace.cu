@@ -543,7 +543,9 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
         V3 diffuse = v3(m0.x, m0.y, m0.z), specular = v3(m1.x, m1.y, m1.z);
         const float transparency = m0.w; float reflectivity = m1.w;
         const float roughness = m2.x, ior = m2.y, emission = m3.x;
-        const uint32_t effectId = __float_as_uint(m2.z), rayConsumption = __float_as_uint(m2.w);
+        const uint32_t effectId = __float_as_uint(m2.z);
+        uint32_t rayConsumption = __float_as_uint(m2.w);   // gpu_material.def: 1..5; clamped so that every reflection advances recDepth (frame stack bound)
+        rayConsumption = rayConsumption < 1u ? 1u : (rayConsumption > (uint32_t)kMaxRecursions ? (uint32_t)kMaxRecursions : rayConsumption);
 
         const float b0 = 1.0f - h.u - h.v;
         const V3 origin = ro + rd * h.t;                                        // :114

@@ -240,4 +240,53 @@ int rgh_gather_instances(const uint32_t* models, uint32_t nModels, const int32_t
     });
 }
 
+
+// ---- ui::TextGenerator::layout without a font file: widths128[c] > 0 marks the code points that have a glyph.  out_xy receives the
+// aligned glyph positions (anchor + pen), bounds4 = lower.xy, upper.xy.  Returns the number of glyph instances.
+int rgh_text_layout(const char* text, int align, const float* widths128, float letterPadding, float lineSpacing, float* out_xy, uint32_t cap, float* bounds4) {
+    int n = -1;
+    guarded([&] {
+        ui::Font font;
+        auto dummy = std::make_shared<render::Mesh>();
+        for(size_t k = 0; k < 128; ++k) { font.charWidth[k] = widths128[k]; if(widths128[k] > 0.0f) font.charMap[k] = dummy; }
+        ui::TextGenerator gen(font, nullptr, nullptr, letterPadding, lineSpacing);
+        auto [ent, bounds] = gen.textWithBounds(text, (ui::Alignment)align);
+        uint32_t k = 0;
+        ent->forEachEntity([&](Entity& e) {
+            if(!e.model) return;
+            const Transform g = e.globalTransform();
+            if(k < cap) { out_xy[2 * k] = g.position.x; out_xy[2 * k + 1] = g.position.y; }
+            ++k;
+        });
+        if(bounds4) { bounds4[0] = bounds.lower.x; bounds4[1] = bounds.lower.y; bounds4[2] = bounds.upper.x; bounds4[3] = bounds.upper.y; }
+        n = (int)k;
+    });
+    return n;
+}
+
+// ---- render::FadeIn (kind 0) / FadeTransition (kind 1) sampled at the given times (seconds since the fade was made); rgba receives
+// 4 floats per sample, peak_index the first sample at which the transition callback fired (-1: never).
+int rgh_fade_sample(int kind, double duration, const float* color3, const double* times, uint32_t n, float* rgba, int* peak_index, int* over_flags) {
+    return guarded([&] {
+        double now = 0.0;
+        render::Clock clock = [&now] { return now; };
+        int peak = -1, cur = 0;
+        std::unique_ptr<render::Fade> f;
+        const vec3 c(color3[0], color3[1], color3[2]);
+        if(kind == 0) f = std::make_unique<render::FadeIn>(clock, duration, c);
+        else f = std::make_unique<render::FadeTransition>(clock, duration, [&] { if(peak < 0) peak = cur; }, c);
+        for(uint32_t k = 0; k < n; ++k) {
+            now = times[k]; cur = (int)k;
+            const vec4 v = f->curColor();
+            rgba[4 * k] = v.x; rgba[4 * k + 1] = v.y; rgba[4 * k + 2] = v.z; rgba[4 * k + 3] = v.w;
+            if(over_flags) over_flags[k] = f->over() ? 1 : 0;
+        }
+        if(peak_index) *peak_index = peak;
+    });
+}
+
+// ---- the frame writers that stand in for the swapchain present
+int rgh_write_image(const char* path, const uint8_t* rgba, uint32_t W, uint32_t H, int png) {
+    return guarded([&] { if(png) render::RenderSystem::writeImagePNG(path, rgba, W, H); else render::RenderSystem::writeImagePPM(path, rgba, W, H); });
+}
 }  // extern "C"

@@ -2,6 +2,9 @@
 #include "raygun_host.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -166,6 +169,7 @@ RenderSystem::RenderSystem(uint32_t width, uint32_t height, int device) : m_widt
     m_ubo.num_samples = 1;
     m_ubo.max_recursions = 5;
     m_raytracer = std::make_unique<Raytracer>(width, height, device);
+    clock = [t0 = std::chrono::steady_clock::now()] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
 }
 
 // One vertex / index buffer over the DISTINCT meshes and one material buffer over all models' material lists;
@@ -205,8 +209,13 @@ void RenderSystem::fillUniformBuffer(gpu::UniformBufferObject& ubo, const Camera
     ubo.clear_color[0] = ubo.clear_color[1] = ubo.clear_color[2] = 0.2f;
 }
 
-void RenderSystem::render(Scene& scene) {  // render_system.cpp:88-100 (then blit / ImGui / present: dropped)
+void RenderSystem::render(Scene& scene) {  // render_system.cpp:88-100 (then blit / ImGui / present: replaced by readFrame / writeFrame*)
     fillUniformBuffer(m_ubo, *scene.camera);
+    m_ubo.time = (float)std::fmod(clock(), 32.0 * 3.14159265358979323846);   // render_system.cpp:253-255
+    if(m_currentFade) {                                                      // render_system.cpp:257-259
+        const vec4 c = m_currentFade->curColor();
+        m_ubo.fade_color[0] = c.x; m_ubo.fade_color[1] = c.y; m_ubo.fade_color[2] = c.z; m_ubo.fade_color[3] = c.w;
+    }
     m_raytracer->setupTopLevelAS(scene);
     m_raytracer->updateRenderTarget(m_ubo);
     m_raytracer->doRaytracing(useFXAA);
@@ -216,6 +225,73 @@ void RenderSystem::readFrame(std::vector<uint8_t>& rgba8) {
     rgba8.resize((size_t)m_width * m_height * 4);
     check(m_raytracer->ctx, rg_read_rgba8(m_raytracer->ctx, rgba8.data()), "rg_read_rgba8");
 }
+// The reference presents the frame through the swapchain (render_system.cpp:130-159); headless, the frame goes to a file.
+void RenderSystem::writeFramePPM(const string& path) { std::vector<uint8_t> rgba; readFrame(rgba); writeImagePPM(path, rgba.data(), m_width, m_height); }
+void RenderSystem::writeFramePNG(const string& path) { std::vector<uint8_t> rgba; readFrame(rgba); writeImagePNG(path, rgba.data(), m_width, m_height); }
+void RenderSystem::writeImagePPM(const string& path, const uint8_t* rgba, uint32_t m_width, uint32_t m_height) {   // binary PPM (P6): RGB, alpha dropped
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if(!f) throw std::runtime_error("writeFramePPM: cannot open " + path);
+    std::fprintf(f, "P6\n%u %u\n255\n", m_width, m_height);
+    std::vector<uint8_t> row((size_t)m_width * 3);
+    for(uint32_t y = 0; y < m_height; ++y) {
+        for(uint32_t x = 0; x < m_width; ++x) std::memcpy(&row[3 * (size_t)x], &rgba[4 * ((size_t)y * m_width + x)], 3);
+        std::fwrite(row.data(), 1, row.size(), f);
+    }
+    std::fclose(f);
+}
+namespace {
+uint32_t crc32Update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static bool ready = false;
+    if(!ready) {
+        for(uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for(int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+        ready = true;
+    }
+    for(size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+void pngChunk(FILE* f, const char type[4], const std::vector<uint8_t>& data) {
+    const uint32_t n = (uint32_t)data.size();
+    const uint8_t len[4] = {uint8_t(n >> 24), uint8_t(n >> 16), uint8_t(n >> 8), uint8_t(n)};
+    std::fwrite(len, 1, 4, f);
+    std::fwrite(type, 1, 4, f);
+    if(n) std::fwrite(data.data(), 1, n, f);
+    uint32_t crc = crc32Update(0xffffffffu, reinterpret_cast<const uint8_t*>(type), 4);
+    crc = crc32Update(crc, data.data(), n) ^ 0xffffffffu;
+    const uint8_t c[4] = {uint8_t(crc >> 24), uint8_t(crc >> 16), uint8_t(crc >> 8), uint8_t(crc)};
+    std::fwrite(c, 1, 4, f);
+}
+}  // namespace
+void RenderSystem::writeImagePNG(const string& path, const uint8_t* rgba, uint32_t m_width, uint32_t m_height) {   // 8-bit RGBA, stored (uncompressed) deflate blocks: no zlib needed
+    std::vector<uint8_t> raw;
+    raw.reserve(((size_t)m_width * 4 + 1) * m_height);
+    for(uint32_t y = 0; y < m_height; ++y) {
+        raw.push_back(0);   // filter type none
+        raw.insert(raw.end(), rgba + 4 * (size_t)y * m_width, rgba + 4 * (size_t)(y + 1) * m_width);
+    }
+    std::vector<uint8_t> z = {0x78, 0x01};
+    uint32_t a = 1, b = 0;   // Adler-32 of the raw stream
+    for(size_t off = 0; off < raw.size() || off == 0; off += 65535) {
+        const size_t n = std::min<size_t>(65535, raw.size() - off);
+        z.push_back(off + n >= raw.size() ? 1 : 0);
+        z.push_back(uint8_t(n)); z.push_back(uint8_t(n >> 8)); z.push_back(uint8_t(~n)); z.push_back(uint8_t((~n) >> 8));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        for(size_t i = 0; i < n; ++i) { a = (a + raw[off + i]) % 65521u; b = (b + a) % 65521u; }
+        if(raw.empty()) break;
+    }
+    const uint32_t adler = (b << 16) | a;
+    z.push_back(uint8_t(adler >> 24)); z.push_back(uint8_t(adler >> 16)); z.push_back(uint8_t(adler >> 8)); z.push_back(uint8_t(adler));
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if(!f) throw std::runtime_error("writeFramePNG: cannot open " + path);
+    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::fwrite(sig, 1, 8, f);
+    std::vector<uint8_t> hdr = {uint8_t(m_width >> 24), uint8_t(m_width >> 16), uint8_t(m_width >> 8), uint8_t(m_width),
+                                uint8_t(m_height >> 24), uint8_t(m_height >> 16), uint8_t(m_height >> 8), uint8_t(m_height), 8, 6, 0, 0, 0};
+    pngChunk(f, "IHDR", hdr);
+    pngChunk(f, "IDAT", z);
+    pngChunk(f, "IEND", {});
+    std::fclose(f);
+}
 rg_timings RenderSystem::timings() {
     rg_timings t{};
     check(m_raytracer->ctx, rg_get_timings(m_raytracer->ctx, &t), "rg_get_timings");
@@ -224,65 +300,97 @@ rg_timings RenderSystem::timings() {
 
 }  // namespace render
 
-// ------------------------------------------------------------------------------------------------ ui::TextGenerator (ui/text.cpp:30-138)
+// ------------------------------------------------------------------------------------------------ ui::TextGenerator
+// Text becomes ordinary ray-traced geometry: one instance per glyph (raygun/ui/text.hpp:39-66 is the interface kept; what a caller of
+// ui/text.cpp:53-138 observes is the set of glyph instances, their pen positions and the bounds).  Here the layout is ONE flat pass
+// over the string that yields glyph placements -- the form the instance upload wants (rg_entity / rg_instance records) -- and the
+// entity tree is built from that list afterwards.
 namespace ui {
 TextGenerator::TextGenerator(const Font& font, std::shared_ptr<Material> material, const RegisterModel& registerModel, float letterPadding_, float lineSpacing_)
     : m_charWidth(font.charWidth), letterPadding(letterPadding_), lineSpacing(lineSpacing_) {
-    for(size_t k = 0; k < font.charMap.size(); ++k) {
-        if(!font.charMap[k]) continue;
-        auto model = std::make_shared<render::Model>();
-        model->mesh = font.charMap[k];
-        model->materials.push_back(material);
-        if(registerModel) registerModel(model);
-        m_charMap[k] = model;
+    for(size_t code = 0; code < font.charMap.size(); ++code) {
+        if(!font.charMap[code]) continue;
+        auto glyph = std::make_shared<render::Model>();
+        glyph->mesh = font.charMap[code];
+        glyph->materials = {material};
+        if(registerModel) registerModel(glyph);
+        m_charMap[code] = std::move(glyph);
     }
 }
-std::pair<std::shared_ptr<Entity>, render::Mesh::Bounds> TextGenerator::textInternal(string_view input) const {
-    auto result = std::make_shared<Entity>("char_group_" + string(input));
-    render::Mesh::Bounds bounds{};
-    vec2 offset{};
-    for(const char c: input) {
-        if(c == ' ') {
-            offset.x += 5 * letterPadding;
-        } else if(c == '\n') {
-            offset.x = 0;
-            offset.y -= lineSpacing;
-            continue;
-        }
-        const auto code = (unsigned char)c;
-        if(code >= m_charMap.size()) continue;
-        const auto& model = m_charMap[code];
-        if(!model) continue;
-        auto entity = result->emplaceChild(std::to_string((int)c));
-        entity->move({offset.x, offset.y, 0.0f});
-        entity->model = model;
-        offset.x += letterPadding + m_charWidth[code];
-        bounds.upper.x = offset.x - letterPadding;
-        bounds.upper.y = offset.y + lineSpacing * 0.66f;
+
+// Layout rules (numerically those of the reference, so that glyph instances land on the same binary32 positions):
+//   pen starts at (0, 0); a glyph is placed at the pen, then the pen advances by letterPadding + its width;
+//   ' ' advances the pen by 5 letterPaddings and places nothing; a line feed returns the pen to x = 0, one lineSpacing down;
+//   code points without a glyph are skipped; the extent is (pen.x - letterPadding, pen.y + 0.66 lineSpacing) after the LAST glyph.
+TextGenerator::Layout TextGenerator::layout(string_view input) const {
+    Layout out;
+    float penX = 0.0f, penY = 0.0f;
+    for(const char ch: input) {
+        const auto code = (unsigned char)ch;
+        if(ch == '\n') { penX = 0.0f; penY -= lineSpacing; continue; }
+        if(ch == ' ') penX += 5 * letterPadding;
+        if(code >= m_charMap.size() || !m_charMap[code]) continue;
+        out.glyphs.push_back({code, penX, penY});
+        penX += letterPadding + m_charWidth[code];
+        out.extent = vec2{penX - letterPadding, penY + lineSpacing * 0.66f};
     }
-    return {result, bounds};
+    return out;
 }
+
+// Alignment = (row, column) of a 3 x 3 anchor grid: the block moves left by 0, 1/2 or 1 extent and down by 0, 1/2 or 1 extent.
+vec3 TextGenerator::anchorOffset(Alignment align, vec2 extent) {
+    const int column = (int)align % 3, row = (int)align / 3;
+    const float dx = column == 0 ? 0.0f : (column == 1 ? -extent.x / 2 : -extent.x);
+    const float dy = row == 0 ? 0.0f : (row == 1 ? -extent.y / 2 : -extent.y);
+    return vec3(dx, dy, 0.0f);
+}
+
 std::pair<std::shared_ptr<Entity>, render::Mesh::Bounds> TextGenerator::textWithBounds(string_view input, Alignment align) const {
-    auto [textEnt, bounds] = textInternal(input);
-    vec3 offset(0.0f);
-    switch(align) {
-    case Alignment::TopLeft: break;
-    case Alignment::TopCenter: offset = vec3(-bounds.upper.x / 2, 0, 0); break;
-    case Alignment::TopRight: offset = vec3(-bounds.upper.x, 0, 0); break;
-    case Alignment::MiddleLeft: offset = vec3(0, -bounds.upper.y / 2, 0); break;
-    case Alignment::MiddleCenter: offset = vec3(-bounds.upper.x / 2, -bounds.upper.y / 2, 0); break;
-    case Alignment::MiddleRight: offset = vec3(-bounds.upper.x, -bounds.upper.y / 2, 0); break;
-    case Alignment::BottomLeft: offset = vec3(0, -bounds.upper.y, 0); break;
-    case Alignment::BottomCenter: offset = vec3(-bounds.upper.x / 2, -bounds.upper.y, 0); break;
-    case Alignment::BottomRight: offset = vec3(-bounds.upper.x, -bounds.upper.y, 0); break;
+    const Layout placed = layout(input);
+    const vec3 anchor = anchorOffset(align, placed.extent);
+    // two levels, as callers of the reference see them: the returned entity is free to be moved by the caller, its single child
+    // carries the anchor offset and the glyph instances hang below it (global position = (caller + anchor) + pen, in this order)
+    auto block = std::make_shared<Entity>("text:" + string(input));
+    auto line = block->emplaceChild("glyphs");
+    line->moveTo(anchor);
+    for(const Placement& g: placed.glyphs) {
+        auto e = line->emplaceChild(string(1, (char)g.code));
+        e->moveTo({g.x, g.y, 0.0f});
+        e->model = m_charMap[g.code];
     }
-    textEnt->moveTo(offset);
-    bounds.upper += offset;
-    bounds.lower += offset;
-    auto result = std::make_shared<Entity>("string_" + string(input));
-    result->addChild(textEnt);
-    return {result, bounds};
+    render::Mesh::Bounds bounds{};
+    bounds.lower = anchor;
+    bounds.upper = vec3(placed.extent.x, placed.extent.y, 0.0f) + anchor;
+    return {block, bounds};
 }
 }  // namespace ui
+
+// ------------------------------------------------------------------------------------------------ render::Fade (fade.hpp:27-63)
+namespace render {
+// alpha envelopes over progress = elapsed / duration (fade.cpp:47-52, :71-88)
+vec4 Fade::curColor() { return vec4{0.0f, 0.0f, 0.0f, 0.0f}; }
+bool Fade::over() const { return true; }
+
+FadeIn::FadeIn(const Clock& clock, double duration, vec3 fromColor) : Fade(clock), m_duration(duration), m_color(fromColor) {}
+vec4 FadeIn::curColor() {
+    const double progress = std::clamp(elapsed() / m_duration, 0.0, 1.0);
+    return vec4{m_color.x, m_color.y, m_color.z, float(1 - progress)};
+}
+bool FadeIn::over() const { return elapsed() > m_duration; }
+
+FadeTransition::FadeTransition(const Clock& clock, double halfDuration, std::function<void()> atPeak, vec3 color)
+    : Fade(clock), m_half(halfDuration), m_atPeak(std::move(atPeak)), m_color(color) {}
+vec4 FadeTransition::curColor() {
+    const double progress = elapsed() / m_half;
+    if(!m_switched) {                       // rising edge: opaque at progress 1, where the scene is switched
+        m_alpha = float(std::clamp(progress, 0.0, 1.0));
+        if(progress >= 1) { m_switched = true; if(m_atPeak) m_atPeak(); }
+    } else {
+        m_alpha = float(std::clamp(2 - progress, 0.0, 1.0));
+    }
+    return vec4{m_color.x, m_color.y, m_color.z, m_alpha};
+}
+bool FadeTransition::over() const { return elapsed() > 2 * m_half; }
+}  // namespace render
 
 }  // namespace raygun

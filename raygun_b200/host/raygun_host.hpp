@@ -204,8 +204,13 @@ class TextGenerator {
     std::shared_ptr<Entity> text(string_view input, Alignment align = Alignment::TopLeft) const { return textWithBounds(input, align).first; }
     std::pair<std::shared_ptr<Entity>, render::Mesh::Bounds> textWithBounds(string_view input, Alignment align = Alignment::TopLeft) const;
 
+    /// The flat form of a laid-out string: one record per glyph instance (pen position before alignment) + the extent of the block.
+    struct Placement { unsigned code; float x, y; };
+    struct Layout { std::vector<Placement> glyphs; vec2 extent{}; };
+    Layout layout(string_view input) const;
+    static vec3 anchorOffset(Alignment align, vec2 extent);
+
   private:
-    std::pair<std::shared_ptr<Entity>, render::Mesh::Bounds> textInternal(string_view input) const;
     std::array<std::shared_ptr<render::Model>, 128> m_charMap = {};
     std::array<float, 128> m_charWidth = {};
     float letterPadding, lineSpacing;
@@ -250,10 +255,63 @@ struct Raytracer {
     static void gatherEntities(const Scene& scene, std::vector<rg_entity>& out);
 };
 
+/// Seconds since the application started (the reference's RG().time()); injected so that a headless run can step time itself.
+using Clock = std::function<double()>;
+
+/// raygun/render/fade.hpp:27-63: a colour laid over the frame by the postprocess pass (ubo.fadeColor); alpha follows an envelope in time.
+class Fade {
+  public:
+    explicit Fade(const Clock& clock) : m_clock(clock), m_start(clock()) {}
+    virtual ~Fade() {}
+    virtual vec4 curColor();
+    virtual bool over() const;
+
+  protected:
+    double elapsed() const { return m_clock() - m_start; }
+
+  private:
+    Clock m_clock;
+    double m_start;
+};
+class FadeIn : public Fade {   // from opaque `fromColor` to the frame within `duration`
+  public:
+    FadeIn(const Clock& clock, double duration, vec3 fromColor = vec3(0.f));
+    vec4 curColor() override;
+    bool over() const override;
+
+  private:
+    double m_duration;
+    vec3 m_color;
+};
+class FadeTransition : public Fade {   // frame -> colour (callback at the peak) -> frame, `halfDuration` each way
+  public:
+    FadeTransition(const Clock& clock, double halfDuration, std::function<void()> atPeak, vec3 color = vec3(0.f));
+    vec4 curColor() override;
+    bool over() const override;
+
+  private:
+    double m_half;
+    std::function<void()> m_atPeak;
+    vec3 m_color;
+    float m_alpha = 0.0f;
+    bool m_switched = false;
+};
+
 /// Headless RenderSystem: same buffer packing and per-frame order as the reference, no swapchain / ImGui.
 class RenderSystem {
   public:
     RenderSystem(uint32_t width, uint32_t height, int device = 0);
+    /// render_system.hpp:65-71: a new fade starts only when none is running.  The clock is passed on to the fade.
+    template <typename F, typename... Args>
+    void makeFade(Args&&... args) {
+        if(!m_currentFade || m_currentFade->over()) m_currentFade = std::make_unique<F>(clock, std::forward<Args>(args)...);
+    }
+    /// time source of fades and ubo.time; default: wall clock since construction.  Set it to step time deterministically.
+    Clock clock;
+    void writeFramePPM(const string& path);   // instead of the swapchain present (render_system.cpp:159)
+    void writeFramePNG(const string& path);
+    static void writeImagePPM(const string& path, const uint8_t* rgba, uint32_t width, uint32_t height);
+    static void writeImagePNG(const string& path, const uint8_t* rgba, uint32_t width, uint32_t height);
     void setupModelBuffers(const std::vector<std::shared_ptr<Model>>& models);   // render_system.cpp:192-223, :270-330
     void render(Scene& scene);                                                   // render_system.cpp:88-162
     void readFrame(std::vector<uint8_t>& rgba8);
@@ -275,6 +333,7 @@ class RenderSystem {
     uint32_t m_width, m_height;
     gpu::UniformBufferObject m_ubo{};
     std::unique_ptr<Raytracer> m_raytracer;
+    std::unique_ptr<Fade> m_currentFade;
 };
 
 }  // namespace render

@@ -591,3 +591,54 @@ def test_resize_sample_change_and_material_edit_equal_a_fresh_context(rgmod, S, 
     edited = S.SceneData(example_scene.vertices, example_scene.indices, example_scene.meshes, mats, example_scene.inst_xform, example_scene.inst_meta)
     assert np.array_equal(rt.read_rgba8(), fresh(200, 120, 2, edited))
     rt.close()
+
+
+def test_api_guards_against_stale_state(rgmod, O, S, example_scene):
+    """Defensive behaviour of the C ABI (no reference counterpart): a resize drops the gather target (old stride), a partitioned
+    context refuses to re-allocate its images under its peers, rg_set_ubo_device validates like rg_set_ubo, and a material with
+    rayConsumption 0 (gpu_material.def documents 1..5) is clamped identically in the kernels and the oracle."""
+    import torch
+    W, H = 128, 72
+    sd = example_scene
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(sd)
+    ubo = S.example_ubo(W, H)
+    _, own = rt.gather_buffer_export()
+    rt.set_gather_target(own)
+    rt.render_frame(ubo, rgmod.RG_FXAA)
+    a = rt.read_gathered_rgba8().copy()
+    assert np.array_equal(a, rt.read_rgba8())
+    rt.resize(96, 54)                                 # frees the gather buffer; the stale target must not be written
+    ubo2 = S.example_ubo(96, 54)
+    rt.render_frame(ubo2, rgmod.RG_FXAA)
+    rt.sync()
+    _, own = rt.gather_buffer_export()
+    rt.set_gather_target(own)
+    rt.render_frame(ubo2, rgmod.RG_FXAA)
+    assert np.array_equal(rt.read_gathered_rgba8(), rt.read_rgba8())
+    # device-side UBO with numSamples 0: rejected, the previous block stays in force
+    bad = ubo2.copy(); bad[35] = 0
+    d_bad = torch.from_numpy(bad.view(np.int32).copy()).cuda(); torch.cuda.synchronize()
+    with pytest.raises(rgmod.RaygunError):
+        rt.set_ubo_device(d_bad.data_ptr())
+    before = rt.read_rgba8().copy()
+    rt.doRaytracing(rgmod.RG_FXAA)
+    assert np.array_equal(rt.read_rgba8(), before)
+    # partitioned contexts must leave the mode before their images move
+    rt.set_partition(0, 2)
+    with pytest.raises(rgmod.RaygunError):
+        rt.set_region(0, 0, 48, 54)
+    with pytest.raises(rgmod.RaygunError):
+        rt.resize(64, 36)
+    rt.set_partition(0, 1)
+    rt.set_region(0, 0, 48, 54)
+    rt.close()
+    # rayConsumption 0 on every material
+    mats = sd.materials.copy()
+    mats[:, 11] = 0
+    sd0 = S.SceneData(sd.vertices, sd.indices, sd.meshes, mats, sd.inst_xform, sd.inst_meta)
+    rt = rgmod.Raytracer(W, H)
+    rt.load_scene(sd0)
+    rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
+    _check_frame(rt, O.OracleScene(sd0).render(ubo, W, H, O.FXAA), rgmod, "rayConsumption 0")
+    rt.close()

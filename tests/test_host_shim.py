@@ -158,6 +158,99 @@ def test_text_layout_matches_text_generator_rules(host):
         assert px.min() == 0.0 and abs(px.max() - widths[ord(c)]) < 1e-6
 
 
+def test_font_snapshot_against_independent_known_answers():
+    """The glyph meshes and widths of the committed text snapshot against tests/golden/font_known_answers.json, which
+    tools/font_known_answers.py computes from the reference's NotoSans.obj with its own numpy reader (NOT with the C++ loader):
+    corner count, binary32 width and the CRC32 of the shifted positions of every glyph the text uses."""
+    import json, zlib
+    z = np.load(os.path.join(ROOT, "tests", "golden", "text_scene.npz"))
+    ka = json.load(open(os.path.join(ROOT, "tests", "golden", "font_known_answers.json")))["glyphs"]
+    assert len(ka) == 124
+    text = bytes(z["text"]).decode()
+    widths = z["widths"]                               # uint32 view of the 128 floats
+    for code in range(128):
+        want = ka.get(str(code))
+        assert int(widths[code]) == (want["width_bits"] if want else 0), code
+    inst, v = z["instances"], z["vertices"]
+    glyphs = [c for c in text if c not in " \n"]
+    for k, c in enumerate(glyphs):
+        m = z["meshes"][inst[k, 12]]
+        pos = np.ascontiguousarray(v[m[0]:m[0] + m[1], 0:3])
+        want = ka[str(ord(c))]
+        assert m[1] == want["corners"] and m[3] == want["corners"], c        # one vertex per face corner, indices 0..n-1
+        assert zlib.crc32(pos.tobytes()) == want["crc32_positions"], c
+
+
+@pytest.mark.parametrize("align", range(9))
+def test_text_layout_rules_with_synthetic_widths(host, align):
+    """ui::TextGenerator over a synthetic font (no files): pen advance, space, line feed, glyph-less code points, the extent after the
+    last glyph and the nine anchor offsets, against a numpy restatement of the rules of ui/text.cpp:53-138 in binary32."""
+    rng = np.random.default_rng(align)
+    widths = np.zeros(128, np.float32)
+    for c in "abcdefgXYZ019.,":
+        widths[ord(c)] = np.float32(rng.uniform(0.2, 0.9))
+    text = "ab c\nXYZ  0q9\n\n.,d"                     # 'q' has no glyph
+    pad, line = np.float32(0.13), np.float32(1.25)
+    out = np.zeros((64, 2), np.float32); b = np.zeros(4, np.float32)
+    n = host.rgh_text_layout(text.encode(), align, _p(widths), C.c_float(pad), C.c_float(line), _p(out), 64, _p(b))
+    x = y = ux = uy = np.float32(0); pens = []
+    for ch in text:
+        if ch == "\n":
+            x = np.float32(0); y = np.float32(y - line); continue
+        if ch == " ":
+            x = np.float32(x + np.float32(5) * pad)
+        if widths[ord(ch)] == 0:
+            continue
+        pens.append((x, y))
+        x = np.float32(x + np.float32(pad + widths[ord(ch)]))
+        ux, uy = np.float32(x - pad), np.float32(y + np.float32(line * np.float32(0.66)))
+    col, row = align % 3, align // 3
+    ax = np.float32(0) if col == 0 else (np.float32(-ux / 2) if col == 1 else np.float32(-ux))
+    ay = np.float32(0) if row == 0 else (np.float32(-uy / 2) if row == 1 else np.float32(-uy))
+    assert n == len(pens) == 11
+    want = np.array([(np.float32(ax + px), np.float32(ay + py)) for px, py in pens], np.float32)
+    assert np.array_equal(out[:n], want)
+    assert np.array_equal(b, np.array([ax, ay, np.float32(ux + ax), np.float32(uy + ay)], np.float32))
+
+
+def test_fade_envelopes(host):
+    """render::FadeIn / FadeTransition (raygun/render/fade.cpp:44-95): alpha over time, callback exactly once at the peak, over()."""
+    t = np.array([0.0, 0.25, 0.5, 1.0, 1.5, 2.0, 2.5], np.float64)
+    col = np.array([0.2, 0.4, 0.6], np.float32)
+    rgba = np.zeros((len(t), 4), np.float32); over = np.zeros(len(t), np.int32); peak = C.c_int(-2)
+    assert host.rgh_fade_sample(0, C.c_double(1.0), _p(col), _p(t), len(t), _p(rgba), C.byref(peak), _p(over)) == 0
+    assert np.allclose(rgba[:, :3], col) and np.allclose(rgba[:, 3], [1, 0.75, 0.5, 0, 0, 0, 0])
+    assert list(over) == [0, 0, 0, 0, 1, 1, 1] and peak.value == -1
+    assert host.rgh_fade_sample(1, C.c_double(1.0), _p(col), _p(t), len(t), _p(rgba), C.byref(peak), _p(over)) == 0
+    assert np.allclose(rgba[:, 3], [0, 0.25, 0.5, 1.0, 0.5, 0, 0])
+    assert peak.value == 3 and list(over) == [0, 0, 0, 0, 0, 0, 1]
+
+
+def test_frame_writers_ppm_and_png(host, tmp_path):
+    """The headless stand-in for the swapchain present (render_system.cpp:159): binary PPM and stored-deflate PNG, read back here."""
+    import struct, zlib
+    W, H = 37, 11
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    ppm, png = str(tmp_path / "f.ppm"), str(tmp_path / "f.png")
+    assert host.rgh_write_image(ppm.encode(), _p(img), W, H, 0) == 0
+    assert host.rgh_write_image(png.encode(), _p(img), W, H, 1) == 0
+    raw = open(ppm, "rb").read()
+    head = f"P6\n{W} {H}\n255\n".encode()
+    assert raw.startswith(head) and np.array_equal(np.frombuffer(raw[len(head):], np.uint8).reshape(H, W, 3), img[..., :3])
+    d = open(png, "rb").read()
+    assert d[:8] == b"\x89PNG\r\n\x1a\n"
+    off, chunks = 8, {}
+    while off < len(d):
+        n, typ = struct.unpack(">I4s", d[off:off + 8])
+        body = d[off + 8:off + 8 + n]
+        assert struct.unpack(">I", d[off + 8 + n:off + 12 + n])[0] == zlib.crc32(typ + body)
+        chunks[typ] = body; off += 12 + n
+    assert struct.unpack(">IIBBBBB", chunks[b"IHDR"]) == (W, H, 8, 6, 0, 0, 0)
+    rows = np.frombuffer(zlib.decompress(chunks[b"IDAT"]), np.uint8).reshape(H, 1 + 4 * W)
+    assert np.all(rows[:, 0] == 0) and np.array_equal(rows[:, 1:].reshape(H, W, 4), img)
+
+
 @pytest.mark.skipif(not os.path.isdir(REF_RES), reason="reference resources not present (GPU box)")
 def test_font_loader_reproduces_the_snapshot(host):
     sys_path = os.path.join(ROOT, "tools")
