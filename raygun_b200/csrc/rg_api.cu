@@ -68,7 +68,7 @@ struct rg_ctx {
     void* dMaterials = nullptr; uint32_t nMaterials = 0;
     std::vector<MeshBlas> meshes;
     Node8* blasNodes = nullptr; Tri* tris = nullptr; uint32_t nodeCap = 0, triCap = 0, nodesUsed = 0, trisUsed = 0;
-    float* dMeshBoxes = nullptr;
+    float* dMeshBoxes = nullptr; float4* dMeshSpheres = nullptr;
 
     rg_instance* dInstRaw = nullptr; InstTrav* dInstTrav = nullptr; InstShade* dInstShade = nullptr; uint32_t* dMeshRoots = nullptr;
     uint32_t instCap = 0, nInst = 0;
@@ -236,7 +236,7 @@ bool chooseScheduler(rg_ctx* c, uint32_t flags) {
 }
 
 void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
-    p.tlasNodes = c->tlasNodes; p.tlasLeaves = c->tlasLeaves; p.blasNodes = c->blasNodes; p.tris = c->tris; p.instShade = c->dInstShade;
+    p.tlasNodes = c->tlasNodes; p.tlasLeaves = c->tlasLeaves; p.blasNodes = c->blasNodes; p.tris = c->tris; p.instShade = c->dInstShade; p.meshSpheres = c->dMeshSpheres;
     p.vertices = (const float4*)c->dVertices; p.indices = c->dIndices; p.materials = (const float4*)c->dMaterials; p.ubo = c->dUbo;
     p.nInst = c->nInst; p.W = c->W; p.H = c->H;
     p.rank = c->rank; p.world = c->world;
@@ -357,7 +357,7 @@ void rg_destroy(rg_ctx* ctx) {
     cudaFree(ctx->arriveTrace); cudaFree(ctx->arrivePost); cudaFree(ctx->dSyncErr); cudaFree(ctx->dPeerTraceFlags); cudaFree(ctx->dPeerPostFlags);
     cudaFree(ctx->sampleScratch); cudaFree(ctx->sampleDone); cudaFree(ctx->tileOrder); cudaFree(ctx->tileCost);
     cudaFree(ctx->gatherOwn); cudaFree(ctx->flushBuf);
-    cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes);
+    cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes); cudaFree(ctx->dMeshSpheres);
     cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->dMeshRoots); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
     cudaFree(ctx->dUbo); cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->ctxPool);
     cudaFree(ctx->dEntities); cudaFree(ctx->dEntTmp); cudaFree(ctx->dEntEmit); cudaFree(ctx->dEntCount);
@@ -419,8 +419,9 @@ int rg_upload_geometry(rg_ctx* ctx, const rg_vertex* vertices, uint32_t n_vertic
     for(uint32_t m = 0; m < n_meshes; ++m) ctx->meshes[m].range = meshes[m];
     ctx->nodesUsed = ctx->trisUsed = 0;
     ctx->haveAs = false; ctx->blasBuilt = false;
-    cudaFree(ctx->dMeshBoxes); cudaFree(ctx->dMeshRoots); ctx->dMeshBoxes = nullptr; ctx->dMeshRoots = nullptr;
+    cudaFree(ctx->dMeshBoxes); cudaFree(ctx->dMeshRoots); cudaFree(ctx->dMeshSpheres); ctx->dMeshBoxes = nullptr; ctx->dMeshRoots = nullptr; ctx->dMeshSpheres = nullptr;
     CK(cudaMalloc(&ctx->dMeshBoxes, sizeof(float) * 6 * ((size_t)n_meshes + 1)));
+    CK(cudaMalloc(&ctx->dMeshSpheres, sizeof(float4) * ((size_t)n_meshes + 1)));
     CK(cudaMalloc(&ctx->dMeshRoots, sizeof(uint32_t) * ((size_t)n_meshes + 1)));
     return 0;
 }
@@ -465,7 +466,7 @@ int rg_build_blas(rg_ctx* ctx) {
             mb.nodeOffset = ctx->nodesUsed; mb.triOffset = ctx->trisUsed;
             TriSource src{ctx->dVertices, ctx->dIndices, mb.range.vtx_off, mb.range.idx_off, mb.range.idx_cnt / 3};
             const uint64_t before = mb.scratch.launches;
-            buildBlas(mb.scratch, src, ctx->blasNodes, mb.nodeOffset, ctx->tris, mb.triOffset, &mb.nNodes, &mb.nTris, ctx->dMeshBoxes + 6 * m, ctx->stream);
+            buildBlas(mb.scratch, src, ctx->blasNodes, mb.nodeOffset, ctx->tris, mb.triOffset, &mb.nNodes, &mb.nTris, ctx->dMeshBoxes + 6 * m, ctx->dMeshSpheres + m, ctx->stream);
             ctx->launches += mb.scratch.launches - before;
             ctx->nodesUsed += mb.nNodes; ctx->trisUsed += mb.nTris;
             mb.built = true;
@@ -489,7 +490,7 @@ static int refitBlasCommon(rg_ctx* ctx, uint32_t mesh, const rg_vertex* new_vert
     TriSource src{ctx->dVertices, ctx->dIndices, mb.range.vtx_off, mb.range.idx_off, mb.range.idx_cnt / 3};
     const uint64_t before = mb.scratch.launches;
     CK(cudaEventRecord(ctx->ev[EV_AS0], ctx->stream));
-    refitBlas(mb.scratch, src, ctx->blasNodes, mb.nodeOffset, mb.nNodes, ctx->tris, mb.triOffset, ctx->dMeshBoxes + 6 * mesh, ctx->stream);
+    refitBlas(mb.scratch, src, ctx->blasNodes, mb.nodeOffset, mb.nNodes, ctx->tris, mb.triOffset, ctx->dMeshBoxes + 6 * mesh, ctx->dMeshSpheres + mesh, ctx->stream);
     CK(cudaEventRecord(ctx->ev[EV_AS1], ctx->stream));
     ctx->launches += mb.scratch.launches - before;
     CK(cudaGetLastError());

@@ -549,7 +549,7 @@ __device__ __forceinline__ void d_prepare_instance(uint32_t i, const rg_instance
     t.instId = i;
     // pure translation: the traversal keeps the ray direction and everything derived from it (bit-identical to the general path)
     t.pad0 = (m[0] == 1.0f && m[1] == 0.0f && m[2] == 0.0f && m[4] == 0.0f && m[5] == 1.0f && m[6] == 0.0f && m[8] == 0.0f && m[9] == 0.0f && m[10] == 1.0f) ? 1u : 0u;
-    t.pad1 = 0;
+    t.pad1 = in.mesh < nMeshes ? in.mesh : 0u;   // index into the per-mesh bounding spheres
     trav[i] = t;
     InstShade s;
     for(int j = 0; j < 12; ++j) s.o2w[j] = m[j];
@@ -659,6 +659,39 @@ __global__ void k_requantize(uint32_t nWide, Node8* __restrict__ nodes, uint32_t
     (void)primOffset;
 }
 
+// Bounding sphere of a mesh around the centre of its box: r^2 = max |v - c|^2 over the vertices its triangles use.  The traversal tests a
+// ray against it before it enters an instance of the mesh (rg_trace.cu travPrim): for round meshes the sphere is half the volume of
+// the box the TLAS knows, and an avoided entry saves the ray transform, the set-up and the BLAS root visit.
+__global__ void k_mesh_sphere_reduce(const float4* __restrict__ vertices, const uint32_t* __restrict__ indices, uint32_t vtxOff, uint32_t idxOff, uint32_t nTri,
+                                     const int32_t* __restrict__ sceneBox, uint32_t* maxBits) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const float cx = 0.5f * (decodeFloat(sceneBox[0]) + decodeFloat(sceneBox[3])), cy = 0.5f * (decodeFloat(sceneBox[1]) + decodeFloat(sceneBox[4])),
+                cz = 0.5f * (decodeFloat(sceneBox[2]) + decodeFloat(sceneBox[5]));
+    float d2 = 0.0f;
+    if(p < nTri) {
+#pragma unroll
+        for(int k = 0; k < 3; ++k) {
+            const float4 v = vertices[2 * (size_t)(vtxOff + indices[idxOff + 3 * p + k])];
+            const float dx = v.x - cx, dy = v.y - cy, dz = v.z - cz;
+            d2 = fmaxf(d2, dx * dx + dy * dy + dz * dz);
+        }
+    }
+#pragma unroll
+    for(int o = 16; o; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    if((threadIdx.x & 31) == 0) atomicMax(maxBits, __float_as_uint(d2));   // non-negative floats order like their bit patterns
+}
+__global__ void k_mesh_sphere_store(const int32_t* sceneBox, const uint32_t* maxBits, uint32_t n, float4* out) {
+    if(threadIdx.x != 0) return;
+    if(n == 0) { *out = make_float4(0.0f, 0.0f, 0.0f, FLT_MAX); return; }
+    const float lx = decodeFloat(sceneBox[0]), ly = decodeFloat(sceneBox[1]), lz = decodeFloat(sceneBox[2]);
+    const float hx = decodeFloat(sceneBox[3]), hy = decodeFloat(sceneBox[4]), hz = decodeFloat(sceneBox[5]);
+    const float r2 = __uint_as_float(*maxBits) * 1.0001f + FLT_MIN;   // rounding of the distances above
+    const float r = sqrtf(r2);
+    const float vSphere = 4.18879f * r * r2, vBox = (hx - lx) * (hy - ly) * (hz - lz);
+    // only worth a test where it can reject what the box lets through: w = FLT_MAX switches it off (flat and boxy meshes)
+    *out = make_float4(0.5f * (lx + hx), 0.5f * (ly + hy), 0.5f * (lz + hz), vSphere < 0.8f * vBox ? r2 : FLT_MAX);
+}
+
 __global__ void k_store_root_box(const int32_t* sceneBox, float* out, uint32_t n) {
     if(threadIdx.x < 6) {
         if(n == 0) out[threadIdx.x] = threadIdx.x < 3 ? 1.0f : -1.0f;  // empty: inverted
@@ -750,16 +783,27 @@ void lbvhCommon(LbvhScratch& s, uint32_t n, cudaStream_t st) {
 }
 }  // namespace
 
+namespace {
+void meshSphere(LbvhScratch& s, const TriSource& src, float4* sphereOut, cudaStream_t st) {   // after k_tri_boxes filled s.sceneBox
+    if(!sphereOut) return;
+    RG_CUDA_OK(cudaMemsetAsync(&s.counters[12], 0, sizeof(uint32_t), st));
+    if(src.nTri) k_mesh_sphere_reduce<<<cdiv(src.nTri, 256), 256, 0, st>>>((const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, src.nTri, s.sceneBox, &s.counters[12]);
+    k_mesh_sphere_store<<<1, 32, 0, st>>>(s.sceneBox, &s.counters[12], src.nTri, sphereOut);
+    s.launches += 2;
+}
+}  // namespace
+
 void buildBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t nodeOffset, Tri* trisBase, uint32_t triOffset, uint32_t* nNodes,
-               uint32_t* nTris, float* rootBoxOut, cudaStream_t st) {
+               uint32_t* nTris, float* rootBoxOut, float4* sphereOut, cudaStream_t st) {
     const uint32_t n = src.nTri;
     *nNodes = 0; *nTris = 0;
     s.reserve(n ? n : 1);
     k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters);
     s.launches++;
-    if(n == 0) { k_store_root_box<<<1, 32, 0, st>>>(s.sceneBox, rootBoxOut, 0); s.launches++; RG_CUDA_OK(cudaStreamSynchronize(st)); return; }
+    if(n == 0) { k_store_root_box<<<1, 32, 0, st>>>(s.sceneBox, rootBoxOut, 0); s.launches++; meshSphere(s, src, sphereOut, st); RG_CUDA_OK(cudaStreamSynchronize(st)); return; }
     k_tri_boxes<<<cdiv(n, 256), 256, 0, st>>>((const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, n, s.primBox, s.sceneBox);
     s.launches++;
+    meshSphere(s, src, sphereOut, st);
     lbvhCommon(s, n, st);
     LeafSourceTri ls{(const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, trisBase};
     collapseHostDriven(s, n, nodesBase, nodeOffset, triOffset, ls, nNodes, nTris, st);
@@ -769,12 +813,13 @@ void buildBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t 
 }
 
 void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t nodeOffset, uint32_t nNodes, Tri* trisBase, uint32_t triOffset,
-               float* rootBoxOut, cudaStream_t st) {
+               float* rootBoxOut, float4* sphereOut, cudaStream_t st) {
     const uint32_t n = src.nTri;
     if(n == 0) return;
     k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters + 4);  // keep queue / node counters; counters+4 is scratch
     k_tri_boxes<<<cdiv(n, 256), 256, 0, st>>>((const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, n, s.primBox, s.sceneBox);
     s.launches += 2;
+    meshSphere(s, src, sphereOut, st);
     if(n >= 2) {
         k_reset_flags<<<cdiv(n - 1, 256), 256, 0, st>>>(s.flags, n - 1);
         k_refit_binary<<<cdiv(n, 128), 128, 0, st>>>(n, s.bnodes, s.primBox, s.vals[s.sortedBuf], s.parent, s.flags);

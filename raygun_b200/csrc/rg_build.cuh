@@ -36,13 +36,14 @@ struct TriSource { const void* vertices; const uint32_t* indices; uint32_t vtxOf
 
 // Builds the BLAS of one mesh.  nodesOut / trisOut point at the first free slot of the shared arrays;
 // returns the number of wide nodes / Tri records written through nNodes / nTris (host values; synchronous).
-// rootBoxOut (device, 6 floats) receives the mesh's object-space box.
+// rootBoxOut (device, 6 floats) receives the mesh's object-space box, sphereOut (device) its bounding sphere (xyz = centre, w = r^2, or
+// FLT_MAX where the sphere cannot reject anything the box lets through).
 void buildBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t nodeOffset, Tri* trisBase, uint32_t triOffset,
-               uint32_t* nNodes, uint32_t* nTris, float* rootBoxOut, cudaStream_t stream);
+               uint32_t* nNodes, uint32_t* nTris, float* rootBoxOut, float4* sphereOut, cudaStream_t stream);
 
 // Refit: vertices changed, topology kept (needs the scratch of the original build, kept per mesh).
 void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t nodeOffset, uint32_t nNodes, Tri* trisBase, uint32_t triOffset,
-               float* rootBoxOut, cudaStream_t stream);
+               float* rootBoxOut, float4* sphereOut, cudaStream_t stream);
 
 // Per-frame TLAS from the raw instance records: instance preparation (world->object, offset table), world boxes from
 // meshBoxes (device, 6 floats per mesh), LBVH, collapse.  instTrav / instShade are indexed by instance id; tlasLeavesOut

@@ -120,12 +120,14 @@ __device__ __forceinline__ float byteF(uint32_t w) {  // 1 + b / 32768 for byte 
     return __uint_as_float(__byte_perm(0x3F800000u, w, 0x3240u + (J << 4)));   // the affine map back to b is folded into the FFMA constants
 }
 
+#ifdef RG_FFMA2   // measured: no gain, the child test is bound by the ALU pipe (PRMT / FMNMX), not by the FMA pipe
 // d = a * b + c on two binary32 values at once (sm_100a FFMA2; b is broadcast): near and far plane of one axis share the multiplier
 __device__ __forceinline__ void fma2(float a0, float a1, float b, float c0, float c1, float& d0, float& d1) {
     asm("{\n\t.reg .b64 va, vb, vc, vd;\n\tmov.b64 va, {%2, %3};\n\tmov.b64 vb, {%4, %4};\n\tmov.b64 vc, {%5, %6};\n\t"
         "fma.rn.f32x2 vd, va, vb, vc;\n\tmov.b64 {%0, %1}, vd;\n\t}"
         : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
 }
+#endif
 
 // One child of a node: slab test on the quantised planes; a hit sets nibble POS of the hit mask.  J: byte of the plane words.
 template <int J, int POS>
@@ -299,8 +301,22 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* _
     T.tg = make_uint2(n1.y, hn & vm & 0x77777777u);   // primitive k of position j: bit 4 j + k
 }
 
+// True when the ray o + t d (t >= 0) certainly misses the sphere (centre sph.xyz, squared radius sph.w) that contains every triangle of
+// a mesh: the instance need not be entered.  Conservative: the discriminant B^2 - A C of |o + t d - c|^2 = r^2 carries a rounding
+// error of a few ulp of A |c - o|^2, which is given away (4e-6 A |c - o|^2), so a grazing ray always enters; closest hits are unchanged.
+__device__ __forceinline__ bool missesSphere(const float4 sph, float ox, float oy, float oz, float dx, float dy, float dz) {
+    if(!(sph.w < 3.0e38f)) return false;   // no useful sphere for this mesh (flat or boxy)
+    const float cx = sph.x - ox, cy = sph.y - oy, cz = sph.z - oz;
+    const float A = fmaf(dx, dx, fmaf(dy, dy, dz * dz)), B = fmaf(cx, dx, fmaf(cy, dy, cz * dz)), L = fmaf(cx, cx, fmaf(cy, cy, cz * cz));
+    const float C = L - sph.w;
+    if(C > 0.0f && B < 0.0f) return true;               // origin outside, centre behind the ray
+    return fmaf(B, B, -A * C) + 4.0e-6f * A * L < 0.0f;   // no real root
+}
+
 // travPrim: ONE primitive of the lane's primitive group -- a triangle test inside an instance, entering an instance in the TLAS.
-template <bool COUNT, class WR>
+// SPH: test the mesh's bounding sphere before entering an instance (pool scheduler: incoherent rays over many instances; the lanes
+// kernel leaves it out -- on the example scene the extra load and test in its hot loop cost 5 % and reject nothing)
+template <bool COUNT, bool SPH, class WR>
 __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
     RayCtx& r = T.r;
     const uint32_t bit = (uint32_t)(__ffs(T.tg.y) - 1);
@@ -315,13 +331,16 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
             const float ox = wray.ox(), oy = wray.oy(), oz = wray.oz();
             bool enter = true, shear;
             float sdx = wray.dx(), sdy = wray.dy(), sdz = wray.dz();   // direction inside the instance
+            const float4 sph = SPH ? __ldg(P.meshSpheres + l3.w) : make_float4(0.0f, 0.0f, 0.0f, 3.4e38f);   // the mesh's bounding sphere in object space (w = r^2)
             if(l3.z) {
                 // pure translation (flagged by the instance preparation): the direction and everything derived from it stay;
                 // the oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t
+                const float tox = __fadd_rn(ox, __uint_as_float(l0.w)), toy = __fadd_rn(oy, __uint_as_float(l1.w)), toz = __fadd_rn(oz, __uint_as_float(l2.w));
+                if(SPH && missesSphere(sph, tox, toy, toz, sdx, sdy, sdz)) return;
                 if(T.tg.y) stack[T.sp++] = T.tg;
                 if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
                 stack[T.sp++] = make_uint2(kInvalid, 0x1000u);
-                r.ox = __fadd_rn(ox, __uint_as_float(l0.w)); r.oy = __fadd_rn(oy, __uint_as_float(l1.w)); r.oz = __fadd_rn(oz, __uint_as_float(l2.w));
+                r.ox = tox; r.oy = toy; r.oz = toz;
                 shear = r.kz == kNoShear;   // first instance of this ray
             } else {
                 // object-space ray: same operation order as the oracle (t is preserved, direction not normalised)
@@ -335,7 +354,7 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
                 sdy = __fadd_rn(__fadd_rn(__fmul_rn(w1[0], dx), __fmul_rn(w1[1], dy)), __fmul_rn(w1[2], dz));
                 sdz = __fadd_rn(__fadd_rn(__fmul_rn(w2[0], dx), __fmul_rn(w2[1], dy)), __fmul_rn(w2[2], dz));
                 shear = true;
-                if(sdx == 0.0f && sdy == 0.0f && sdz == 0.0f) {
+                if((sdx == 0.0f && sdy == 0.0f && sdz == 0.0f) || (SPH && missesSphere(sph, oox, ooy, ooz, sdx, sdy, sdz))) {
                     enter = false;
                 } else {
                     if(T.tg.y) stack[T.sp++] = T.tg;
@@ -394,10 +413,10 @@ __device__ __forceinline__ bool travPop(Trav& T, const uint2* __restrict__ stack
 
 // One step of the fixed order node -> primitive -> pop (a lane goes on with nodes only once its pending primitives are done);
 // true when the traversal is complete.  wray: the world-space ray given to travInit (needed when an instance is entered or left).
-template <bool COUNT, class WR>
+template <bool COUNT, bool SPH, class WR>
 __device__ __forceinline__ bool travStep(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
     if((T.ng.y & 0xff000000u) && !T.tg.y) travNode<COUNT>(P, T, stack, hit, tmin, cnt);
-    if(T.tg.y) travPrim<COUNT>(P, T, stack, hit, wray, tmin, cnt);
+    if(T.tg.y) travPrim<COUNT, SPH>(P, T, stack, hit, wray, tmin, cnt);
     if(!(T.ng.y & 0xff000000u) && !T.tg.y) return travPop(T, stack, wray);
     return false;
 }
@@ -451,7 +470,7 @@ __device__ __forceinline__ uint32_t f2h(float f) { return (uint32_t)__half_as_us
 __device__ __forceinline__ uint2 packHalf4(float x, float y, float z, float w) { return make_uint2(f2h(x) | (f2h(y) << 16), f2h(z) | (f2h(w) << 16)); }
 
 #ifndef RG_TRACE_MIN_BLOCKS
-#define RG_TRACE_MIN_BLOCKS 4
+#define RG_TRACE_MIN_BLOCKS 5   // pool kernel: 96 registers (a few spills) x 20 warps / SM; swept 3..6 in round 2: C3 56.3 / 46.5 / 45.0 / 45.9 ms
 #endif
 #ifndef RG_FETCH_THRESHOLD
 #define RG_FETCH_THRESHOLD 4     // lanes without a ray before the warp fetches from its ray queue (swept 2..16 on C3)
@@ -970,7 +989,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
             if(rayCount == 0u && nEmpty >= RG_EXIT_THRESHOLD && hitCount) break;
             if(!exhausted && freeCount >= RG_REFILL_THRESHOLD && rayCount == 0u) break;
             bool done = false;
-            if(myCtx != kNoCtx) done = travStep<COUNT>(P, T, stack, hit, WorldRayPool{&W.ray[0][myCtx]}, tmin, cntT) || ++steps > kMaxStepsPerRay;
+            if(myCtx != kNoCtx) done = travStep<COUNT, true>(P, T, stack, hit, WorldRayPool{&W.ray[0][myCtx]}, tmin, cntT) || ++steps > kMaxStepsPerRay;
             const uint32_t mDone = __ballot_sync(0xffffffffu, done);
             if(mDone) {
                 if(done) {   // park the closest hit; the lane is free for the next ray
@@ -1099,7 +1118,7 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
             Trav T;
             const WorldRayRegs wr{{ro.x, ro.y, ro.z}, {rd.x, rd.y, rd.z}, rtmax};
             travInit<true>(P, T, hit, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmax);
-            for(uint32_t steps = 0; !travStep<COUNT>(P, T, stack, hit, wr, rtmin, cntT) && steps < kMaxStepsPerRay; ++steps) {}
+            for(uint32_t steps = 0; !travStep<COUNT, false>(P, T, stack, hit, wr, rtmin, cntT) && steps < kMaxStepsPerRay; ++steps) {}
             // ---- shade: hit / miss program, then the frames that resume, up to the next traceRayEXT
             const int outcome = shadeContext<COUNT, MULTI>(P, K, hit, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
                                                            FramesLocal{frames}, pix, &s_cnt[CNT_SKY][tid], cntT);
@@ -1129,7 +1148,7 @@ __global__ void k_trace_rays(const TraceParams P, const float* __restrict__ rays
     uint32_t cnt[CNT_N];
     const WorldRayRegs wr{{q[0], q[1], q[2]}, {q[3], q[4], q[5]}, q[7]};
     travInit<true>(P, T, hit, q[0], q[1], q[2], q[3], q[4], q[5], q[7]);
-    for(uint32_t steps = 0; !travStep<false>(P, T, stack, hit, wr, q[6], cnt) && steps < kMaxStepsPerRay; ++steps) {}
+    for(uint32_t steps = 0; !travStep<false, true>(P, T, stack, hit, wr, q[6], cnt) && steps < kMaxStepsPerRay; ++steps) {}
     tuv[3 * i] = hit.t; tuv[3 * i + 1] = hit.u; tuv[3 * i + 2] = hit.v;
     instPrim[2 * i] = hit.inst; instPrim[2 * i + 1] = hit.prim;
 }

@@ -52,7 +52,8 @@ struct alignas(16) InstTrav {  // 64 B
     float w2o[12];       // world -> object, 3x4 row-major
     uint32_t blasRoot;   // absolute index of the BLAS root node; 0xffffffff = empty mesh
     uint32_t instId;     // gl_InstanceCustomIndexEXT
-    uint32_t pad0, pad1;
+    uint32_t pad0;       // 1: pure translation (the ray direction is kept)
+    uint32_t pad1;       // mesh index (bounding sphere look-up)
 };
 static_assert(sizeof(InstTrav) == 64, "InstTrav");
 
