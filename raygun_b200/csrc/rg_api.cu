@@ -174,7 +174,7 @@ int buildTlasFromRaw(rg_ctx* ctx, uint32_t n) {
     if(n) {
         const uint64_t before = ctx->tlasScratch.launches;
         buildTlas(ctx->tlasScratch, ctx->dInstRaw, n, ctx->dMeshRoots, (uint32_t)ctx->meshes.size(), ctx->dInstTrav, ctx->dInstShade, ctx->dMeshBoxes,
-                  ctx->tlasNodes, ctx->tlasLeaves, ctx->stream);
+                  ctx->dMeshSpheres, ctx->tlasNodes, ctx->tlasLeaves, ctx->stream);
         ctx->launches += ctx->tlasScratch.launches - before;
     }
     CK(cudaEventRecord(ctx->ev[EV_AS1], ctx->stream));
@@ -236,7 +236,7 @@ bool chooseScheduler(rg_ctx* c, uint32_t flags) {
 }
 
 void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
-    p.tlasNodes = c->tlasNodes; p.tlasLeaves = c->tlasLeaves; p.blasNodes = c->blasNodes; p.tris = c->tris; p.instShade = c->dInstShade; p.meshSpheres = c->dMeshSpheres;
+    p.tlasNodes = c->tlasNodes; p.tlasLeaves = c->tlasLeaves; p.blasNodes = c->blasNodes; p.tris = c->tris; p.instShade = c->dInstShade;
     p.vertices = (const float4*)c->dVertices; p.indices = c->dIndices; p.materials = (const float4*)c->dMaterials; p.ubo = c->dUbo;
     p.nInst = c->nInst; p.W = c->W; p.H = c->H;
     p.rank = c->rank; p.world = c->world;

@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(1024) k_collapse_all(uint2* queue0, uint2* que
 
 // world->object from the 3x4 (binary64, explicitly rounded operations; same formula as oracle/orc_scene.cpp invert3x4)
 __device__ __forceinline__ void d_prepare_instance(uint32_t i, const rg_instance* __restrict__ raw, uint32_t n, const uint32_t* __restrict__ meshRoots,
-                                                   uint32_t nMeshes, InstTrav* __restrict__ trav, InstShade* __restrict__ shade) {
+                                                   uint32_t nMeshes, InstTrav* __restrict__ trav, InstShade* __restrict__ shade, const float4* __restrict__ meshSpheres) {
     if(i >= n) return;
     const rg_instance in = raw[i];
     const float* m = in.xform;
@@ -549,7 +549,9 @@ __device__ __forceinline__ void d_prepare_instance(uint32_t i, const rg_instance
     t.instId = i;
     // pure translation: the traversal keeps the ray direction and everything derived from it (bit-identical to the general path)
     t.pad0 = (m[0] == 1.0f && m[1] == 0.0f && m[2] == 0.0f && m[4] == 0.0f && m[5] == 1.0f && m[6] == 0.0f && m[8] == 0.0f && m[9] == 0.0f && m[10] == 1.0f) ? 1u : 0u;
-    t.pad1 = in.mesh < nMeshes ? in.mesh : 0u;   // index into the per-mesh bounding spheres
+    t.pad1 = in.mesh < nMeshes ? in.mesh : 0u;
+    const float4 sph = (meshSpheres && in.mesh < nMeshes) ? meshSpheres[in.mesh] : make_float4(0.0f, 0.0f, 0.0f, FLT_MAX);
+    t.sphere[0] = sph.x; t.sphere[1] = sph.y; t.sphere[2] = sph.z; t.sphere[3] = sph.w;
     trav[i] = t;
     InstShade s;
     for(int j = 0; j < 12; ++j) s.o2w[j] = m[j];
@@ -557,12 +559,12 @@ __device__ __forceinline__ void d_prepare_instance(uint32_t i, const rg_instance
     shade[i] = s;
 }
 __global__ void k_prepare_instances(const rg_instance* __restrict__ raw, uint32_t n, const uint32_t* __restrict__ meshRoots, uint32_t nMeshes,
-                                    InstTrav* __restrict__ trav, InstShade* __restrict__ shade) {
-    d_prepare_instance(blockIdx.x * blockDim.x + threadIdx.x, raw, n, meshRoots, nMeshes, trav, shade);
+                                    InstTrav* __restrict__ trav, InstShade* __restrict__ shade, const float4* __restrict__ meshSpheres) {
+    d_prepare_instance(blockIdx.x * blockDim.x + threadIdx.x, raw, n, meshRoots, nMeshes, trav, shade, meshSpheres);
 }
 
 struct TlasFusedArgs {
-    const rg_instance* raw; uint32_t n; const uint32_t* meshRoots; uint32_t nMeshes; InstTrav* trav; InstShade* shade; const float* meshBoxes;
+    const rg_instance* raw; uint32_t n; const uint32_t* meshRoots; uint32_t nMeshes; InstTrav* trav; InstShade* shade; const float* meshBoxes; const float4* meshSpheres;
     Aabb* primBox; int32_t* sceneBox; uint32_t* keys0; uint32_t* vals0; uint32_t* keys1; uint32_t* vals1;
     BNode* bnodes; uint2* range; uint32_t* parent; uint32_t* flags; uint2* queue0; uint2* queue1; uint32_t* counters; uint32_t* wideRef;
     Node8* tlasNodes; InstTrav* tlasLeaves;
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(1024) k_tlas_fused(const TlasFusedArgs A) {
     const uint32_t n = A.n, tid = threadIdx.x, nt = blockDim.x;
     const uint32_t nUp = (n + 31u) & ~31u;
     if(tid < 3) A.sceneBox[tid] = 0x7fffffff; else if(tid < 6) A.sceneBox[tid] = (int)0x80000000;
-    for(uint32_t i = tid; i < n; i += nt) d_prepare_instance(i, A.raw, n, A.meshRoots, A.nMeshes, A.trav, A.shade);
+    for(uint32_t i = tid; i < n; i += nt) d_prepare_instance(i, A.raw, n, A.meshRoots, A.nMeshes, A.trav, A.shade, A.meshSpheres);
     __syncthreads();
     for(uint32_t i = tid; i < nUp; i += nt) d_inst_boxes(i, A.shade, A.meshBoxes, n, A.primBox, A.sceneBox);   // whole warps: shuffles inside
     __syncthreads();
@@ -833,19 +835,19 @@ void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t 
 }
 
 void buildTlas(LbvhScratch& s, const rg_instance* raw, uint32_t nInst, const uint32_t* meshRoots, uint32_t nMeshes, InstTrav* instTrav,
-               InstShade* instShade, const float* meshBoxes, Node8* tlasNodes, InstTrav* tlasLeavesOut, cudaStream_t st) {
+               InstShade* instShade, const float* meshBoxes, const float4* meshSpheres, Node8* tlasNodes, InstTrav* tlasLeavesOut, cudaStream_t st) {
     const uint32_t n = nInst;
     s.reserve(n ? n : 1);
     if(n == 0) { k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters); s.launches++; return; }
     if(n <= kTlasFusedMax) {   // one launch for the whole build
-        TlasFusedArgs a{raw, n, meshRoots, nMeshes, instTrav, instShade, meshBoxes, s.primBox, s.sceneBox, s.keys[0], s.vals[0], s.keys[1], s.vals[1],
+        TlasFusedArgs a{raw, n, meshRoots, nMeshes, instTrav, instShade, meshBoxes, meshSpheres, s.primBox, s.sceneBox, s.keys[0], s.vals[0], s.keys[1], s.vals[1],
                         s.bnodes, s.range, s.parent, s.flags, s.queue[0], s.queue[1], s.counters, s.wideRef, tlasNodes, tlasLeavesOut};
         k_tlas_fused<<<1, n <= 32 ? 64 : (n <= 256 ? 256 : 1024), 0, st>>>(a);
         s.launches++;
         s.sortedBuf = 1;
         return;
     }
-    k_prepare_instances<<<cdiv(n, 128), 128, 0, st>>>(raw, n, meshRoots, nMeshes, instTrav, instShade);
+    k_prepare_instances<<<cdiv(n, 128), 128, 0, st>>>(raw, n, meshRoots, nMeshes, instTrav, instShade, meshSpheres);
     k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters);
     k_inst_boxes<<<cdiv(n, 128), 128, 0, st>>>(instShade, meshBoxes, n, s.primBox, s.sceneBox);
     s.launches += 3;

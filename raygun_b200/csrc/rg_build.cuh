@@ -49,6 +49,6 @@ void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t 
 // meshBoxes (device, 6 floats per mesh), LBVH, collapse.  instTrav / instShade are indexed by instance id; tlasLeavesOut
 // receives the InstTrav records in leaf order.  One launch for n <= kTlasFusedMax; fully asynchronous for n <= kTlasSingleBlockMax.
 void buildTlas(LbvhScratch& s, const rg_instance* raw, uint32_t nInst, const uint32_t* meshRoots, uint32_t nMeshes, InstTrav* instTrav,
-               InstShade* instShade, const float* meshBoxes, Node8* tlasNodes, InstTrav* tlasLeavesOut, cudaStream_t stream);
+               InstShade* instShade, const float* meshBoxes, const float4* meshSpheres, Node8* tlasNodes, InstTrav* tlasLeavesOut, cudaStream_t stream);
 
 }  // namespace rg

@@ -324,14 +324,15 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
     const uint32_t primIdx = (T.tg.x & ~kPrimGroupBit) + bit - (bit >> 2);   // bit 4 j + k -> element 3 j + k of the group (rg_types.cuh)
     if(T.curInst == kInvalid) {
         const uint4* lp = reinterpret_cast<const uint4*>(P.tlasLeaves + primIdx);
-        const uint4 l3 = __ldg(lp + 3), l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);   // all four in flight at once
+        const uint4 l3 = __ldg(lp + 3), l0 = __ldg(lp), l1 = __ldg(lp + 1), l2 = __ldg(lp + 2);   // all in flight at once
+        const uint4 l4 = SPH ? __ldg(lp + 4) : make_uint4(0u, 0u, 0u, 0x7f7fffffu);               // the mesh's bounding sphere in object space (w = r^2)
         // instance of an empty mesh, or stack exhausted (never with sane scenes): skip
         if(l3.x != kInvalid && T.sp + 6 <= kStackSize) {
             if(COUNT) cnt[CNT_INST]++;
             const float ox = wray.ox(), oy = wray.oy(), oz = wray.oz();
             bool enter = true, shear;
             float sdx = wray.dx(), sdy = wray.dy(), sdz = wray.dz();   // direction inside the instance
-            const float4 sph = SPH ? __ldg(P.meshSpheres + l3.w) : make_float4(0.0f, 0.0f, 0.0f, 3.4e38f);   // the mesh's bounding sphere in object space (w = r^2)
+            const float4 sph = make_float4(__uint_as_float(l4.x), __uint_as_float(l4.y), __uint_as_float(l4.z), __uint_as_float(l4.w));
             if(l3.z) {
                 // pure translation (flagged by the instance preparation): the direction and everything derived from it stay;
                 // the oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t

@@ -21,7 +21,6 @@ struct TraceParams {
     const Node8* blasNodes;
     const Tri* tris;
     const InstShade* instShade;
-    const float4* meshSpheres;   // per mesh: bounding sphere (centre, r^2; FLT_MAX = no test)
     const float4* vertices;   // 2 x float4 per Vertex
     const uint32_t* indices;
     const float4* materials;  // 4 x float4 per gpu::Material

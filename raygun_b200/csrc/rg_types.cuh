@@ -7,7 +7,7 @@
 //   nodes      Node8  x 80 B   compressed 8-wide BVH nodes, 5 x 128-bit loads each; all BLASes back to back,
 //                              the per-frame TLAS in its own array
 //   tris       Tri    x 48 B   3 x float4: vertex positions re-laid out in leaf order, w0 = primitive id
-//   tlasLeaves InstTrav x 64 B world->object 3x4 + BLAS root, gathered in TLAS leaf order each frame
+//   tlasLeaves InstTrav x 80 B world->object 3x4 + BLAS root + the mesh's bounding sphere, gathered in TLAS leaf order each frame
 //   instShade  InstShade x 64 B object->world 3x4 + the offset-table entry, indexed by instance id
 #pragma once
 #include <cstdint>
@@ -48,14 +48,15 @@ struct alignas(16) Tri {  // 48 B
 };
 static_assert(sizeof(Tri) == 48, "Tri must be 3 x 16 bytes");
 
-struct alignas(16) InstTrav {  // 64 B
+struct alignas(16) InstTrav {  // 80 B = 5 x 128-bit loads, all issued at once when an instance is reached
     float w2o[12];       // world -> object, 3x4 row-major
     uint32_t blasRoot;   // absolute index of the BLAS root node; 0xffffffff = empty mesh
     uint32_t instId;     // gl_InstanceCustomIndexEXT
     uint32_t pad0;       // 1: pure translation (the ray direction is kept)
-    uint32_t pad1;       // mesh index (bounding sphere look-up)
+    uint32_t pad1;       // mesh index
+    float sphere[4];     // the mesh's bounding sphere in object space: centre, r^2 (FLT_MAX: no test) -- see k_mesh_sphere_store
 };
-static_assert(sizeof(InstTrav) == 64, "InstTrav");
+static_assert(sizeof(InstTrav) == 80, "InstTrav");
 
 struct alignas(16) InstShade {  // 64 B
     float o2w[12];  // object -> world, 3x4 row-major
