@@ -38,6 +38,8 @@ enum { EV_AS0, EV_AS1, EV_RT0, EV_RTONLY1, EV_ROUGH0, EV_ROUGH1, EV_POST1, EV_GA
 struct rg_ctx {
     int device = 0, numSms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;       // the tile order of the NEXT frame is computed here, beside the post chain
+    cudaEvent_t evTraceDone = nullptr, evOrderDone = nullptr; bool orderPending = false;
     std::string err;
     uint64_t launches = 0;
 
@@ -46,6 +48,7 @@ struct rg_ctx {
     int rx0 = 0, ry0 = 0, rw = 0, rh = 0;     // rendered rectangle (region + halo)
     uint2 *base = nullptr, *normal = nullptr, *rough = nullptr, *final_ = nullptr, *roughA = nullptr, *roughB = nullptr;
     signed char* trans = nullptr;
+    uint32_t *blurList = nullptr, *blurCount = nullptr; int blurParity = 0;   // pixels the blur passes write (rg_post.cu)
     uint32_t *rgba8 = nullptr, *idInst = nullptr, *idPrim = nullptr;
     uint2* fxaaOut = nullptr;          // FXAA target (the reference writes baseImage and swaps; pointers stay put here so peers can keep them)
     bool lastFxaa = false;
@@ -77,7 +80,7 @@ struct rg_ctx {
     rg_instance* hInstPinned = nullptr; uint32_t hInstCap = 0;
 
     float* dUbo = nullptr; rg_ubo hUbo{}; rg_ubo* hUboPinned = nullptr; bool uboOnDevice = false;
-    uint32_t* dWork = nullptr; unsigned long long* dCounters = nullptr; float4* ctxPool = nullptr;
+    unsigned long long* dCounters = nullptr; float4* ctxPool = nullptr;
     rg_entity* dEntities = nullptr; rg_instance* dEntTmp = nullptr; uint32_t* dEntEmit = nullptr; uint32_t* dEntCount = nullptr; uint32_t entCap = 0;
     // trace scheduler (rg_trace.cu: k_trace_lanes / k_trace_pool).  RG_SCHED_AUTO times both on consecutive frames and keeps the
     // faster one; the comparison is repeated every kSchedReprobe frames so a changing scene can change the choice.
@@ -89,7 +92,7 @@ struct rg_ctx {
     uint32_t lastFlags = 0;
     void* flushBuf = nullptr;
     float lastRaysMs = 0.0f;
-    bool debugPostOnly = false, frameCostsValid = false;
+    bool debugPostOnly = false;
 };
 
 namespace {
@@ -107,6 +110,7 @@ void freeImages(rg_ctx* c) {
     cudaFree(c->base); cudaFree(c->normal); cudaFree(c->rough); cudaFree(c->final_); cudaFree(c->roughA); cudaFree(c->roughB); cudaFree(c->trans);
     cudaFree(c->fxaaOut); c->fxaaOut = nullptr;
     cudaFree(c->rgba8); cudaFree(c->idInst); cudaFree(c->idPrim);
+    cudaFree(c->blurList); cudaFree(c->blurCount); c->blurList = c->blurCount = nullptr;
     c->base = c->normal = c->rough = c->final_ = c->roughA = c->roughB = nullptr; c->trans = nullptr; c->rgba8 = c->idInst = c->idPrim = nullptr;
 }
 
@@ -121,6 +125,7 @@ int allocImages(rg_ctx* ctx) {
     uint2** imgs[7] = {&ctx->base, &ctx->normal, &ctx->rough, &ctx->final_, &ctx->roughA, &ctx->roughB, &ctx->fxaaOut};
     for(auto p: imgs) { CK(cudaMalloc(p, n * sizeof(uint2))); CK(cudaMemsetAsync(*p, 0, n * sizeof(uint2), ctx->stream)); }
     CK(cudaMalloc(&ctx->trans, n)); CK(cudaMemsetAsync(ctx->trans, 0, n, ctx->stream));
+    CK(cudaMalloc(&ctx->blurList, n * 4)); CK(cudaMalloc(&ctx->blurCount, 8)); CK(cudaMemsetAsync(ctx->blurCount, 0, 8, ctx->stream)); ctx->blurParity = 0;
     CK(cudaMalloc(&ctx->idInst, n * 4)); CK(cudaMalloc(&ctx->idPrim, n * 4));
     CK(cudaMemsetAsync(ctx->idInst, 0xff, n * 4, ctx->stream)); CK(cudaMemsetAsync(ctx->idPrim, 0xff, n * 4, ctx->stream));
     const size_t ni = (size_t)(ctx->ix1 - ctx->ix0) * (ctx->iy1 - ctx->iy0);
@@ -188,10 +193,10 @@ int ensureSchedule(rg_ctx* ctx) {
     const bool part = ctx->world > 1;
     const uint32_t dw = part ? ctx->W : (uint32_t)ctx->rw, dh = part ? ctx->H : (uint32_t)ctx->rh;
     const uint32_t slots = traceShareTiles(dw, dh, ctx->rank, ctx->world);
-    const uint32_t S = (uint32_t)ctx->hUbo.num_samples;
     const uint64_t key = ((uint64_t)dw << 40) ^ ((uint64_t)dh << 20) ^ ((uint64_t)ctx->rank << 8) ^ ctx->world ^ ((uint64_t)ctx->rx0 << 50) ^ ((uint64_t)ctx->ry0 << 12);
     if(slots != ctx->schedSlots || key != ctx->schedKey) {
         CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->side)); ctx->orderPending = false;
         cudaFree(ctx->sampleDone); cudaFree(ctx->tileOrder); cudaFree(ctx->tileCost);
         ctx->sampleDone = ctx->tileOrder = ctx->tileCost = nullptr;
         CK(cudaMalloc(&ctx->sampleDone, 4 * (size_t)(slots ? slots : 1) * 32));
@@ -199,9 +204,16 @@ int ensureSchedule(rg_ctx* ctx) {
         CK(cudaMalloc(&ctx->tileCost, 4 * (size_t)(slots ? slots : 1)));
         CK(cudaMemsetAsync(ctx->sampleDone, 0, 4 * (size_t)(slots ? slots : 1) * 32, ctx->stream));
         CK(cudaMemsetAsync(ctx->tileCost, 0, 4 * (size_t)(slots ? slots : 1), ctx->stream));
-        ctx->schedSlots = slots; ctx->schedKey = key; ctx->haveTileHistory = false; ctx->frameCostsValid = false; ctx->schedSamples = 0;
+        ctx->schedSlots = slots; ctx->schedKey = key; ctx->haveTileHistory = false; ctx->schedSamples = 0;
         cudaFree(ctx->sampleScratch); ctx->sampleScratch = nullptr;
     }
+    return 0;
+}
+
+// The per-sample scratch (48 B x pixels x numSamples) exists only while a kernel that parks samples runs: the pool kernel, or the
+// lanes kernel on a small share of the frame (see lanesSequential).
+int ensureSampleScratch(rg_ctx* ctx) {
+    const uint32_t S = (uint32_t)ctx->hUbo.num_samples, slots = ctx->schedSlots;
     if(S > 1 && S > ctx->schedSamples) {
         CK(cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->sampleScratch); ctx->sampleScratch = nullptr;
@@ -209,6 +221,15 @@ int ensureSchedule(rg_ctx* ctx) {
         ctx->schedSamples = S;
     }
     return 0;
+}
+
+// Lanes kernel: all numSamples samples of a pixel in one lane, one after the other (sums in registers / local memory, nothing
+// parked) when the rank's share has enough tiles to balance whole pixels over the persistent grid; on a small share one work
+// item per sample keeps the tail short (a sample's ray tree is sequential).  RGB200_LANES_SEQ=0|1 overrides (developer knob).
+bool lanesSequential(rg_ctx* ctx) {
+    static const int forced = [] { const char* e = getenv("RGB200_LANES_SEQ"); return e ? atoi(e) : -1; }();
+    if(forced >= 0) return forced != 0;
+    return false;   // measured (B200, C2): 4.80 ms against 4.43 ms -- see DESIGN.md 4.1
 }
 
 constexpr uint32_t kSchedReprobe = 256;   // two probe frames (one per kernel) every 256: < 0.5 % even when the loser is 60 % slower
@@ -251,7 +272,7 @@ void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
         p.targets[0] = self; p.nTargets = 1; p.self = 0;
     }
     p.idInst = (flags & RG_DEBUG_IDS) ? c->idInst : nullptr; p.idPrim = (flags & RG_DEBUG_IDS) ? c->idPrim : nullptr;
-    p.workCounter = c->dWork; p.counters = c->dCounters; p.flags = flags; p.ctxPool = c->ctxPool;
+    p.workCounter = reinterpret_cast<uint32_t*>(c->dCounters + 16); p.counters = c->dCounters; p.flags = flags; p.ctxPool = c->ctxPool;
     p.sampleScratch = c->sampleScratch; p.sampleDone = c->sampleDone;
     p.tileOrder = c->haveTileHistory ? c->tileOrder : nullptr; p.tileCost = c->tileCost;
     // miss.rmiss:63-66 (oracle/orc_shade.cpp skyMix): scatter = 1 - clamp(pow(4 - lightDir.y, 1/15), .8, 1);
@@ -269,6 +290,7 @@ void fillPostParams(rg_ctx* c, PostParams& p, uint32_t flags) {
     p.base = c->base; p.normal = c->normal; p.rough = c->rough; p.final_ = c->final_; p.roughA = c->roughA; p.roughB = c->roughB;
     p.fxaaOut = c->fxaaOut;  // fxaa.comp:35 writes baseImage and the host swaps base <-> final (raytracer.cpp:138-140); here the FXAA
                              // result has its own buffer and rg_read_image maps the selectors, so image pointers never move
+    p.blurList = c->blurList; p.blurCount = c->blurCount; p.blurParity = c->blurParity;
     p.trans = c->trans; p.rgba8 = c->rgba8; p.gather = (flags & RG_NO_GATHER) ? nullptr : c->gatherTarget;
     p.W = (int)c->W; p.H = (int)c->H; p.rx0 = c->rx0; p.ry0 = c->ry0; p.rw = c->rw; p.rh = c->rh;
     p.ix0 = c->ix0; p.iy0 = c->iy0; p.ix1 = c->ix1; p.iy1 = c->iy1;
@@ -278,14 +300,15 @@ void fillPostParams(rg_ctx* c, PostParams& p, uint32_t flags) {
 }
 
 int runPost(rg_ctx* ctx, uint32_t flags) {
+    ctx->blurParity ^= 1;
     PostParams pp; fillPostParams(ctx, pp, flags);
     CK(cudaEventRecord(ctx->ev[EV_ROUGH0], ctx->stream));
     launchRoughPrepare(pp, ctx->stream);
-    launchRoughBlur(pp, ctx->stream);
+    const int blurLaunches = launchRoughBlur(pp, ctx->numSms, ctx->stream);
     CK(cudaEventRecord(ctx->ev[EV_ROUGH1], ctx->stream));
     launchPostprocess(pp, ctx->stream);
     launchFxaaBlit(pp, ctx->stream);
-    ctx->launches += 1 + 20 + 1 + 1;
+    ctx->launches += 1 + blurLaunches + 1 + 1;
     ctx->lastFxaa = (flags & RG_FXAA) != 0;
     CK(cudaEventRecord(ctx->ev[EV_POST1], ctx->stream));
     CK(cudaEventRecord(ctx->ev[EV_GATHER1], ctx->stream));
@@ -321,19 +344,21 @@ int rg_create(rg_ctx** out, int cuda_device, uint32_t width, uint32_t height) {
     cudaGetDeviceProperties(&prop, cuda_device);
     ctx->numSms = prop.multiProcessorCount;
     if(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 5; }
+    if(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(ctx->stream); delete ctx; return 5; }
     if(const char* e = getenv("RGB200_TRACE_SCHED"))   // developer override for A/B timing: lanes | pool | auto
         ctx->schedMode = !strcmp(e, "lanes") ? RG_SCHED_LANES : (!strcmp(e, "pool") ? RG_SCHED_POOL : RG_SCHED_AUTO);
     // every allocation is checked: a half-initialised context must not reach the caller
     bool ok = true;
     auto good = [&](cudaError_t e) { ok = ok && e == cudaSuccess; };
     for(auto& e: ctx->ev) good(cudaEventCreate(&e));
-    good(cudaMalloc(&ctx->dUbo, 192)); good(cudaMalloc(&ctx->dWork, 4)); good(cudaMalloc(&ctx->dCounters, 16 * 8));
+    good(cudaEventCreateWithFlags(&ctx->evTraceDone, cudaEventDisableTiming)); good(cudaEventCreateWithFlags(&ctx->evOrderDone, cudaEventDisableTiming));
+    good(cudaMalloc(&ctx->dUbo, 192)); good(cudaMalloc(&ctx->dCounters, 17 * 8));   // 16 counters + the trace kernels' work counter: one memset per frame
     good(cudaMalloc(&ctx->ctxPool, tracePoolBytes(ctx->numSms)));
     good(cudaMallocHost(&ctx->hUboPinned, sizeof(rg_ubo)));
     good(cudaMalloc(&ctx->arriveTrace, 4 * kMaxPeers)); good(cudaMalloc(&ctx->arrivePost, 4 * kMaxPeers)); good(cudaMalloc(&ctx->dSyncErr, 4));
     good(cudaMalloc(&ctx->dPeerTraceFlags, sizeof(void*) * kMaxPeers)); good(cudaMalloc(&ctx->dPeerPostFlags, sizeof(void*) * kMaxPeers));
     if(ok) {
-        good(cudaMemset(ctx->dUbo, 0, 192)); good(cudaMemset(ctx->dCounters, 0, 128));
+        good(cudaMemset(ctx->dUbo, 0, 192)); good(cudaMemset(ctx->dCounters, 0, 17 * 8));
         good(cudaMemset(ctx->arriveTrace, 0, 4 * kMaxPeers)); good(cudaMemset(ctx->arrivePost, 0, 4 * kMaxPeers)); good(cudaMemset(ctx->dSyncErr, 0, 4));
         good(cudaMemset(ctx->dPeerTraceFlags, 0, sizeof(void*) * kMaxPeers)); good(cudaMemset(ctx->dPeerPostFlags, 0, sizeof(void*) * kMaxPeers));
     }
@@ -352,6 +377,7 @@ void rg_destroy(rg_ctx* ctx) {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if(ctx->side) cudaStreamSynchronize(ctx->side);
     freeImages(ctx);
     for(auto& pr: ctx->peerIpcOpened) for(void* ptr: pr) if(ptr) cudaIpcCloseMemHandle(ptr);
     cudaFree(ctx->arriveTrace); cudaFree(ctx->arrivePost); cudaFree(ctx->dSyncErr); cudaFree(ctx->dPeerTraceFlags); cudaFree(ctx->dPeerPostFlags);
@@ -359,12 +385,15 @@ void rg_destroy(rg_ctx* ctx) {
     cudaFree(ctx->gatherOwn); cudaFree(ctx->flushBuf);
     cudaFree(ctx->dVertices); cudaFree(ctx->dIndices); cudaFree(ctx->dMaterials); cudaFree(ctx->blasNodes); cudaFree(ctx->tris); cudaFree(ctx->dMeshBoxes); cudaFree(ctx->dMeshSpheres);
     cudaFree(ctx->dInstRaw); cudaFree(ctx->dInstTrav); cudaFree(ctx->dInstShade); cudaFree(ctx->dMeshRoots); cudaFree(ctx->tlasNodes); cudaFree(ctx->tlasLeaves);
-    cudaFree(ctx->dUbo); cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->ctxPool);
+    cudaFree(ctx->dUbo); cudaFree(ctx->dCounters); cudaFree(ctx->ctxPool);
     cudaFree(ctx->dEntities); cudaFree(ctx->dEntTmp); cudaFree(ctx->dEntEmit); cudaFree(ctx->dEntCount);
     cudaFreeHost(ctx->hInstPinned); cudaFreeHost(ctx->hUboPinned);
     for(auto& m: ctx->meshes) m.scratch.release();
     ctx->tlasScratch.release();
     for(auto& e: ctx->ev) cudaEventDestroy(e);
+    if(ctx->evTraceDone) cudaEventDestroy(ctx->evTraceDone);
+    if(ctx->evOrderDone) cudaEventDestroy(ctx->evOrderDone);
+    if(ctx->side) cudaStreamDestroy(ctx->side);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -640,22 +669,26 @@ int rg_render(rg_ctx* ctx, uint32_t flags) {
         ctx->launches++;
     }
     if(ensureSchedule(ctx)) return 1;
-    CK(cudaMemsetAsync(ctx->dWork, 0, 4, ctx->stream));
-    CK(cudaMemsetAsync(ctx->dCounters, 0, 128, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dCounters, 0, 17 * 8, ctx->stream));   // ray counters + work counter
     CK(cudaEventRecord(ctx->ev[EV_RT0], ctx->stream));
-    if(ctx->frameCostsValid) {   // heavy-first order from the previous frame's per-tile ray counts
-        launchOrderTiles(ctx->tileCost, ctx->schedSlots, ctx->tileOrder, ctx->stream);
-        ctx->launches++;
-        ctx->haveTileHistory = true;
-    }
+    if(ctx->orderPending) { CK(cudaStreamWaitEvent(ctx->stream, ctx->evOrderDone, 0)); ctx->orderPending = false; }
     TraceParams tp; fillTraceParams(ctx, tp, flags);
     const bool pool = chooseScheduler(ctx, flags);
+    const bool seq = !pool && lanesSequential(ctx);
+    if(!seq) { if(ensureSampleScratch(ctx)) return 1; tp.sampleScratch = ctx->sampleScratch; }
     if(ctx->schedProbe >= 0) CK(cudaEventRecord(ctx->ev[EV_PROBE0], ctx->stream));
-    launchTrace(tp, ctx->numSms, pool, ctx->stream);
+    launchTrace(tp, ctx->numSms, pool, seq, ctx->stream);
     if(ctx->schedProbe >= 0) CK(cudaEventRecord(ctx->ev[EV_PROBE1], ctx->stream));
     ctx->launches++;
-    ctx->frameCostsValid = true;
     CK(cudaEventRecord(ctx->ev[EV_TRACE1], ctx->stream));
+    {   // heavy-first tile order for the NEXT frame from this frame's per-tile ray counts: a one-block kernel, run beside the post chain
+        CK(cudaEventRecord(ctx->evTraceDone, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->side, ctx->evTraceDone, 0));
+        launchOrderTiles(ctx->tileCost, ctx->schedSlots, ctx->tileOrder, ctx->side);
+        CK(cudaEventRecord(ctx->evOrderDone, ctx->side));
+        ctx->launches++;
+        ctx->orderPending = true; ctx->haveTileHistory = true;
+    }
     if(partitioned) {   // every rank's share of this rectangle has landed once all ranks signalled
         k_signal<<<1, 32, 0, ctx->stream>>>(ctx->dPeerTraceFlags, ctx->world, ctx->rank, ctx->frameId);
         k_wait<<<1, 32, 0, ctx->stream>>>(ctx->arriveTrace, ctx->world, ctx->frameId, ctx->dSyncErr);
@@ -732,6 +765,11 @@ int rg_get_timings(rg_ctx* ctx, rg_timings* out) {
         out->generic_hits = c[8];
         out->rays_primary = c[0]; out->rays_shadow = c[1]; out->rays_reflect = c[2]; out->rays_refract = c[3]; out->sky_lookups = c[4];
         out->nodes_visited = c[5]; out->tris_tested = c[6]; out->instances_entered = c[7];
+        if(c[13] && getenv("RGB200_DEBUG_TAIL")) {   // written by a -DRG_DEBUG_TAIL build of the lanes kernel only
+            const double span = (double)(c[10] - ~c[12]), busy = (double)c[11] / (double)c[13];
+            fprintf(stderr, "[rgb200] trace warps %llu: first start -> last end %.3f ms, mean warp lifetime %.3f ms (%.1f %% of the span)\n", c[13], span * 1e-6, busy * 1e-6,
+                    100.0 * busy / span);
+        }
     }
     cudaGetLastError();
     return 0;

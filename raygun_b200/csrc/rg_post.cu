@@ -49,58 +49,73 @@ __device__ __forceinline__ float dist4(F4 a, F4 b) {
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float fromSnorm8(signed char v) { return fmaxf((float)v / 127.0f, -1.0f); }
 
-// rough_prepare.comp:28-54
+// rough_prepare.comp:28-54.  Besides the three images the shader writes, the kernel appends every pixel the blur passes will touch
+// (transition weight >= 0.001 after the SNORM8 store, i.e. a stored byte > 0) to `list` (warp vote + one atomic per warp): the 20 blur
+// sub-passes then run over that list -- on the example scene 11 % of the pixels -- instead of scanning the whole transition image 20 times.
+// listCount[parity] is this frame's counter; the other one is cleared for the next frame.
 __global__ void k_rough_prepare(const uint2* __restrict__ rough, const uint2* __restrict__ normal, int W, int H, signed char* __restrict__ trans,
-                                uint2* __restrict__ roughA, uint2* __restrict__ roughB) {
+                                uint2* __restrict__ roughA, uint2* __restrict__ roughB, uint32_t* __restrict__ list, uint32_t* __restrict__ listCount, int parity) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if(x >= W || y >= H) return;
+    if(x == 0 && y == 0) listCount[parity ^ 1] = 0u;
+    const bool inside = x < W && y < H;
+    bool active = false;
     const size_t i = (size_t)y * W + x;
-    const uint2 rraw = __ldg(rough + i);
-    const F4 r = unpackHalf4(rraw);
-    const F4 ru = loadOob0(rough, x, y + 1, W, H), rd = loadOob0(rough, x, y - 1, W, H), rl = loadOob0(rough, x + 1, y, W, H), rr = loadOob0(rough, x - 1, y, W, H);
-    const F4 n = unpackHalf4(__ldg(normal + i));
-    const F4 nu = loadOob0(normal, x, y + 1, W, H), nd = loadOob0(normal, x, y - 1, W, H), nl = loadOob0(normal, x + 1, y, W, H), nr = loadOob0(normal, x - 1, y, W, H);
-    const float uf = fminf(ru.w, r.w) * clampf(1.0f - dist4(nu, n) * 10.0f, 0.0f, 1.0f);
-    const float df = fminf(rd.w, r.w) * clampf(1.0f - dist4(nd, n) * 10.0f, 0.0f, 1.0f);
-    const float lf = fminf(rl.w, r.w) * clampf(1.0f - dist4(nl, n) * 10.0f, 0.0f, 1.0f);
-    const float rf = fminf(rr.w, r.w) * clampf(1.0f - dist4(nr, n) * 10.0f, 0.0f, 1.0f);
-    float t = fminf(fminf(fminf(uf, df), lf), rf);
-    t = (t == t) ? clampf(t, -1.0f, 1.0f) : 0.0f;
-    trans[i] = (signed char)__float2int_rn(t * 127.0f);
-    roughA[i] = rraw;
-    roughB[i] = rraw;
+    if(inside) {
+        const uint2 rraw = __ldg(rough + i);
+        const F4 r = unpackHalf4(rraw);
+        const F4 ru = loadOob0(rough, x, y + 1, W, H), rd = loadOob0(rough, x, y - 1, W, H), rl = loadOob0(rough, x + 1, y, W, H), rr = loadOob0(rough, x - 1, y, W, H);
+        const F4 n = unpackHalf4(__ldg(normal + i));
+        const F4 nu = loadOob0(normal, x, y + 1, W, H), nd = loadOob0(normal, x, y - 1, W, H), nl = loadOob0(normal, x + 1, y, W, H), nr = loadOob0(normal, x - 1, y, W, H);
+        const float uf = fminf(ru.w, r.w) * clampf(1.0f - dist4(nu, n) * 10.0f, 0.0f, 1.0f);
+        const float df = fminf(rd.w, r.w) * clampf(1.0f - dist4(nd, n) * 10.0f, 0.0f, 1.0f);
+        const float lf = fminf(rl.w, r.w) * clampf(1.0f - dist4(nl, n) * 10.0f, 0.0f, 1.0f);
+        const float rf = fminf(rr.w, r.w) * clampf(1.0f - dist4(nr, n) * 10.0f, 0.0f, 1.0f);
+        float t = fminf(fminf(fminf(uf, df), lf), rf);
+        t = (t == t) ? clampf(t, -1.0f, 1.0f) : 0.0f;
+        const signed char t8 = (signed char)__float2int_rn(t * 127.0f);
+        trans[i] = t8;
+        roughA[i] = rraw;
+        roughB[i] = rraw;
+        active = t8 > 0;   // fromSnorm8(t8) >= 0.001  <=>  t8 >= 1
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, active), lane = threadIdx.x & 31u;   // blockDim.x == 32: a warp is one row segment
+    if(m) {
+        uint32_t base = 0;
+        if(lane == 0) base = atomicAdd(listCount + parity, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if(active) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
 }
 
-// rough_blur.h:23-40; (ox, oy) = (1,0) for the H pass, (0,1) for the V pass.  Most pixels are inactive (transition weight < 0.001,
-// i.e. SNORM8 <= 0) and a pass is bound by block scheduling, not bandwidth: one thread owns 4 horizontally adjacent pixels and leaves
-// after one 32-bit load when none of them is active (PX = 4); PX = 1 for small images.
-template <int PX>
-__global__ void k_rough_blur(const uint2* __restrict__ in, uint2* __restrict__ out, const signed char* __restrict__ trans, int W, int H, int ox, int oy) {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if(x0 >= W || y >= H) return;
-    const size_t row = (size_t)y * W;
-    signed char t4[PX];
-    if(PX == 4 && ((row + x0) & 3) == 0 && x0 + 3 < W) {
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(trans + row + x0));
-#pragma unroll
-        for(int k = 0; k < PX; ++k) t4[k] = (signed char)((w >> (8 * k)) & 0xffu);
-    } else {
-#pragma unroll
-        for(int k = 0; k < PX; ++k) t4[k] = x0 + k < W ? trans[row + x0 + k] : (signed char)0;
-    }
-    bool any = false;
-#pragma unroll
-    for(int k = 0; k < PX; ++k) any |= t4[k] > 0;
-    if(!any) return;
-#pragma unroll
-    for(int k = 0; k < PX; ++k) {
-        const int x = x0 + k;
-        if(x >= W) break;
-        const float t = fromSnorm8(t4[k]);
-        if(t < 0.001f) continue;
-        const size_t i = row + x;
-        const F4 r = unpackHalf4(__ldg(in + i));
-        const F4 r1 = loadOob0(in, x + ox, y + oy, W, H), r2 = loadOob0(in, x - ox, y - oy, W, H);
+// One blur sub-pass of rough_blur.h:23-40 at pixel (x, y) of `in`, as the value the shader STORES (binary16); (ox, oy) = (1,0) for
+// the H pass, (0,1) for the V pass.  A pixel whose transition weight is below 0.001 is not written by the shader, and every rough
+// image holds the rough_prepare value there, so `in` itself is what a later pass reads.
+__device__ __forceinline__ uint2 blurPixel(const uint2* __restrict__ in, const signed char* __restrict__ trans, int x, int y, int W, int H, int ox, int oy) {
+    const size_t i = (size_t)y * W + x;
+    const uint2 raw = __ldg(in + i);
+    const float t = fromSnorm8(trans[i]);
+    if(t < 0.001f) return raw;
+    const F4 r = unpackHalf4(raw);
+    const F4 r1 = loadOob0(in, x + ox, y + oy, W, H), r2 = loadOob0(in, x - ox, y - oy, W, H);
+    const float s = 1.0f - t - t;
+    return packHalf4(r.x * s + r1.x * t + r2.x * t, r.y * s + r1.y * t + r2.y * t, r.z * s + r1.z * t + r2.z * t, r.w);
+}
+
+// Blur over the list of active pixels.  FUSED: one H pass and the V pass that follows it in ONE launch: out = V(H(in)), where the three
+// H values a V pixel reads (rows y - 1, y, y + 1) are recomputed on the fly and rounded to binary16 as the H pass would have stored
+// them -- bit-identical to the two launches, half the launches and no intermediate image.  !FUSED: a single sub-pass (ox, oy).
+template <bool FUSED>
+__global__ void __launch_bounds__(256) k_rough_blur_list(const uint2* __restrict__ in, uint2* __restrict__ out, const signed char* __restrict__ trans,
+                                                         const uint32_t* __restrict__ list, const uint32_t* __restrict__ count, int W, int H, int ox, int oy) {
+    const uint32_t n = *count;
+    for(uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t i = list[k];
+        const int y = (int)(i / (uint32_t)W), x = (int)(i - (uint32_t)y * (uint32_t)W);
+        if(!FUSED) { out[i] = blurPixel(in, trans, x, y, W, H, ox, oy); continue; }
+        const float t = fromSnorm8(trans[i]);   // >= 0.001: the pixel is on the list
+        const F4 r = unpackHalf4(blurPixel(in, trans, x, y, W, H, 1, 0));
+        const F4 r1 = y + 1 < H ? unpackHalf4(blurPixel(in, trans, x, y + 1, W, H, 1, 0)) : F4{0, 0, 0, 0};
+        const F4 r2 = y > 0 ? unpackHalf4(blurPixel(in, trans, x, y - 1, W, H, 1, 0)) : F4{0, 0, 0, 0};
         const float s = 1.0f - t - t;
         out[i] = packHalf4(r.x * s + r1.x * t + r2.x * t, r.y * s + r1.y * t + r2.y * t, r.z * s + r1.z * t + r2.z * t, r.w);
     }
@@ -298,23 +313,22 @@ inline dim3 grid2d(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h +
 
 void launchRoughPrepare(const PostParams& p, cudaStream_t st) {
     const dim3 b(32, 8);
-    k_rough_prepare<<<grid2d(p.rw, p.rh, b), b, 0, st>>>(p.rough, p.normal, p.rw, p.rh, p.trans, p.roughA, p.roughB);
+    k_rough_prepare<<<grid2d(p.rw, p.rh, b), b, 0, st>>>(p.rough, p.normal, p.rw, p.rh, p.trans, p.roughA, p.roughB, p.blurList, p.blurCount, p.blurParity);
 }
-void launchRoughBlur(const PostParams& p, cudaStream_t st) {
-    const dim3 b(32, 8);
-    // large images: 4 pixels per thread (a pass is bound by block scheduling); small ones (640x360, the bands of an 8-GPU frame): 1 pixel
-    // per thread, there the pass is bound by the latency of a thread and wants all the parallelism it can get
-    const bool wide = (size_t)p.rw * p.rh >= (size_t)800000;
-    const dim3 g(((wide ? (p.rw + 3) / 4 : p.rw) + b.x - 1) / b.x, (p.rh + b.y - 1) / b.y);
-    for(int i = 0; i < 10; ++i) {
-        if(wide) {
-            k_rough_blur<4><<<g, b, 0, st>>>(p.roughA, p.roughB, p.trans, p.rw, p.rh, 1, 0);
-            k_rough_blur<4><<<g, b, 0, st>>>(p.roughB, p.roughA, p.trans, p.rw, p.rh, 0, 1);
-        } else {
-            k_rough_blur<1><<<g, b, 0, st>>>(p.roughA, p.roughB, p.trans, p.rw, p.rh, 1, 0);
-            k_rough_blur<1><<<g, b, 0, st>>>(p.roughB, p.roughA, p.trans, p.rw, p.rh, 0, 1);
-        }
+// The reference's 10 x (H: A -> B, V: B -> A) as 9 fused launches (B -> A, A -> B, ..., B -> A: both images hold the rough_prepare
+// value wherever a pass does not write) + the last H and V on their own, so that roughA (the result) AND roughB (the last H pass)
+// end up exactly as the 20 dispatches leave them.  Grid: one wave of the SMs, grid-stride over the list.
+int launchRoughBlur(const PostParams& p, int numSms, cudaStream_t st) {
+    const uint32_t* cnt = p.blurCount + p.blurParity;
+    const int g = numSms * 4;
+    const uint2 *in = p.roughB; uint2* out = p.roughA;
+    for(int i = 0; i < 9; ++i) {
+        k_rough_blur_list<true><<<g, 256, 0, st>>>(in, out, p.trans, p.blurList, cnt, p.rw, p.rh, 0, 0);
+        const uint2* t = in; in = out; out = const_cast<uint2*>(t);
     }
+    k_rough_blur_list<false><<<g, 256, 0, st>>>(p.roughA, p.roughB, p.trans, p.blurList, cnt, p.rw, p.rh, 1, 0);
+    k_rough_blur_list<false><<<g, 256, 0, st>>>(p.roughB, p.roughA, p.trans, p.blurList, cnt, p.rw, p.rh, 0, 1);
+    return 11;
 }
 void launchPostprocess(const PostParams& p, cudaStream_t st) {
     const dim3 b(32, 8);

@@ -8,6 +8,9 @@ namespace rg {
 struct PostParams {
     uint2 *base, *normal, *rough, *final_, *roughA, *roughB, *fxaaOut;  // rgba16f, pitch rw
     signed char* trans;   // R8_SNORM, pitch rw
+    uint32_t* blurList;   // rw * rh entries: pixels the blur passes write (built by rough_prepare)
+    uint32_t* blurCount;  // [2]: this frame's list length at [blurParity], the other one is cleared for the next frame
+    int blurParity;
     uint32_t* rgba8;      // interior region only, pitch ix1 - ix0
     uint32_t* gather;     // optional full-frame RGBA8 target (may be peer memory), pitch W
     int W, H;             // full frame
@@ -19,7 +22,7 @@ struct PostParams {
 };
 
 void launchRoughPrepare(const PostParams& p, cudaStream_t st);
-void launchRoughBlur(const PostParams& p, cudaStream_t st);     // 10 x (H, V)
+int launchRoughBlur(const PostParams& p, int numSms, cudaStream_t st);     // 10 x (H, V); returns the number of launches
 void launchPostprocess(const PostParams& p, cudaStream_t st);
 void launchFxaaBlit(const PostParams& p, cudaStream_t st);
 

@@ -538,7 +538,9 @@ struct ShadeConsts { V3 L; int maxRec; bool strictIeee; int numSamples; uint32_t
 constexpr uint32_t kMaxRaysPerSample = 1u << 20;   // watchdogs: far above anything a scene can need, they only turn a bug into a wrong
 constexpr uint32_t kMaxStepsPerRay = 1u << 18;     // image instead of a hung GPU
 struct PixInfo { uint32_t xy, pslot, sample, rays; };   // lx | ly << 16, pixel slot, sample index, rays traced for this sample so far
-template <bool COUNT, bool MULTI, class FR>
+// SEQ: the numSamples samples of a pixel run one after the other in the same lane (lanes kernel, large frames): the sums of
+// raygen.h:105-111 are carried in three quads behind the context's frames -- no scratch, no atomics, no fences.
+template <bool COUNT, bool MULTI, bool SEQ, class FR>
 __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeConsts& K, const Hit& h, V3& ro, V3& rd, float& rtmin, float& rtmax, V3& hv,
                                             float& depth, float& curIOR, float& refDepth, int& rayType, int& missIndex, int& rayKind, int& recDepth, int& sp,
                                             const FR fr, const PixInfo& pix, uint32_t* skyLookups, uint32_t* cntT) {
@@ -670,15 +672,29 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             V3 accColor = hv, accNormal = v3(cold0.x, cold0.y, cold0.z), accRough = v3(cold1.x, cold1.y, cold1.z);
             float accRoughA = cold1.w, accContrib = cold0.w, accDepth = depth;
             bool last = true;
-            if(K.S > 1u) {   // park this sample; the lane finishing the pixel's last sample sums all of them in order
+            if(SEQ && K.S > 1u) {   // raygen.h:105-111: acc = 0; acc += sample i, in the loop's order
+                float4 s0 = make_float4(0, 0, 0, 0), s1 = s0, s2 = s0;
+                if(sample) { s0 = fr.ld(kCtxQuads); s1 = fr.ld(kCtxQuads + 1); s2 = fr.ld(kCtxQuads + 2); }
+                s0 = make_float4(s0.x + hv.x, s0.y + hv.y, s0.z + hv.z, s0.w + cold0.w);
+                s1 = make_float4(s1.x + cold0.x, s1.y + cold0.y, s1.z + cold0.z, s1.w + depth);
+                s2 = make_float4(s2.x + cold1.x, s2.y + cold1.y, s2.z + cold1.z, s2.w + cold1.w);
+                last = sample == K.S - 1u;
+                if(last) {
+                    accColor = v3(s0.x, s0.y, s0.z); accContrib = s0.w; accNormal = v3(s1.x, s1.y, s1.z); accDepth = s1.w;
+                    accRough = v3(s2.x, s2.y, s2.z); accRoughA = s2.w;
+                } else { fr.st(kCtxQuads, s0); fr.st(kCtxQuads + 1, s1); fr.st(kCtxQuads + 2, s2); }
+            } else if(K.S > 1u) {   // park this sample; the lane finishing the pixel's last sample sums all of them in order
                 float4* rec = P.sampleScratch + 3 * ((size_t)pslot * K.S + sample);
                 __stcg(rec, make_float4(hv.x, hv.y, hv.z, cold0.w));
                 __stcg(rec + 1, make_float4(cold0.x, cold0.y, cold0.z, depth));
                 __stcg(rec + 2, cold1);
-                __threadfence();
-                last = atomicAdd(P.sampleDone + pslot, 1u) == K.S - 1u;
+                // release: the three stores above are visible (in L2) before the count.  No acquire fence on the reading side: the
+                // records are read past L1 (ld.global.cg) by loads that cannot issue before the atomic's result is known, and a
+                // gpu-scope acquire / __threadfence would invalidate the SM's whole L1 (CCTL.IVALL) at the end of EVERY sample.
+                uint32_t done;
+                asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(done) : "l"(P.sampleDone + pslot) : "memory");
+                last = done == K.S - 1u;
                 if(last) {
-                    __threadfence();
                     P.sampleDone[pslot] = 0u;   // ready for the next frame
                     accColor = v3(0, 0, 0); accNormal = v3(0, 0, 0); accRough = v3(0, 0, 0); accRoughA = 0; accContrib = 0; accDepth = 0;
                     const float4* all = P.sampleScratch + 3 * (size_t)pslot * K.S;
@@ -943,7 +959,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
                 int sp = (int)((sel >> 16) & 255u);
                 PixInfo pix;
                 pix.xy = W.pix[0][c]; pix.pslot = W.pix[1][c]; pix.sample = W.pix[2][c]; pix.rays = W.pix[3][c];
-                const bool ended = shadeContext<COUNT, MULTI>(P, K, h, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
+                const bool ended = shadeContext<COUNT, MULTI, false>(P, K, h, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
                                                               FramesPool{fr}, pix, &s_cnt[CNT_SKY][tid], cntT) == 2;
                 if(ended) {
                     outcome = 2;
@@ -1029,8 +1045,9 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
 // global counter 8 or more at a time.  On the example scene (BASELINE config 2) this keeps 21 of 32 lanes busy at 8 CTAs / SM and
 // beats the pool scheduler; on incoherent bounces (config 3) a warp waits for its longest ray and the pool wins.  rg_render
 // picks per scene by timing both (rg_api.cu).
-template <bool COUNT, bool MULTI>
+template <bool COUNT, bool MULTI, bool SEQ>
 __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const TraceParams P) {
+    static_assert(!SEQ || (RG_LANES_REFILL == 32 && RG_GRAB_MAX == 32), "SEQ: a warp owns one whole tile at a time");
     __shared__ float s_ubo[48];
     __shared__ uint32_t s_cnt[5][128];    // per lane: rays by kind + sky lookups
     const uint32_t tid = threadIdx.x;
@@ -1052,9 +1069,10 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
     const uint32_t nChunks = (nTiles + kChunkTiles - 1) / kChunkTiles;
     const uint32_t myChunks = nChunks > P.rank ? (nChunks - P.rank + P.world - 1) / P.world : 0u;
     const uint32_t S = (uint32_t)numSamples;
-    const uint32_t total = myChunks * kChunkTiles * 32u * S;   // one work item per pixel SAMPLE
+    // one work item per pixel SAMPLE; SEQ: per pixel (its samples follow each other in the lane that took it)
+    const uint32_t total = myChunks * kChunkTiles * 32u * (SEQ ? 1u : S);
 
-    float4 frames[kCtxQuads];   // suspended shader invocations (local memory)
+    float4 frames[kCtxQuads + (SEQ ? 3 : 0)];   // suspended shader invocations (local memory) [+ the pixel's sums]
     uint2 stack[kStackSize];
     uint32_t cntT[CNT_N];
     if(COUNT) {
@@ -1062,6 +1080,7 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
         for(int k = 0; k < CNT_N; ++k) cntT[k] = 0;
     }
     bool exhausted = false, busy = false;
+    bool pixValid = false;   // SEQ: the lane holds a pixel whose samples are not all traced yet
     PixInfo pix;
     pix.xy = 0; pix.pslot = 0; pix.sample = 0; pix.rays = 0;
     V3 hv = v3(0, 0, 0), ro = v3(0, 0, 0), rd = v3(0, 0, 0);
@@ -1069,10 +1088,40 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
     int recDepth = 0, sp = 0, rayType = RT_GENERIC, missIndex = 0, rayKind = CNT_PRIMARY;
     const V3 camO = v3((VI[0] * 0.0f + VI[4] * 0.0f) + (VI[8] * 0.0f + VI[12] * 1.0f), (VI[1] * 0.0f + VI[5] * 0.0f) + (VI[9] * 0.0f + VI[13] * 1.0f),
                        (VI[2] * 0.0f + VI[6] * 0.0f) + (VI[10] * 0.0f + VI[14] * 1.0f));
+#ifdef RG_DEBUG_TAIL   // developer build: how long every warp of the persistent grid had work (printed by rg_get_timings under RGB200_DEBUG_TAIL)
+    unsigned long long tWarp0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tWarp0));
+#endif
+    // raygen.h:80-100: the primary ray of sample `sample` of the lane's pixel (pix.xy)
+    auto startSample = [&](uint32_t sample) {
+        const uint32_t lx = pix.xy & 0xffffu, ly = pix.xy >> 16;
+        busy = true;
+        pix.sample = sample; pix.rays = 1u;
+        const float2 off = aaOffset(numSamples, (int)sample);
+        const float pcx = (float)lx + 0.5f + off.x, pcy = (float)ly + 0.5f + off.y;
+        const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
+        // target = projInverse * (d.x, d.y, 1, 1); direction = viewInverse * (normalize(target.xyz), 0)
+        const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
+                          (PI[2] * ddx + PI[6] * ddy) + (PI[10] + PI[14]));
+        const V3 nt = normalize(tgt);
+        rd = v3((VI[0] * nt.x + VI[4] * nt.y) + (VI[8] * nt.z), (VI[1] * nt.x + VI[5] * nt.y) + (VI[9] * nt.z), (VI[2] * nt.x + VI[6] * nt.y) + (VI[10] * nt.z));
+        ro = camO; rtmin = 0.001f; rtmax = 10000.0f;
+        rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_PRIMARY;
+        hv = v3(0, 0, 0); depth = 0; refDepth = 0; curIOR = 1.0f; recDepth = 0; sp = 0;
+        frames[kMaxFrames * 8] = make_float4(0, 0, 0, 0); frames[kMaxFrames * 8 + 1] = make_float4(0, 0, 0, 0);
+        s_cnt[CNT_PRIMARY][tid]++;
+    };
 
     while(true) {
-        // ---- refill idle lanes (warp vote + prefix compaction over one atomic)
         uint32_t idle = __ballot_sync(0xffffffffu, !busy);
+        if(SEQ && idle == 0xffffffffu && __any_sync(0xffffffffu, pixValid)) {
+            // the whole warp finished sample i of its tile: sample i + 1 of the same 32 pixels, again in lock-step
+            if(pixValid) {
+                if(pix.sample + 1u < S) startSample(pix.sample + 1u);
+                else pixValid = false;
+            }
+            idle = __ballot_sync(0xffffffffu, !busy);
+        }
+        // ---- refill idle lanes (warp vote + prefix compaction over one atomic)
         while(!exhausted && __popc(idle) >= RG_LANES_REFILL) {
             // at most RG_GRAB_MAX consecutive work items per grab: the samples of one (possibly very expensive) tile spread over several warps
             const int nIdle = __popc(idle), n = nIdle < RG_GRAB_MAX ? nIdle : RG_GRAB_MAX, leader = __ffs(idle) - 1;
@@ -1084,27 +1133,16 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
             if(served) {
                 const uint32_t w = basew + rank;
                 if(w < total) {
-                    const uint32_t l = w & 31u, pos = (w >> 5) / S;
-                    const uint32_t sample = (w >> 5) % S;
+                    // w = ((slot position * S) + sample) * 32 + pixel in tile: consecutive items = one sample index of one 8x4 tile
+                    const uint32_t l = w & 31u, pos = SEQ ? (w >> 5) : (w >> 5) / S;
+                    const uint32_t sample = SEQ ? 0u : (w >> 5) % S;
                     const uint32_t j = P.tileOrder ? __ldg(P.tileOrder + pos) : pos;
                     const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
                     const uint32_t lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u), ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
                     if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
-                        busy = true;
-                        pix.xy = lx | (ly << 16); pix.pslot = j * 32u + l; pix.sample = sample; pix.rays = 1u;
-                        // raygen.h:80-100
-                        const float2 off = aaOffset(numSamples, (int)sample);
-                        const float pcx = (float)lx + 0.5f + off.x, pcy = (float)ly + 0.5f + off.y;
-                        const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
-                        const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
-                                          (PI[2] * ddx + PI[6] * ddy) + (PI[10] + PI[14]));
-                        const V3 nt = normalize(tgt);
-                        rd = v3((VI[0] * nt.x + VI[4] * nt.y) + (VI[8] * nt.z), (VI[1] * nt.x + VI[5] * nt.y) + (VI[9] * nt.z), (VI[2] * nt.x + VI[6] * nt.y) + (VI[10] * nt.z));
-                        ro = camO; rtmin = 0.001f; rtmax = 10000.0f;
-                        rayType = RT_GENERIC; missIndex = 0; rayKind = CNT_PRIMARY;
-                        hv = v3(0, 0, 0); depth = 0; refDepth = 0; curIOR = 1.0f; recDepth = 0; sp = 0;
-                        frames[kMaxFrames * 8] = make_float4(0, 0, 0, 0); frames[kMaxFrames * 8 + 1] = make_float4(0, 0, 0, 0);
-                        s_cnt[CNT_PRIMARY][tid]++;
+                        pix.xy = lx | (ly << 16); pix.pslot = j * 32u + l;
+                        pixValid = SEQ;
+                        startSample(sample);
                     }
                 }
             }
@@ -1121,13 +1159,19 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
             travInit<true>(P, T, hit, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmax);
             for(uint32_t steps = 0; !travStep<COUNT, false>(P, T, stack, hit, wr, rtmin, cntT) && steps < kMaxStepsPerRay; ++steps) {}
             // ---- shade: hit / miss program, then the frames that resume, up to the next traceRayEXT
-            const int outcome = shadeContext<COUNT, MULTI>(P, K, hit, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
-                                                           FramesLocal{frames}, pix, &s_cnt[CNT_SKY][tid], cntT);
+            const int outcome = shadeContext<COUNT, MULTI, SEQ>(P, K, hit, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
+                                                                FramesLocal{frames}, pix, &s_cnt[CNT_SKY][tid], cntT);
             if(outcome == 1) { s_cnt[rayKind][tid]++; pix.rays++; }
             else busy = false;
         }
     }
 
+#ifdef RG_DEBUG_TAIL
+    if(lane == 0) {
+        unsigned long long tWarp1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tWarp1));
+        atomicMax(P.counters + 10, tWarp1); atomicAdd(P.counters + 11, tWarp1 - tWarp0); atomicMax(P.counters + 12, ~tWarp0); atomicAdd(P.counters + 13, 1ull);
+    }
+#endif
     // ---- ray counters: warp reduce, one atomic per warp and counter
 #pragma unroll
     for(int k = 0; k < CNT_N; ++k) {
@@ -1197,16 +1241,16 @@ void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, cudaStre
     if(nSlots) k_order_tiles<<<1, 1024, 0, stream>>>(cost, nSlots, order);
 }
 
-template <bool COUNT, bool MULTI, bool POOL>
+template <bool COUNT, bool MULTI, bool POOL, bool SEQ>
 static int tracePerSm() {   // persistent grid: a multiple of the SM count; resident CTAs per SM limited by registers / shared memory
     static int perSm = [] {
         int v = 0;
         if(POOL) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_pool<COUNT, MULTI>, 128, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_lanes<COUNT, MULTI>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_trace_lanes<COUNT, MULTI, SEQ>, 128, 0);
         if(const char* e = getenv(POOL ? "RGB200_POOL_CTAS" : "RGB200_LANES_CTAS")) { const int w = atoi(e); if(w >= 1 && w < v) v = w; }   // developer knob: occupancy sweeps
         if(const char* e = getenv(POOL ? "RGB200_POOL_CARVEOUT" : "RGB200_LANES_CARVEOUT")) {   // developer knob: shared-memory carve-out in percent (the rest is L1)
             if(POOL) cudaFuncSetAttribute(k_trace_pool<COUNT, MULTI>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-            else cudaFuncSetAttribute(k_trace_lanes<COUNT, MULTI>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+            else cudaFuncSetAttribute(k_trace_lanes<COUNT, MULTI, SEQ>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
         }
         return v < 1 ? 1 : v;
     }();
@@ -1214,21 +1258,24 @@ static int tracePerSm() {   // persistent grid: a multiple of the SM count; resi
 }
 
 template <bool COUNT, bool MULTI>
-static void launchTraceK(const TraceParams& p, int numSms, bool pool, cudaStream_t stream) {
-    if(pool) k_trace_pool<COUNT, MULTI><<<numSms * tracePerSm<COUNT, MULTI, true>(), 128, 0, stream>>>(p);
-    else k_trace_lanes<COUNT, MULTI><<<numSms * tracePerSm<COUNT, MULTI, false>(), 128, 0, stream>>>(p);
+static void launchTraceK(const TraceParams& p, int numSms, bool pool, bool seq, cudaStream_t stream) {
+    if(pool) k_trace_pool<COUNT, MULTI><<<numSms * tracePerSm<COUNT, MULTI, true, false>(), 128, 0, stream>>>(p);
+    else if(seq) k_trace_lanes<COUNT, MULTI, true><<<numSms * tracePerSm<COUNT, MULTI, false, true>(), 128, 0, stream>>>(p);
+    else k_trace_lanes<COUNT, MULTI, false><<<numSms * tracePerSm<COUNT, MULTI, false, false>(), 128, 0, stream>>>(p);
 }
 
 size_t tracePoolBytes(int numSms) {   // frames of every context of every warp of the largest persistent pool grid
-    int perSm = tracePerSm<false, false, true>();
-    if(tracePerSm<false, true, true>() > perSm) perSm = tracePerSm<false, true, true>();
-    if(tracePerSm<true, true, true>() > perSm) perSm = tracePerSm<true, true, true>();
+    int perSm = tracePerSm<false, false, true, false>();
+    if(tracePerSm<false, true, true, false>() > perSm) perSm = tracePerSm<false, true, true, false>();
+    if(tracePerSm<true, true, true, false>() > perSm) perSm = tracePerSm<true, true, true, false>();
     return sizeof(float4) * (size_t)numSms * perSm * 4u * kPoolCtx * kCtxQuads;
 }
 
-void launchTrace(const TraceParams& p, int numSms, bool pool, cudaStream_t stream) {
-    if(p.flags & RG_COUNT_TRAVERSAL) { launchTraceK<true, true>(p, numSms, pool, stream); return; }
-    if(p.nTargets > 1) launchTraceK<false, true>(p, numSms, pool, stream); else launchTraceK<false, false>(p, numSms, pool, stream);
+int traceLanesWarps(int numSms) { return numSms * tracePerSm<false, false, false, true>() * 4; }
+
+void launchTrace(const TraceParams& p, int numSms, bool pool, bool seq, cudaStream_t stream) {
+    if(p.flags & RG_COUNT_TRAVERSAL) { launchTraceK<true, true>(p, numSms, pool, seq, stream); return; }
+    if(p.nTargets > 1) launchTraceK<false, true>(p, numSms, pool, seq, stream); else launchTraceK<false, false>(p, numSms, pool, seq, stream);
 }
 
 void launchTraceRays(const TraceParams& p, const float* rays8, uint32_t n, float* tuv, uint32_t* instPrim, cudaStream_t stream) {

@@ -53,7 +53,10 @@ struct TraceParams {
 };
 
 // pool: per-warp context pools with ray / hit queues (incoherent bounces); otherwise one context per lane (coherent scenes)
-void launchTrace(const TraceParams& p, int numSms, bool pool, cudaStream_t stream);
+// seq (lanes kernel only): the numSamples samples of a pixel follow each other in one lane and are summed there (no sampleScratch /
+// sampleDone traffic); otherwise one work item per sample, parked in sampleScratch and summed by the lane that finishes the last one
+void launchTrace(const TraceParams& p, int numSms, bool pool, bool seq, cudaStream_t stream);
+int traceLanesWarps(int numSms);   // resident warps of the lanes kernel's persistent grid
 size_t tracePoolBytes(int numSms);
 // number of tile slots of this rank's share of the trace domain (sizes tileOrder / tileCost / sampleDone / sampleScratch)
 uint32_t traceShareTiles(uint32_t dw, uint32_t dh, uint32_t rank, uint32_t world);
