@@ -352,13 +352,13 @@ int rg_create(rg_ctx** out, int cuda_device, uint32_t width, uint32_t height) {
     auto good = [&](cudaError_t e) { ok = ok && e == cudaSuccess; };
     for(auto& e: ctx->ev) good(cudaEventCreate(&e));
     good(cudaEventCreateWithFlags(&ctx->evTraceDone, cudaEventDisableTiming)); good(cudaEventCreateWithFlags(&ctx->evOrderDone, cudaEventDisableTiming));
-    good(cudaMalloc(&ctx->dUbo, 192)); good(cudaMalloc(&ctx->dCounters, 17 * 8));   // 16 counters + the trace kernels' work counter: one memset per frame
+    good(cudaMalloc(&ctx->dUbo, 192)); good(cudaMalloc(&ctx->dCounters, 17 * 8 + 17 * 4));   // 16 counters + the trace kernels' work counter (one memset per frame) + the tile sort's scratch
     good(cudaMalloc(&ctx->ctxPool, tracePoolBytes(ctx->numSms)));
     good(cudaMallocHost(&ctx->hUboPinned, sizeof(rg_ubo)));
     good(cudaMalloc(&ctx->arriveTrace, 4 * kMaxPeers)); good(cudaMalloc(&ctx->arrivePost, 4 * kMaxPeers)); good(cudaMalloc(&ctx->dSyncErr, 4));
     good(cudaMalloc(&ctx->dPeerTraceFlags, sizeof(void*) * kMaxPeers)); good(cudaMalloc(&ctx->dPeerPostFlags, sizeof(void*) * kMaxPeers));
     if(ok) {
-        good(cudaMemset(ctx->dUbo, 0, 192)); good(cudaMemset(ctx->dCounters, 0, 17 * 8));
+        good(cudaMemset(ctx->dUbo, 0, 192)); good(cudaMemset(ctx->dCounters, 0, 17 * 8 + 17 * 4));
         good(cudaMemset(ctx->arriveTrace, 0, 4 * kMaxPeers)); good(cudaMemset(ctx->arrivePost, 0, 4 * kMaxPeers)); good(cudaMemset(ctx->dSyncErr, 0, 4));
         good(cudaMemset(ctx->dPeerTraceFlags, 0, sizeof(void*) * kMaxPeers)); good(cudaMemset(ctx->dPeerPostFlags, 0, sizeof(void*) * kMaxPeers));
     }
@@ -669,9 +669,10 @@ int rg_render(rg_ctx* ctx, uint32_t flags) {
         ctx->launches++;
     }
     if(ensureSchedule(ctx)) return 1;
+    // the tile sort of the previous frame (side stream) reads the ray counters and writes the order this frame uses
+    if(ctx->orderPending) { CK(cudaStreamWaitEvent(ctx->stream, ctx->evOrderDone, 0)); ctx->orderPending = false; }
     CK(cudaMemsetAsync(ctx->dCounters, 0, 17 * 8, ctx->stream));   // ray counters + work counter
     CK(cudaEventRecord(ctx->ev[EV_RT0], ctx->stream));
-    if(ctx->orderPending) { CK(cudaStreamWaitEvent(ctx->stream, ctx->evOrderDone, 0)); ctx->orderPending = false; }
     TraceParams tp; fillTraceParams(ctx, tp, flags);
     const bool pool = chooseScheduler(ctx, flags);
     const bool seq = !pool && lanesSequential(ctx);
@@ -684,9 +685,9 @@ int rg_render(rg_ctx* ctx, uint32_t flags) {
     {   // heavy-first tile order for the NEXT frame from this frame's per-tile ray counts: a one-block kernel, run beside the post chain
         CK(cudaEventRecord(ctx->evTraceDone, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->side, ctx->evTraceDone, 0));
-        launchOrderTiles(ctx->tileCost, ctx->schedSlots, ctx->tileOrder, ctx->side);
+        launchOrderTiles(ctx->tileCost, ctx->schedSlots, ctx->tileOrder, ctx->dCounters, reinterpret_cast<uint32_t*>(ctx->dCounters + 17), ctx->numSms, ctx->side);
         CK(cudaEventRecord(ctx->evOrderDone, ctx->side));
-        ctx->launches++;
+        ctx->launches += 2;
         ctx->orderPending = true; ctx->haveTileHistory = true;
     }
     if(partitioned) {   // every rank's share of this rectangle has landed once all ranks signalled

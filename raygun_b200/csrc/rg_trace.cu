@@ -120,7 +120,8 @@ __device__ __forceinline__ float byteF(uint32_t w) {  // 1 + b / 32768 for byte 
     return __uint_as_float(__byte_perm(0x3F800000u, w, 0x3240u + (J << 4)));   // the affine map back to b is folded into the FFMA constants
 }
 
-#ifdef RG_FFMA2   // measured: no gain, the child test is bound by the ALU pipe (PRMT / FMNMX), not by the FMA pipe
+#ifdef RG_FFMA2   // measured: no gain; moving the byte decode of one or two axes from PRMT (ALU pipe) to I2F.U8 (conversion pipe) gains nothing
+// either (C2 4.34 / 4.33 / 4.29 ms): the node step is bound by the number of instructions issued, not by one pipe
 // d = a * b + c on two binary32 values at once (sm_100a FFMA2; b is broadcast): near and far plane of one axis share the multiplier
 __device__ __forceinline__ void fma2(float a0, float a1, float b, float c0, float c1, float& d0, float& d1) {
     asm("{\n\t.reg .b64 va, vb, vc, vd;\n\tmov.b64 va, {%2, %3};\n\tmov.b64 vb, {%4, %4};\n\tmov.b64 vc, {%5, %6};\n\t"
@@ -1208,37 +1209,62 @@ uint32_t traceShareTiles(uint32_t dw, uint32_t dh, uint32_t rank, uint32_t world
 }
 
 namespace {
-// Counting sort of the tile slots into 8 cost classes (relative to the mean), most expensive class first.
-__global__ void __launch_bounds__(1024) k_order_tiles(uint32_t* cost, uint32_t n, uint32_t* order) {
-    __shared__ unsigned long long sSum;
-    __shared__ uint32_t sCount[8], sBase[8];
-    if(threadIdx.x == 0) sSum = 0ull;
+// Counting sort of the tile slots into 8 cost classes (relative to the mean cost = rays of the frame / slots, from the trace kernel's own
+// ray counters), most expensive class first: a histogram pass and a scatter pass over all SMs.  work[0..7] = class counts, work[8..15] =
+// scatter cursors (both zero on entry; the scatter pass leaves them zero again).
+__device__ __forceinline__ int costClass(uint32_t c, float mean) {   // 7 = >= 8x mean ... 0 = < mean / 8
+    const float r = (float)c / mean;
+    const int k = 3 + (int)floorf(log2f(fmaxf(r, 1e-6f)));
+    return k < 0 ? 0 : (k > 7 ? 7 : k);
+}
+__device__ __forceinline__ float meanCost(const unsigned long long* counters, uint32_t n) {
+    const unsigned long long rays = counters[CNT_PRIMARY] + counters[CNT_SHADOW] + counters[CNT_REFLECT] + counters[CNT_REFRACT];
+    return fmaxf((float)rays / (float)(n ? n : 1u), 1.0f);
+}
+__global__ void __launch_bounds__(256) k_order_hist(const uint32_t* __restrict__ cost, uint32_t n, const unsigned long long* __restrict__ counters, uint32_t* __restrict__ work) {
+    __shared__ uint32_t sCount[8];
     if(threadIdx.x < 8) sCount[threadIdx.x] = 0u;
     __syncthreads();
-    unsigned long long local = 0;
-    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) local += cost[i];
-    atomicAdd(&sSum, local);
+    const float mean = meanCost(counters, n);
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sCount[costClass(cost[i], mean)], 1u);
     __syncthreads();
-    const float mean = fmaxf((float)sSum / (float)(n ? n : 1u), 1.0f);
-    auto classOf = [&](uint32_t c) {   // 7 = >= 8x mean ... 0 = < mean / 8
-        const float r = (float)c / mean;
-        int k = 3 + (int)floorf(log2f(fmaxf(r, 1e-6f)));
-        return k < 0 ? 0 : (k > 7 ? 7 : k);
-    };
-    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&sCount[classOf(cost[i])], 1u);
+    if(threadIdx.x < 8 && sCount[threadIdx.x]) atomicAdd(work + threadIdx.x, sCount[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_order_scatter(uint32_t* __restrict__ cost, uint32_t n, const unsigned long long* __restrict__ counters, uint32_t* __restrict__ work,
+                                                       uint32_t* __restrict__ order, uint32_t* __restrict__ done) {
+    __shared__ uint32_t sBase[8];
+    if(threadIdx.x == 0) { uint32_t run = 0; for(int k = 7; k >= 0; --k) { sBase[k] = run; run += work[k]; } }
     __syncthreads();
-    if(threadIdx.x == 0) { uint32_t run = 0; for(int k = 7; k >= 0; --k) { sBase[k] = run; run += sCount[k]; } }
+    const float mean = meanCost(counters, n);
+    const uint32_t lane = threadIdx.x & 31u;
+    for(uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += gridDim.x * blockDim.x) {   // warp-uniform trip count
+        const uint32_t i = i0 + lane;
+        const int cls = i < n ? costClass(cost[i], mean) : -1;
+#pragma unroll
+        for(int k = 0; k < 8; ++k) {   // one atomic per warp and class
+            const uint32_t m = __ballot_sync(0xffffffffu, cls == k);
+            if(!m) continue;
+            uint32_t at = 0;
+            if(lane == (uint32_t)(__ffs(m) - 1)) at = atomicAdd(work + 8 + k, (uint32_t)__popc(m));
+            at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
+            if(cls == k) order[sBase[k] + at + __popc(m & ((1u << lane) - 1u))] = i;
+        }
+        if(i < n) cost[i] = 0u;
+    }
+    // the last block to finish clears the histogram and the cursors for the next frame
     __syncthreads();
-    for(uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t c = cost[i];
-        order[atomicAdd(&sBase[classOf(c)], 1u)] = i;
-        cost[i] = 0u;
+    if(threadIdx.x == 0) {
+        __threadfence();
+        if(atomicAdd(done, 1u) == gridDim.x - 1u) { for(int k = 0; k < 16; ++k) work[k] = 0u; *done = 0u; }
     }
 }
 }  // namespace
 
-void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, cudaStream_t stream) {
-    if(nSlots) k_order_tiles<<<1, 1024, 0, stream>>>(cost, nSlots, order);
+void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, const unsigned long long* counters, uint32_t* work, int numSms, cudaStream_t stream) {
+    if(!nSlots) return;
+    const int g = (int)((nSlots + 255u) / 256u) < numSms * 2 ? (int)((nSlots + 255u) / 256u) : numSms * 2;
+    k_order_hist<<<g, 256, 0, stream>>>(cost, nSlots, counters, work);
+    k_order_scatter<<<g, 256, 0, stream>>>(cost, nSlots, counters, work, order, work + 16);
 }
 
 template <bool COUNT, bool MULTI, bool POOL, bool SEQ>

@@ -60,8 +60,9 @@ int traceLanesWarps(int numSms);   // resident warps of the lanes kernel's persi
 size_t tracePoolBytes(int numSms);
 // number of tile slots of this rank's share of the trace domain (sizes tileOrder / tileCost / sampleDone / sampleScratch)
 uint32_t traceShareTiles(uint32_t dw, uint32_t dh, uint32_t rank, uint32_t world);
-// order[] = tile slots sorted by descending cost class (8 classes relative to the mean); cost[] is cleared for the next frame
-void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, cudaStream_t stream);
+// order[] = tile slots sorted by descending cost class (8 classes relative to the mean = rays counted by the trace kernel / slots); cost[]
+// is cleared for the next frame.  work: 17 zeroed words of scratch (left zeroed).  Two launches.
+void launchOrderTiles(uint32_t* cost, uint32_t nSlots, uint32_t* order, const unsigned long long* counters, uint32_t* work, int numSms, cudaStream_t stream);
 // debug: n rays (8 floats each) -> closest hits
 void launchTraceRays(const TraceParams& p, const float* rays8, uint32_t n, float* tuv, uint32_t* instPrim, cudaStream_t stream);
 

@@ -16,7 +16,7 @@ for spec in sys.argv[1:]:
         d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
         def val(k):
             return float(d[k].replace(",", "")) * UNIT.get(u[k], 1) if d.get(k) not in (None, "", "n/a") else None
-        name = re.sub(r"<.*", "", d["Kernel Name"].split("::")[-1]).split("(")[0].strip()
+        name = re.sub(r"<.*", "", d["Kernel Name"].split("(")[0].split("::")[-1]).strip()
         rec = {"dram_bytes": (val("dram__bytes_read.sum") or 0) + (val("dram__bytes_write.sum") or 0), "dram_read": val("dram__bytes_read.sum"),
                "dram_write": val("dram__bytes_write.sum"), "lts_bytes": (val("lts__t_sectors.sum") or 0) * 32.0,
                "thread_inst": (val("smsp__inst_executed.sum") or 0) * (val("smsp__thread_inst_executed_per_inst_executed.ratio") or 0),
