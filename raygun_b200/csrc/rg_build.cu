@@ -370,10 +370,29 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
                              uint32_t* __restrict__ wideRef) {
     const uint32_t bref = it.x, wide = it.y;
 
-    uint32_t c[8];
+    // Box, surface, primitive count and (for internal refs) the two children of every current child are loaded ONCE, when the child
+    // appears: the opening loop below is then one round of (independent) loads per opened subtree -- the latency of an item is what
+    // bounds a level, and the levels of a small tree (the per-frame TLAS) run one after the other.
+    uint32_t c[8], cLeft[8], cRight[8], cCnt[8];
+    float clo[8][3], chi[8][3], cArea[8];
+    auto fetch = [&](int k, uint32_t ref) {
+        c[k] = ref;
+        if(ref & kLeafBit) {
+            const Aabb bx = primBox[vals[ref & ~kLeafBit]];
+            for(int a = 0; a < 3; ++a) { clo[k][a] = bx.lo[a]; chi[k][a] = bx.hi[a]; }
+            cLeft[k] = cRight[k] = kInvalid; cCnt[k] = 1u;
+        } else {
+            const BNode bn = bnodes[ref];
+            const uint2 rg = range[ref];
+            for(int a = 0; a < 3; ++a) { clo[k][a] = bn.lo[a]; chi[k][a] = bn.hi[a]; }
+            cLeft[k] = bn.left; cRight[k] = bn.right; cCnt[k] = rg.y - rg.x + 1u;
+        }
+        const float dx = chi[k][0] - clo[k][0], dy = chi[k][1] - clo[k][1], dz = chi[k][2] - clo[k][2];
+        cArea[k] = dx * dy + dy * dz + dz * dx;
+    };
     int n;
-    if(bref & kLeafBit) { c[0] = bref; n = 1; }
-    else { c[0] = bnodes[bref].left; c[1] = bnodes[bref].right; n = 2; }
+    if(bref & kLeafBit) { fetch(0, bref); n = 1; }
+    else { const BNode root = bnodes[bref]; fetch(0, root.left); fetch(1, root.right); n = 2; }
 
     // phase 0: open subtrees with more than kMaxLeafPrims primitives (largest surface first);
     // phase 1: with free slots left, open small subtrees too (tighter boxes, one primitive per slot).
@@ -381,50 +400,47 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
         while(n < 8) {
             int best = -1; float bestArea = -1.0f;
             for(int k = 0; k < n; ++k) {
-                const uint32_t cnt = refCount(c[k], range);
-                const bool open = phase == 0 ? (cnt > (uint32_t)kMaxLeafPrims) : (cnt > 1u);
-                if(!open) continue;
-                float lo[3], hi[3];
-                loadRefBox(c[k], bnodes, primBox, vals, lo, hi);
-                const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-                const float area = dx * dy + dy * dz + dz * dx;
-                if(area > bestArea) { bestArea = area; best = k; }
+                const bool open = phase == 0 ? (cCnt[k] > (uint32_t)kMaxLeafPrims) : (cCnt[k] > 1u);
+                if(open && cArea[k] > bestArea) { bestArea = cArea[k]; best = k; }
             }
             if(best < 0) break;
-            const uint32_t r = c[best];
-            c[best] = bnodes[r].left;
-            c[n++] = bnodes[r].right;
+            const uint32_t l = cLeft[best], r = cRight[best];
+            fetch(best, l);
+            fetch(n++, r);
         }
     }
 
-    float clo[8][3], chi[8][3];
     float ctr[3] = {0, 0, 0}, nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for(int k = 0; k < n; ++k) {
-        loadRefBox(c[k], bnodes, primBox, vals, clo[k], chi[k]);
+    for(int k = 0; k < n; ++k)
         for(int a = 0; a < 3; ++a) { nlo[a] = fminf(nlo[a], clo[k][a]); nhi[a] = fmaxf(nhi[a], chi[k][a]); }
-    }
     for(int a = 0; a < 3; ++a) ctr[a] = 0.5f * (nlo[a] + nhi[a]);
 
-    // greedy octant assignment: slot bit 2/1/0 = +x/+y/+z side of the node centre
+    // greedy octant assignment: slot bit 2/1/0 = +x/+y/+z side of the node centre.  n rounds, each takes the (child, slot) pair of
+    // largest cost among the free ones (first in child-major order on ties).  The 64 candidates of a round are unrolled over
+    // registers (done flags as bit masks): this is the longest serial stretch of an item.
     int slotOfChild[8];
     {
-        bool childDone[8] = {false, false, false, false, false, false, false, false};
-        bool slotDone[8] = {false, false, false, false, false, false, false, false};
         float d[8][3];
-        for(int k = 0; k < n; ++k)
-            for(int a = 0; a < 3; ++a) d[k][a] = 0.5f * (clo[k][a] + chi[k][a]) - ctr[a];
+#pragma unroll
+        for(int k = 0; k < 8; ++k)
+#pragma unroll
+            for(int a = 0; a < 3; ++a) d[k][a] = k < n ? 0.5f * (clo[k][a] + chi[k][a]) - ctr[a] : 0.0f;
+        uint32_t childDone = ~((1u << n) - 1u), slotDone = 0u, packed = 0u;   // children >= n never compete
+#pragma unroll 1
         for(int round = 0; round < n; ++round) {
-            float bestCost = -FLT_MAX; int bk = -1, bs = -1;
-            for(int k = 0; k < n; ++k) {
-                if(childDone[k]) continue;
-                for(int s = 0; s < 8; ++s) {
-                    if(slotDone[s]) continue;
-                    const float cost = ((s & 4) ? d[k][0] : -d[k][0]) + ((s & 2) ? d[k][1] : -d[k][1]) + ((s & 1) ? d[k][2] : -d[k][2]);
-                    if(cost > bestCost) { bestCost = cost; bk = k; bs = s; }
+            float bestCost = -FLT_MAX; int bk = 0, bs = 0;
+#pragma unroll
+            for(int k = 0; k < 8; ++k) {
+#pragma unroll
+                for(int sl = 0; sl < 8; ++sl) {
+                    const float cost = ((sl & 4) ? d[k][0] : -d[k][0]) + ((sl & 2) ? d[k][1] : -d[k][1]) + ((sl & 1) ? d[k][2] : -d[k][2]);
+                    const bool freePair = !((childDone >> k) & 1u) && !((slotDone >> sl) & 1u);
+                    if(freePair && cost > bestCost) { bestCost = cost; bk = k; bs = sl; }
                 }
             }
-            childDone[bk] = true; slotDone[bs] = true; slotOfChild[bk] = bs;
+            childDone |= 1u << bk; slotDone |= 1u << bs; packed |= (uint32_t)bs << (4 * bk);
         }
+        for(int k = 0; k < n; ++k) slotOfChild[k] = (int)((packed >> (4 * k)) & 7u);
     }
 
     // positions: leaves first, then internal children (the traversal tests positions pairwise and stops at the first empty pair)
@@ -433,7 +449,7 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
     uint32_t nLeaf = 0, nInternal = 0;
     for(int s = 0; s < 8; ++s) childOfSlot[s] = -1;
     for(int k = 0; k < n; ++k) {
-        isInner[k] = refCount(c[k], range) > (uint32_t)kMaxLeafPrims;
+        isInner[k] = cCnt[k] > (uint32_t)kMaxLeafPrims;
         if(!isInner[k]) posOfChild[k] = (int)nLeaf++;
         childOfSlot[slotOfChild[k]] = k;
     }
@@ -461,7 +477,7 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
             queueOut[qBase + ci] = make_uint2(c[k], childBase + ci);
             ++ci;
         } else {
-            const uint32_t cnt = refCount(c[k], range), first = refFirst(c[k], range);
+            const uint32_t cnt = cCnt[k], first = refFirst(c[k], range);
             vm |= ((1u << cnt) - 1u) << (4 * j);
             for(uint32_t kk = 0; kk < cnt; ++kk) writeLeafPrim(leafSrc, primOffset + primBase + kLeafStride * (uint32_t)j + kk, vals[first + kk]);
         }
@@ -476,46 +492,48 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
     nodes[nodeOffset + wide] = nd;
 }
 
-// one launch per level (host reads the queue size in between): large builds
-template <class LeafSource>
-__global__ void k_collapse_level(const uint2* __restrict__ queueIn, const uint32_t* __restrict__ nInPtr, uint2* __restrict__ queueOut, uint32_t* nOutPtr,
-                                 uint32_t* nodeCounter, uint32_t* primCounter, const BNode* __restrict__ bnodes, const uint2* __restrict__ range,
-                                 const Aabb* __restrict__ primBox, const uint32_t* __restrict__ vals, Node8* __restrict__ nodes, uint32_t nodeOffset,
-                                 uint32_t primOffset, LeafSource leafSrc, uint32_t* __restrict__ wideRef) {
-    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-    if(item >= *nInPtr) return;
-    collapseItem<LeafSource>(queueIn[item], queueOut, nOutPtr, nodeCounter, primCounter, bnodes, range, primBox, vals, nodes, nodeOffset, primOffset,
-                             leafSrc, wideRef);
+// Barrier over the whole (co-resident: cooperative launch) grid.  bar counts arrivals of all epochs; epoch e is complete at e * gridDim.x.
+// A two-second escape turns a lost CTA into an error flag instead of a hung GPU.
+__device__ __forceinline__ void gridBarrier(uint32_t* bar, uint32_t epoch, uint32_t* err) {
+    __syncthreads();
+    if(threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const uint32_t target = epoch * gridDim.x;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while(*reinterpret_cast<volatile uint32_t*>(bar) < target) {
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if(t1 - t0 > 2000000000ull) { *err = 1u; break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
 }
 
-// all levels in ONE block-wide loop (no host round trip): the per-frame TLAS.  counters: [0],[1] queue sizes, [2] nodes, [3] prims.
+// Every collapse level inside ONE persistent grid (no host round trip, all SMs): level L takes its items from queue[L & 1], appends the
+// internal children to queue[(L + 1) & 1] and counts them in levelCount[L + 1]; a grid barrier separates the levels.  sync: [0] barrier,
+// [1] error flag, [16 + L] items of level L (all zero on entry).  counters: [2] wide nodes, [3] primitive slots.
 template <class LeafSource>
-__global__ void __launch_bounds__(1024) k_collapse_all(uint2* queue0, uint2* queue1, uint32_t* counters, uint32_t n, const BNode* __restrict__ bnodes,
+__global__ void __launch_bounds__(256) k_collapse_grid(uint2* queue0, uint2* queue1, uint32_t* counters, uint32_t* sync, uint32_t n, const BNode* __restrict__ bnodes,
                                                        const uint2* __restrict__ range, const Aabb* __restrict__ primBox,
                                                        const uint32_t* __restrict__ vals, Node8* __restrict__ nodes, uint32_t nodeOffset,
                                                        uint32_t primOffset, LeafSource leafSrc, uint32_t* __restrict__ wideRef) {
-    __shared__ uint32_t sCount;
-    if(threadIdx.x == 0) {
-        queue0[0] = make_uint2(n >= 2 ? 0u : kLeafBit, 0u);
-        counters[0] = 1; counters[1] = 0; counters[2] = 1; counters[3] = 0;
+    uint32_t* levelCount = sync + 16;
+    if(blockIdx.x == 0 && threadIdx.x == 0) {
+        queue0[0] = make_uint2(n >= 2 ? 0u : kLeafBit, 0u);   // root item: binary node 0 (or the single leaf) -> wide node 0
+        levelCount[0] = 1u; counters[2] = 1u; counters[3] = 0u;
     }
-    __syncthreads();
-    int in = 0;
-    while(true) {
-        if(threadIdx.x == 0) sCount = counters[in];
-        __syncthreads();
-        const uint32_t count = sCount;
-        if(count == 0) break;
-        uint2* qIn = in ? queue1 : queue0;
-        uint2* qOut = in ? queue0 : queue1;
-        for(uint32_t item = threadIdx.x; item < count; item += blockDim.x)
-            collapseItem<LeafSource>(qIn[item], qOut, &counters[in ^ 1], &counters[2], &counters[3], bnodes, range, primBox, vals, nodes, nodeOffset,
+    gridBarrier(sync, 1u, sync + 1);
+    for(uint32_t level = 0; level < 110u; ++level) {
+        const uint32_t count = __ldcg(levelCount + level);
+        if(count == 0u) break;
+        const uint2* qIn = (level & 1u) ? queue1 : queue0;
+        uint2* qOut = (level & 1u) ? queue0 : queue1;
+        for(uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < count; item += gridDim.x * blockDim.x)   // queue slots are reused: read past L1
+            collapseItem<LeafSource>(__ldcg(qIn + item), qOut, levelCount + level + 1, &counters[2], &counters[3], bnodes, range, primBox, vals, nodes, nodeOffset,
                                      primOffset, leafSrc, wideRef);
-        __threadfence_block();
-        __syncthreads();
-        if(threadIdx.x == 0) counters[in] = 0;
-        in ^= 1;
-        __syncthreads();
+        gridBarrier(sync, level + 2u, sync + 1);
     }
 }
 
@@ -624,12 +642,6 @@ __global__ void __launch_bounds__(1024) k_tlas_fused(const TlasFusedArgs A) {
     }
 }
 
-__global__ void k_collapse_seed(uint2* queue, uint32_t* counters, uint32_t n) {
-    // root item: binary node 0 (or the single leaf) -> wide node 0
-    queue[0] = make_uint2(n >= 2 ? 0u : kLeafBit, 0u);
-    counters[0] = 1; counters[1] = 0; counters[2] = 1; counters[3] = 0;
-}
-
 // Refit of the wide nodes after the binary boxes changed: re-quantise every node from wideRef.
 template <class LeafSource>
 __global__ void k_requantize(uint32_t nWide, Node8* __restrict__ nodes, uint32_t nodeOffset, uint32_t primOffset, const uint32_t* __restrict__ wideRef,
@@ -717,27 +729,22 @@ void radixSort(LbvhScratch& s, uint32_t n, cudaStream_t st) {
     s.sortedBuf = (uint32_t)cur;  // 4 passes -> back in buffer 0
 }
 
+// Launches k_collapse_grid cooperatively: as many CTAs as the widest level can use, never more than fit on the device at once.
 template <class LeafSource>
-void collapseHostDriven(LbvhScratch& s, uint32_t n, Node8* nodes, uint32_t nodeOffset, uint32_t primOffset, LeafSource leafSrc, uint32_t* nNodes,
-                        uint32_t* nPrims, cudaStream_t st) {
-    k_collapse_seed<<<1, 1, 0, st>>>(s.queue[0], s.counters, n);
-    s.launches++;
-    int in = 0;
-    uint32_t count = 1;
-    const uint32_t* keysUnused = nullptr; (void)keysUnused;
-    while(count) {
-        k_collapse_level<LeafSource><<<cdiv(count, 64), 64, 0, st>>>(s.queue[in], &s.counters[in], s.queue[in ^ 1], &s.counters[in ^ 1], &s.counters[2],
-                                                                      &s.counters[3], s.bnodes, s.range, s.primBox, s.vals[s.sortedBuf], nodes, nodeOffset,
-                                                                      primOffset, leafSrc, s.wideRef);
-        s.launches++;
-        uint32_t h[4];
-        RG_CUDA_OK(cudaMemcpyAsync(h, s.counters, sizeof(h), cudaMemcpyDeviceToHost, st));
-        RG_CUDA_OK(cudaStreamSynchronize(st));
-        count = h[in ^ 1];
-        *nNodes = h[2]; *nPrims = h[3];
-        RG_CUDA_OK(cudaMemsetAsync(&s.counters[in], 0, sizeof(uint32_t), st));
-        in ^= 1;
-    }
+void collapseGrid(LbvhScratch& s, uint32_t n, Node8* nodes, uint32_t nodeOffset, uint32_t primOffset, LeafSource leafSrc, cudaStream_t st) {
+    static int perSm = [] { int v = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_collapse_grid<LeafSource>, 256, 0); return v < 1 ? 1 : v; }();
+    int dev = 0, numSms = 1;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&numSms, cudaDevAttrMultiProcessorCount, dev);
+    uint32_t grid = cdiv(n, 1024u);
+    if(grid > (uint32_t)(numSms * perSm)) grid = (uint32_t)(numSms * perSm);
+    if(grid < 1u) grid = 1u;
+    RG_CUDA_OK(cudaMemsetAsync(s.gridSync, 0, 4 * 128, st));
+    uint2 *q0 = s.queue[0], *q1 = s.queue[1];
+    uint32_t *counters = s.counters, *sync = s.gridSync, *wideRef = s.wideRef;
+    const BNode* bnodes = s.bnodes; const uint2* range = s.range; const Aabb* primBox = s.primBox; const uint32_t* vals = s.vals[s.sortedBuf];
+    void* args[] = {&q0, &q1, &counters, &sync, &n, &bnodes, &range, &primBox, &vals, &nodes, &nodeOffset, &primOffset, &leafSrc, &wideRef};
+    RG_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_collapse_grid<LeafSource>, dim3(grid), dim3(256), args, 0, st));
+    s.launches += 2;
 }
 
 }  // namespace
@@ -759,13 +766,14 @@ void LbvhScratch::reserve(uint32_t n) {
     RG_CUDA_OK(cudaMalloc(&parent, 4 * 2 * (size_t)n));
     RG_CUDA_OK(cudaMalloc(&flags, 4 * (size_t)n));
     RG_CUDA_OK(cudaMalloc(&counters, 4 * 16));
+    RG_CUDA_OK(cudaMalloc(&gridSync, 4 * 128));
     RG_CUDA_OK(cudaMalloc(&sceneBox, 4 * 6));
     RG_CUDA_OK(cudaMalloc(&wideRef, 4 * 8 * (size_t)n));
 }
 
 void LbvhScratch::release() {
     cudaFree(primBox); cudaFree(hist); cudaFree(bnodes); cudaFree(range); cudaFree(parent); cudaFree(flags); cudaFree(counters); cudaFree(sceneBox);
-    cudaFree(wideRef);
+    cudaFree(wideRef); cudaFree(gridSync); gridSync = nullptr;
     for(int i = 0; i < 2; ++i) { cudaFree(keys[i]); cudaFree(vals[i]); cudaFree(queue[i]); keys[i] = vals[i] = nullptr; queue[i] = nullptr; }
     primBox = nullptr; hist = nullptr; bnodes = nullptr; range = nullptr; parent = nullptr; flags = nullptr; counters = nullptr; sceneBox = nullptr;
     wideRef = nullptr;
@@ -808,10 +816,15 @@ void buildBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t 
     meshSphere(s, src, sphereOut, st);
     lbvhCommon(s, n, st);
     LeafSourceTri ls{(const float4*)src.vertices, src.indices, src.vtxOff, src.idxOff, trisBase};
-    collapseHostDriven(s, n, nodesBase, nodeOffset, triOffset, ls, nNodes, nTris, st);
+    collapseGrid(s, n, nodesBase, nodeOffset, triOffset, ls, st);
     k_store_root_box<<<1, 32, 0, st>>>(s.sceneBox, rootBoxOut, n);
     s.launches++;
-    RG_CUDA_OK(cudaStreamSynchronize(st));
+    uint32_t h[4] = {0, 0, 0, 0}, syncWords[2] = {0, 0};
+    RG_CUDA_OK(cudaMemcpyAsync(h, s.counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+    RG_CUDA_OK(cudaMemcpyAsync(syncWords, s.gridSync, sizeof(syncWords), cudaMemcpyDeviceToHost, st));
+    RG_CUDA_OK(cudaStreamSynchronize(st));   // the ONE host round trip of a BLAS build: the caller needs the node / triangle counts
+    if(syncWords[1]) fprintf(stderr, "rgb200: BLAS collapse: grid barrier timed out\n");
+    *nNodes = h[2]; *nTris = h[3];
 }
 
 void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t nodeOffset, uint32_t nNodes, Tri* trisBase, uint32_t triOffset,
@@ -853,14 +866,7 @@ void buildTlas(LbvhScratch& s, const rg_instance* raw, uint32_t nInst, const uin
     s.launches += 3;
     lbvhCommon(s, n, st);
     LeafSourceInst ls{instTrav, tlasLeavesOut};
-    if(n <= kTlasSingleBlockMax) {   // fully asynchronous: every level inside one block
-        k_collapse_all<LeafSourceInst><<<1, 1024, 0, st>>>(s.queue[0], s.queue[1], s.counters, n, s.bnodes, s.range, s.primBox, s.vals[s.sortedBuf],
-                                                          tlasNodes, 0, 0, ls, s.wideRef);
-        s.launches++;
-    } else {
-        uint32_t nNodes = 0, nPrims = 0;
-        collapseHostDriven(s, n, tlasNodes, 0, 0, ls, &nNodes, &nPrims, st);
-    }
+    collapseGrid(s, n, tlasNodes, 0, 0, ls, st);   // fully asynchronous
 }
 
 }  // namespace rg

@@ -23,6 +23,7 @@ struct LbvhScratch {
     uint32_t* counters = nullptr;             // [8]: 0,1 queue counts, 2 node counter, 3 prim counter
     int32_t* sceneBox = nullptr;              // [6] order-preserving int encoding of the scene box
     uint32_t* wideRef = nullptr;              // [8 * maxWideNodes] binary ref per wide slot (refit)
+    uint32_t* gridSync = nullptr;             // [128] k_collapse_grid: barrier, error flag, items per level (from word 16)
     uint32_t sortedBuf = 0;                   // which of keys[]/vals[] holds the sorted result
     uint64_t launches = 0;
     void reserve(uint32_t n);
@@ -30,7 +31,6 @@ struct LbvhScratch {
 };
 
 constexpr uint32_t kTlasFusedMax = 1024;             // instances: the whole TLAS build in one block / one launch
-constexpr uint32_t kTlasSingleBlockMax = 1u << 17;   // instances; above this the level loop goes back to the host
 
 struct TriSource { const void* vertices; const uint32_t* indices; uint32_t vtxOff, idxOff, nTri; };
 
@@ -47,7 +47,7 @@ void refitBlas(LbvhScratch& s, const TriSource& src, Node8* nodesBase, uint32_t 
 
 // Per-frame TLAS from the raw instance records: instance preparation (world->object, offset table), world boxes from
 // meshBoxes (device, 6 floats per mesh), LBVH, collapse.  instTrav / instShade are indexed by instance id; tlasLeavesOut
-// receives the InstTrav records in leaf order.  One launch for n <= kTlasFusedMax; fully asynchronous for n <= kTlasSingleBlockMax.
+// receives the InstTrav records in leaf order.  One launch for n <= kTlasFusedMax; fully asynchronous (no host round trip) at every size.
 void buildTlas(LbvhScratch& s, const rg_instance* raw, uint32_t nInst, const uint32_t* meshRoots, uint32_t nMeshes, InstTrav* instTrav,
                InstShade* instShade, const float* meshBoxes, const float4* meshSpheres, Node8* tlasNodes, InstTrav* tlasLeavesOut, cudaStream_t stream);
 
