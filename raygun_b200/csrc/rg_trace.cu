@@ -67,7 +67,7 @@ struct RayCtx {
     float ox, oy, oz;
     float ix, iy, iz;     // 1/d (zero components clamped to +-1e-30)
     float Sx, Sy, Sz;     // Woop shear
-    uint32_t octinv;      // bit 2/1/0 set when d.x/d.y/d.z >= 0
+    uint32_t octinv;      // bit 2/1/0 set when 1/d.x, 1/d.y, 1/d.z > 0
     int kx, ky, kz;       // kz == kNoShear: shear constants not computed yet
 };
 
@@ -89,7 +89,8 @@ __device__ __forceinline__ void setupSlab(RayCtx& r, float ox, float oy, float o
     r.ix = __frcp_approx(fabsf(dx) > eps ? dx : copysignf(eps, dx));
     r.iy = __frcp_approx(fabsf(dy) > eps ? dy : copysignf(eps, dy));
     r.iz = __frcp_approx(fabsf(dz) > eps ? dz : copysignf(eps, dz));
-    r.octinv = (dx >= 0.0f ? 4u : 0u) | (dy >= 0.0f ? 2u : 0u) | (dz >= 0.0f ? 1u : 0u);
+    // by the sign BIT of the (clamped) direction, i.e. of 1/d: the near / far plane choice of the slab test must agree with it (d = -0)
+    r.octinv = (__float_as_int(r.ix) >= 0 ? 4u : 0u) | (__float_as_int(r.iy) >= 0 ? 2u : 0u) | (__float_as_int(r.iz) >= 0 ? 1u : 0u);
 }
 // ... and those of the triangle test (Woop shear; two IEEE divisions).  Only needed inside an instance, so they are computed when
 // the first instance is entered (kz == kNoShear until then): rays that miss every instance box never pay for them, and a ray that
@@ -251,7 +252,8 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* _
     const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
     const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
     if(COUNT) cnt[CNT_NODES]++;
-    const float sx = __uint_as_float((n0.w & 0xffu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
+    // 2^e per axis from the exponent bytes (x: one shift; the bit of ey that lands in the sign is dropped by |.|, an operand modifier)
+    const float sx = fabsf(__uint_as_float(n0.w << 23)), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
                 sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
     const float px = __uint_as_float(n0.x) - r.ox, py = __uint_as_float(n0.y) - r.oy, pz = __uint_as_float(n0.z) - r.oz;
     // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
@@ -267,7 +269,7 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* _
     const float ofx = (bx - ax) + wx, ofy = (by - ay) + wy, ofz = (bz - az) + wz;
     // near / far plane words by the sign of the direction: one LOP3 each on the packed words BEFORE the byte decode
     // (a plain ?: lets the compiler select after decoding both, which doubles the PRMTs)
-    const uint32_t mx = (r.octinv & 4u) ? 0u : 0xffffffffu, my = (r.octinv & 2u) ? 0u : 0xffffffffu, mz = (r.octinv & 1u) ? 0u : 0xffffffffu;
+    const uint32_t mx = (uint32_t)(__float_as_int(r.ix) >> 31), my = (uint32_t)(__float_as_int(r.iy) >> 31), mz = (uint32_t)(__float_as_int(r.iz) >> 31);
     const uint32_t vm = n1.w;
     // The children sit in positions 0..n-1 (rg_types.cuh): two at a time, stop at the first empty pair (vm nibbles of
     // occupied positions are non-zero).  A hit child sets its nibble of hn.

@@ -45,3 +45,28 @@ def test_closest_hit_matches_oracle(example_scene, oracle_example):
             ok = ip[k, 0] == 0xffffffff
         bad += not ok
     assert bad == 0, f"{bad} of {len(rays)} rays differ from the oracle (bit-exact t,u,v + ids expected)"
+
+
+def test_negative_zero_direction_components(example_scene, oracle_example):
+    """Axis-parallel rays whose zero components carry a MINUS sign (reflections produce them): the slab test's near / far plane choice
+    must follow the sign bit of the clamped reciprocal, not `d >= 0` (which is true for -0 while 1 / -1e-30 is negative)."""
+    import raygun_b200 as rg
+    sd = example_scene
+    rt = rg.Raytracer(64, 36)
+    rt.load_scene(sd)
+    rays = _random_rays(sd, 4000, 7)
+    rng = np.random.default_rng(8)
+    for k in range(len(rays)):
+        axes = rng.permutation(3)[: 1 + (k % 2)]
+        rays[k, 3 + axes] = np.float32(-0.0)
+    assert np.signbit(rays[:, 3:6]).any()
+    tuv, ip = rt.debug_trace_rays(rays)
+    bad = 0
+    for k in range(len(rays)):
+        hit, t, u, v, inst, prim = oracle_example.closest_hit(rays[k, :3], rays[k, 3:6], 0.01, 1000.0, brute=(k % 4 == 0))
+        if hit:
+            ok = ip[k, 0] == inst and ip[k, 1] == prim and tuv[k, 0] == np.float32(t) and tuv[k, 1] == np.float32(u) and tuv[k, 2] == np.float32(v)
+        else:
+            ok = ip[k, 0] == 0xffffffff
+        bad += not ok
+    assert bad == 0, f"{bad} of {len(rays)} rays with -0 direction components differ from the oracle"
