@@ -642,3 +642,38 @@ def test_api_guards_against_stale_state(rgmod, O, S, example_scene):
     rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
     _check_frame(rt, O.OracleScene(sd0).render(ubo, W, H, O.FXAA), rgmod, "rayConsumption 0")
     rt.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_materials_lights_and_cameras(rgmod, O, S, example_scene, seed):
+    """The shading state machine under materials the fixtures never combine: every material of the example scene replaced by a
+    seeded random one (transparent + reflective + rough + emissive, rayConsumption 1..5, ior below and above 1, grid effect),
+    a random light direction (including straight down and grazing) and a random camera; both schedulers against the oracle."""
+    import dataclasses
+    rng = np.random.default_rng(seed)
+    mats = []
+    for k in range(len(example_scene.materials)):
+        mats.append(S.make_material(diffuse=rng.uniform(0, 1, 3), transparency=float(rng.choice([0.0, 0.3, 0.98, 1.0])), specular=rng.uniform(0, 1, 3),
+                                    reflectivity=float(rng.choice([0.0, 0.2, 0.9, 1.0])), roughness=float(rng.choice([0.0, 0.3, 1.0])),
+                                    ior=float(rng.choice([0.8, 1.0, 1.33, 1.5, 2.4])), effectId=int(rng.integers(0, 2)), rayConsumption=int(rng.integers(1, 6)),
+                                    emission=float(rng.choice([0.0, 0.5, 3.0]))))
+    sd = dataclasses.replace(example_scene, materials=np.stack(mats))
+    W, H, ns, mr = 200, 112, 2, 5 + seed % 2
+    light = [np.array([0.0, -1.0, 0.0], np.float32), None, np.array([0.995, -0.0998, 0.0], np.float32)][seed % 3]
+    cam = S.example_camera_transform()
+    cam.position = (cam.position + rng.uniform(-1.5, 1.5, 3)).astype(np.float32)
+    cam.look_at(rng.uniform(-1, 1, 3).astype(np.float32))
+    ubo = S.make_ubo(cam.to_mat4_colmajor(), S.proj_inverse(W, H), ns, mr, light_dir=light)
+    ref = O.OracleScene(sd).render(ubo, W, H, O.FXAA)
+    c = ref["counters"]
+    assert c["reflect"] > 1000 and c["refract"] > 1000 and c["shadow"] > 1000
+    for sched in (rgmod.RG_SCHED_LANES, rgmod.RG_SCHED_POOL):
+        rt = rgmod.Raytracer(W, H)
+        rt.set_trace_scheduler(sched)
+        rt.load_scene(sd)
+        rt.render_frame(ubo, rgmod.RG_FXAA | rgmod.RG_DEBUG_IDS)
+        _check_frame(rt, ref, rgmod, f"random materials seed {seed} sched={sched}")
+        tm = rt.timings()
+        for a, b in (("rays_primary", "primary"), ("rays_shadow", "shadow"), ("rays_reflect", "reflect"), ("rays_refract", "refract"), ("sky_lookups", "skylookup")):
+            assert abs(tm[a] - c[b]) <= max(4, 2e-4 * c[b]), (a, tm[a], c[b])
+        rt.close()

@@ -70,3 +70,89 @@ def test_negative_zero_direction_components(example_scene, oracle_example):
             ok = ip[k, 0] == 0xffffffff
         bad += not ok
     assert bad == 0, f"{bad} of {len(rays)} rays with -0 direction components differ from the oracle"
+
+
+def _torture_scene(S, seed=3):
+    """Three meshes (a triangle soup with degenerate, duplicated, tiny and huge triangles; a box; one triangle) under 48 instances with
+    rotations, non-uniform and NEGATIVE scales, shear, pure translations, exact duplicates (ties on the instance id), tiny and large scales."""
+    rng = np.random.default_rng(seed)
+    F = np.float32
+    def verts(p):
+        v = np.zeros((len(p), 8), np.uint32)
+        f = v.view(F)
+        f[:, 0:3] = p; f[:, 4:7] = (0, 1, 0)
+        return v
+    # soup: 300 triangles
+    tri = rng.uniform(-1, 1, size=(300, 3, 3)).astype(F)
+    tri[:, 1:] = tri[:, :1] + rng.normal(scale=0.25, size=(300, 2, 3)).astype(F)
+    tri[10, 2] = tri[10, 1]                                  # zero area: two equal vertices
+    tri[11, 2] = tri[11, 0] + F(2) * (tri[11, 1] - tri[11, 0])   # collinear
+    tri[12] = tri[12, 0]                                     # a point
+    tri[20:30] = tri[40:50]                                  # exact duplicates (smaller primitive id must win)
+    tri[30, 1:] = tri[30, :1] + rng.normal(scale=1e-4, size=(2, 3)).astype(F)   # tiny
+    tri[31] *= F(300.0)                                      # huge
+    soup_v = verts(tri.reshape(-1, 3)); soup_i = np.arange(900, dtype=np.uint32)
+    c = np.array([[x, y, z] for x in (-1, 1) for y in (-1, 1) for z in (-1, 1)], F) * F(0.5)
+    box_i = np.array([0, 1, 3, 0, 3, 2, 4, 6, 7, 4, 7, 5, 0, 4, 5, 0, 5, 1, 2, 3, 7, 2, 7, 6, 0, 2, 6, 0, 6, 4, 1, 5, 7, 1, 7, 3], np.uint32)
+    one_v = verts(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], F)); one_i = np.array([0, 1, 2], np.uint32)
+    vertices = np.concatenate([soup_v, verts(c), one_v]); indices = np.concatenate([soup_i, box_i, one_i])
+    meshes = np.array([(0, 900, 0, 900), (900, 8, 900, 36), (908, 3, 936, 3)], np.uint32)
+    xf, meta = [], []
+    def add(m, mesh):
+        xf.append(np.asarray(m, F).reshape(12)); meta.append((mesh, int(meshes[mesh, 0]), int(meshes[mesh, 2]), 0))
+    for k in range(44):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        sc = np.exp(rng.uniform(-1.5, 1.5, 3)) * rng.choice([-1.0, 1.0], 3)
+        a = q @ np.diag(sc)
+        if k % 5 == 0: a = a + 0.3 * rng.normal(size=(3, 3))      # shear
+        if k % 7 == 0: a = np.eye(3)                               # pure translation
+        if k == 3: a = a * 1e-3
+        if k == 4: a = a * 50.0
+        t = rng.uniform(-6, 6, 3)
+        add(np.concatenate([a, t[:, None]], 1), k % 3)
+    for k in (1, 2, 8, 9):                                         # exact duplicates of earlier instances
+        xf.append(xf[k].copy()); meta.append(meta[k])
+    mats = np.stack([S.make_material()])
+    return S.SceneData(vertices, indices, meshes, mats, np.stack(xf).astype(F), np.array(meta, np.uint32), name="torture")
+
+
+def _torture_rays(sd):
+    rays = _random_rays(sd, 6000, 5)
+    rng = np.random.default_rng(6)
+    n = len(rays)
+    free = rng.integers(0, n, n // 3)                    # origins anywhere, not on a surface
+    rays[free, :3] = rng.uniform(-8, 8, size=(len(free), 3)).astype(np.float32)
+    tiny = rng.integers(0, n, n // 10)
+    rays[tiny, 3 + rng.integers(0, 3, len(tiny))] = np.float32(1e-36) * rng.choice([-1, 1], len(tiny)).astype(np.float32)   # below the slab clamp
+    neg0 = rng.integers(0, n, n // 10)
+    rays[neg0, 3 + rng.integers(0, 3, len(neg0))] = np.float32(-0.0)
+    far = rng.integers(0, n, n // 20)
+    rays[far, :3] *= np.float32(1e4)                     # origins far outside
+    rays[:, 6] = np.where(rng.random(n) < 0.2, 0.0, 0.01).astype(np.float32)
+    rays[:, 7] = np.where(rng.random(n) < 0.2, rng.uniform(0.05, 5.0, n), 1000.0).astype(np.float32)
+    return rays
+
+
+def test_torture_scene_closest_hit():
+    """Degenerate / duplicated geometry, mirrored and sheared instances, extreme rays: ids and t, u, v bit for bit against the oracle
+    (every fourth ray against its brute-force loop over all triangles)."""
+    import raygun_b200 as rg
+    from raygun_b200 import scene as S
+    from oracle import oracle as O
+    sd = _torture_scene(S)
+    osc = O.OracleScene(sd)
+    rt = rg.Raytracer(64, 36)
+    rt.load_scene(sd)
+    rays = _torture_rays(sd)
+    n = len(rays)
+    tuv, ip = rt.debug_trace_rays(rays)
+    bad = []
+    for k in range(n):
+        hit, t, u, v, inst, prim = osc.closest_hit(rays[k, :3], rays[k, 3:6], float(rays[k, 6]), float(rays[k, 7]), brute=(k % 4 == 0))
+        if hit:
+            ok = ip[k, 0] == inst and ip[k, 1] == prim and tuv[k, 0] == np.float32(t) and tuv[k, 1] == np.float32(u) and tuv[k, 2] == np.float32(v)
+        else:
+            ok = ip[k, 0] == 0xffffffff
+        if not ok:
+            bad.append((k, hit, t, inst, prim, int(ip[k, 0]), int(ip[k, 1]), float(tuv[k, 0])))
+    assert not bad, f"{len(bad)} of {n} rays differ from the oracle, first: {bad[:5]}"

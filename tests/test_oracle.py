@@ -292,3 +292,23 @@ def test_sphere_integrator_restatement_behaves():
     assert e["position"][:2, 1].min() >= 1.0 - 1e-4                               # never below floor + radius
     assert peak[0] < 2.5 < peak[1]                                                # restitution 0.6 loses energy, 1.0 keeps bouncing
     assert abs(float((e["rotation"][0] ** 2).sum()) - 1.0) < 1e-5
+
+
+def test_oracle_bvh_equals_brute_force_on_torture_scene():
+    """The oracle's own two closest-hit routes agree on degenerate / duplicated triangles, mirrored / sheared / duplicated instances and
+    extreme rays (the scene and rays of tests/test_gpu_traversal.py::test_torture_scene_closest_hit)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("tgt", os.path.join(os.path.dirname(__file__), "test_gpu_traversal.py"))
+    tgt = importlib.util.module_from_spec(spec); spec.loader.exec_module(tgt)
+    from raygun_b200 import scene as S
+    from oracle import oracle as O
+    sd = tgt._torture_scene(S)
+    osc = O.OracleScene(sd)
+    rays = tgt._torture_rays(sd)[:1500]
+    hits = 0
+    for r in rays:
+        a = osc.closest_hit(r[:3], r[3:6], float(r[6]), float(r[7]))
+        b = osc.closest_hit(r[:3], r[3:6], float(r[6]), float(r[7]), brute=True)
+        assert a == b, (r, a, b)
+        hits += a[0]
+    assert 100 < hits < len(rays)
