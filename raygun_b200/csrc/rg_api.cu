@@ -271,6 +271,10 @@ void fillTraceParams(rg_ctx* c, TraceParams& p, uint32_t flags) {
         p.dx0 = (uint32_t)c->rx0; p.dy0 = (uint32_t)c->ry0; p.dw = (uint32_t)c->rw; p.dh = (uint32_t)c->rh;
         p.targets[0] = self; p.nTargets = 1; p.self = 0;
     }
+    {
+        auto magic = [](uint32_t d) { return d <= 1u ? 0xffffffffu : (uint32_t)(0x100000000ull / d); };
+        p.magicS = magic((uint32_t)c->hUbo.num_samples); p.magicTilesX = magic((p.dw + 7u) / 8u);
+    }
     p.idInst = (flags & RG_DEBUG_IDS) ? c->idInst : nullptr; p.idPrim = (flags & RG_DEBUG_IDS) ? c->idPrim : nullptr;
     p.workCounter = reinterpret_cast<uint32_t*>(c->dCounters + 16); p.counters = c->dCounters; p.flags = flags; p.ctxPool = c->ctxPool;
     p.sampleScratch = c->sampleScratch; p.sampleDone = c->sampleDone;

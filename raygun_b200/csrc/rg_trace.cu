@@ -62,6 +62,16 @@ __device__ __forceinline__ V3 refract3(V3 I, V3 N, float eta) {
     return eta * I - (eta * d + sqrtf(k)) * N;
 }
 
+// n / d and n % d for any n < 2^32 with m = floor(2^32 / d) (0xffffffff for d == 1): the high product is the quotient or one below it.
+// The work-item decode runs for every tile sample; two runtime divisions there are ~50 instructions of the loop every warp keeps in
+// the instruction caches, this is ~12.
+__device__ __forceinline__ uint32_t divMagic(uint32_t n, uint32_t d, uint32_t m, uint32_t& rem) {
+    uint32_t q = __umulhi(n, m), r = n - q * d;
+    if(r >= d) { ++q; r -= d; }
+    rem = r;
+    return q;
+}
+
 // ------------------------------------------------------------------------------------------------ traversal
 struct RayCtx {
     float ox, oy, oz;
@@ -158,6 +168,9 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return d;
 }
 
+__device__ __noinline__ float edge64(float a, float b, float c, float d) {   // a * b - c * d, one rounding at the end of the binary64 evaluation
+    return (float)__dsub_rn(__dmul_rn((double)a, (double)b), __dmul_rn((double)c, (double)d));
+}
 // Watertight ray / triangle test (Woop, Benthin, Wald 2013), no culling; operation order == oracle/orc_scene.cpp intersectTri.
 __device__ __forceinline__ bool triTest(const RayCtx& r, const float4 p0, const float4 p1, const float4 p2, float tmin, float& tOut, float& uOut,
                                         float& vOut) {
@@ -171,10 +184,8 @@ __device__ __forceinline__ bool triTest(const RayCtx& r, const float4 p0, const 
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
     float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
     float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
-    if(U == 0.0f || V == 0.0f || W == 0.0f) {  // rare: exact edge hit, redo in binary64 (products of floats are exact there)
-        U = (float)__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx));
-        V = (float)__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx));
-        W = (float)__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax));
+    if(U == 0.0f || V == 0.0f || W == 0.0f) {  // rare: exact edge hit, redo in binary64 (products of floats are exact there); out of line
+        U = edge64(Cx, By, Cy, Bx); V = edge64(Ax, Cy, Ay, Cx); W = edge64(Bx, Ay, By, Ax);
     }
     if((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
     const float det = __fadd_rn(__fadd_rn(U, V), W);
@@ -709,14 +720,21 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
                 }
             }
             if(last) {      // raygen.h:114 + raygen.rgen:35-38
-                // x / numSamples: for a power of two the product with the reciprocal is the same correctly rounded value
+                // x / numSamples: for a power of two the product with the reciprocal is the same correctly rounded value.  (The other
+                // sample counts take one rolled loop over the twelve values: this code runs once per pixel but sits in the instruction
+                // caches of every warp.)
                 const float inv = (float)K.numSamples;
-                const bool pow2 = (K.S & (K.S - 1u)) == 0u;
-                const float rinv = pow2 ? 1.0f / inv : 0.0f;
-                auto divN = [&](float x) { return pow2 ? x * rinv : divShared(x, inv); };
-                const uint2 ob = packHalf4(divN(accColor.x), divN(accColor.y), divN(accColor.z), divN(accContrib));
-                const uint2 on = packHalf4(divN(accNormal.x), divN(accNormal.y), divN(accNormal.z), divN(logf(accDepth) * 0.25f));
-                const uint2 orr = packHalf4(divN(accRough.x), divN(accRough.y), divN(accRough.z), divN(accRoughA));
+                float q[12] = {accColor.x, accColor.y, accColor.z, accContrib, accNormal.x, accNormal.y, accNormal.z, logf(accDepth) * 0.25f,
+                               accRough.x, accRough.y, accRough.z, accRoughA};
+                if((K.S & (K.S - 1u)) == 0u) {
+                    const float rinv = 1.0f / inv;
+#pragma unroll
+                    for(int k = 0; k < 12; ++k) q[k] *= rinv;
+                } else {
+#pragma unroll 1
+                    for(int k = 0; k < 12; ++k) q[k] = divShared(q[k], inv);
+                }
+                const uint2 ob = packHalf4(q[0], q[1], q[2], q[3]), on = packHalf4(q[4], q[5], q[6], q[7]), orr = packHalf4(q[8], q[9], q[10], q[11]);
                 // the pixel goes to every GPU whose post-chain rectangle contains it (own images or peer memory over NVLink)
 #pragma unroll
                 for(int q = 0; q < (MULTI ? kMaxPeers : 1); ++q) {   // static indices: the targets stay in the constant bank
@@ -905,18 +923,19 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
             const uint32_t w = basew + lane;
             if(c != kNoCtx && w < total) {
                 // w = ((slot position * S) + sample) * 32 + pixel in tile: consecutive items = one sample index of one 8x4 tile
-                const uint32_t l = w & 31u, pos = (w >> 5) / S;
-                const uint32_t sample = (w >> 5) % S;
+                uint32_t sample, tcol;
+                const uint32_t l = w & 31u, pos = divMagic(w >> 5, S, P.magicS, sample);
                 const uint32_t j = P.tileOrder ? __ldg(P.tileOrder + pos) : pos;
                 const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
-                const uint32_t lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u), ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
+                const uint32_t trow = divMagic(tile, tilesX, P.magicTilesX, tcol);
+                const uint32_t lx = P.dx0 + tcol * 8u + (l & 7u), ly = P.dy0 + trow * 4u + (l >> 3);   // frame coordinates
                 if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
                     ok = true;
                     W.pix[0][c] = lx | (ly << 16); W.pix[1][c] = j * 32u + l; W.pix[2][c] = sample; W.pix[3][c] = 1u;
                     // raygen.h:80-100
                     const float2 off = aaOffset(numSamples, (int)sample);
                     const float pcx = (float)lx + 0.5f + off.x, pcy = (float)ly + 0.5f + off.y;
-                    const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
+                    const float ddx = divShared(pcx, (float)P.W) * 2.0f - 1.0f, ddy = divShared(pcy, (float)P.H) * 2.0f - 1.0f;
                     // target = projInverse * (d.x, d.y, 1, 1); direction = viewInverse * (normalize(target.xyz), 0)
                     const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
                                       (PI[2] * ddx + PI[6] * ddy) + (PI[10] + PI[14]));
@@ -1101,7 +1120,7 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
         pix.sample = sample; pix.rays = 1u;
         const float2 off = aaOffset(numSamples, (int)sample);
         const float pcx = (float)lx + 0.5f + off.x, pcy = (float)ly + 0.5f + off.y;
-        const float ddx = __fdiv_rn(pcx, (float)P.W) * 2.0f - 1.0f, ddy = __fdiv_rn(pcy, (float)P.H) * 2.0f - 1.0f;
+        const float ddx = divShared(pcx, (float)P.W) * 2.0f - 1.0f, ddy = divShared(pcy, (float)P.H) * 2.0f - 1.0f;
         // target = projInverse * (d.x, d.y, 1, 1); direction = viewInverse * (normalize(target.xyz), 0)
         const V3 tgt = v3((PI[0] * ddx + PI[4] * ddy) + (PI[8] + PI[12]), (PI[1] * ddx + PI[5] * ddy) + (PI[9] + PI[13]),
                           (PI[2] * ddx + PI[6] * ddy) + (PI[10] + PI[14]));
@@ -1137,11 +1156,12 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
                 const uint32_t w = basew + rank;
                 if(w < total) {
                     // w = ((slot position * S) + sample) * 32 + pixel in tile: consecutive items = one sample index of one 8x4 tile
-                    const uint32_t l = w & 31u, pos = SEQ ? (w >> 5) : (w >> 5) / S;
-                    const uint32_t sample = SEQ ? 0u : (w >> 5) % S;
+                    uint32_t sample = 0u, tcol;
+                    const uint32_t l = w & 31u, pos = SEQ ? (w >> 5) : divMagic(w >> 5, S, P.magicS, sample);
                     const uint32_t j = P.tileOrder ? __ldg(P.tileOrder + pos) : pos;
                     const uint32_t tile = ((j / kChunkTiles) * P.world + P.rank) * kChunkTiles + (j % kChunkTiles);
-                    const uint32_t lx = P.dx0 + (tile % tilesX) * 8u + (l & 7u), ly = P.dy0 + (tile / tilesX) * 4u + (l >> 3);   // frame coordinates
+                    const uint32_t trow = divMagic(tile, tilesX, P.magicTilesX, tcol);
+                    const uint32_t lx = P.dx0 + tcol * 8u + (l & 7u), ly = P.dy0 + trow * 4u + (l >> 3);   // frame coordinates
                     if(tile < nTiles && lx < P.dx0 + P.dw && ly < P.dy0 + P.dh) {
                         pix.xy = lx | (ly << 16); pix.pslot = j * 32u + l;
                         pixValid = SEQ;

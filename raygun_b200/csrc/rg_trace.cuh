@@ -30,6 +30,7 @@ struct TraceParams {
     // trace domain: the pixels this launch is responsible for.  Single GPU / overdraw mode: the context's own rectangle.
     // Partitioned mode (world > 1): the full frame, of which this rank takes every world-th chunk of kChunkTiles 8x4 tiles.
     uint32_t dx0, dy0, dw, dh;
+    uint32_t magicS, magicTilesX;   // floor(2^32 / numSamples), floor(2^32 / tiles per row of the domain) (0xffffffff for a divisor of 1): rg_trace.cu divMagic
     uint32_t rank, world;
     // where a finished pixel is stored: every target whose rectangle (region + halo) contains it.  Target `self` is this
     // context's own images; the others are peer GPUs' images, written over NVLink (peer pointers, same process or CUDA IPC).
