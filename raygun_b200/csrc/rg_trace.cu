@@ -38,14 +38,15 @@ __device__ __forceinline__ V3 operator*(float s, V3 a) { return v3(a.x * s, a.y 
 __device__ __forceinline__ V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 #ifndef RG_INLINE_MATH
-__device__ __noinline__ float rsqrtIeee(float x) { return 1.0f / sqrtf(x); }   // ONE copy: the IEEE sqrt + divide expansion is large, and the
-__device__ __noinline__ float powShared(float x, float y) { return powf(x, y); }   // instruction caches are this kernel's bottleneck
-__device__ __noinline__ float divShared(float x, float y) { return x / y; }        // (same IEEE results as the inlined forms)
-#else
-__device__ __forceinline__ float rsqrtIeee(float x) { return 1.0f / sqrtf(x); }
-__device__ __forceinline__ float powShared(float x, float y) { return powf(x, y); }
-__device__ __forceinline__ float divShared(float x, float y) { return x / y; }
+#define RG_MATH_FN __device__ __noinline__   // ONE copy of every library expansion: the kernels are sensitive to their instruction-cache
+#else                                        // footprint (an all-inlined build, +224 instructions, is 4 % slower on C2); results are the same
+#define RG_MATH_FN __device__ __forceinline__
 #endif
+RG_MATH_FN float rsqrtIeee(float x) { return 1.0f / sqrtf(x); }
+RG_MATH_FN float powShared(float x, float y) { return powf(x, y); }
+RG_MATH_FN float divShared(float x, float y) { return x / y; }
+RG_MATH_FN float logShared(float x) { return logf(x); }
+RG_MATH_FN float sqrtShared(float x) { return sqrtf(x); }
 __device__ __forceinline__ V3 normalize(V3 a) { const float r = rsqrtIeee(dot(a, a)); return a * r; }
 __device__ __forceinline__ V3 mix3(V3 a, V3 b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
@@ -59,7 +60,7 @@ __device__ __forceinline__ V3 refract3(V3 I, V3 N, float eta) {
     const float d = dot(N, I);
     const float k = 1.0f - eta * eta * (1.0f - d * d);
     if(!(k >= 0.0f)) return v3(0.0f, 0.0f, 0.0f);
-    return eta * I - (eta * d + sqrtf(k)) * N;
+    return eta * I - (eta * d + sqrtShared(k)) * N;
 }
 
 // n / d and n % d for any n < 2^32 with m = floor(2^32 / d) (0xffffffff for d == 1): the high product is the quotient or one below it.
@@ -106,6 +107,9 @@ __device__ __forceinline__ void setupSlab(RayCtx& r, float ox, float oy, float o
 // the first instance is entered (kz == kNoShear until then): rays that miss every instance box never pay for them, and a ray that
 // enters a rotated / scaled instance pays once (for the object-space direction) instead of twice.
 constexpr int kNoShear = 3;
+// CALLS: the two IEEE divisions through the shared routine (pool kernel: C3 44.1 -> 43.1 ms) or expanded in place (lanes kernel: a
+// call inside its traversal loop costs 2 %); measured per kernel, same results.
+template <bool CALLS>
 __device__ __forceinline__ void setupShear(RayCtx& r, float dx, float dy, float dz) {
     const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
     const int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
@@ -114,8 +118,8 @@ __device__ __forceinline__ void setupShear(RayCtx& r, float dx, float dy, float 
     const float dkz = sel3(kz, dx, dy, dz);
     if(dkz < 0.0f) { const int t = kx; kx = ky; ky = t; }
     r.kx = kx; r.ky = ky; r.kz = kz;
-    r.Sx = __fdiv_rn(sel3(kx, dx, dy, dz), dkz);
-    r.Sy = __fdiv_rn(sel3(ky, dx, dy, dz), dkz);
+    r.Sx = CALLS ? divShared(sel3(kx, dx, dy, dz), dkz) : __fdiv_rn(sel3(kx, dx, dy, dz), dkz);
+    r.Sy = CALLS ? divShared(sel3(ky, dx, dy, dz), dkz) : __fdiv_rn(sel3(ky, dx, dy, dz), dkz);
     r.Sz = __frcp_rn(dkz);
 }
 
@@ -177,10 +181,22 @@ __device__ __forceinline__ bool triTest(const RayCtx& r, const float4 p0, const 
     const float A0 = __fsub_rn(p0.x, r.ox), A1 = __fsub_rn(p0.y, r.oy), A2 = __fsub_rn(p0.z, r.oz);
     const float B0 = __fsub_rn(p1.x, r.ox), B1 = __fsub_rn(p1.y, r.oy), B2 = __fsub_rn(p1.z, r.oz);
     const float C0 = __fsub_rn(p2.x, r.ox), C1 = __fsub_rn(p2.y, r.oy), C2 = __fsub_rn(p2.z, r.oz);
-    const float Akz = sel3(r.kz, A0, A1, A2), Bkz = sel3(r.kz, B0, B1, B2), Ckz = sel3(r.kz, C0, C1, C2);
-    const float Ax = __fsub_rn(sel3(r.kx, A0, A1, A2), __fmul_rn(r.Sx, Akz)), Ay = __fsub_rn(sel3(r.ky, A0, A1, A2), __fmul_rn(r.Sy, Akz));
-    const float Bx = __fsub_rn(sel3(r.kx, B0, B1, B2), __fmul_rn(r.Sx, Bkz)), By = __fsub_rn(sel3(r.ky, B0, B1, B2), __fmul_rn(r.Sy, Bkz));
-    const float Cx = __fsub_rn(sel3(r.kx, C0, C1, C2), __fmul_rn(r.Sx, Ckz)), Cy = __fsub_rn(sel3(r.ky, C0, C1, C2), __fmul_rn(r.Sy, Ckz));
+    // the nine axis selects of the three vertices share six predicates (one asm block: 6 ISETP + 18 SEL instead of 18 + 18)
+    float Akx, Aky, Akz, Bkx, Bky, Bkz, Ckx, Cky, Ckz;
+    asm("{\n\t.reg .pred x0, x1, y0, y1, z0, z1;\n\t"
+        "setp.eq.s32 x0, %9, 0;\n\tsetp.eq.s32 x1, %9, 1;\n\tsetp.eq.s32 y0, %10, 0;\n\tsetp.eq.s32 y1, %10, 1;\n\t"
+        "setp.eq.s32 z0, %11, 0;\n\tsetp.eq.s32 z1, %11, 1;\n\t"
+        "selp.f32 %0, %13, %14, x1;\n\tselp.f32 %0, %12, %0, x0;\n\tselp.f32 %1, %13, %14, y1;\n\tselp.f32 %1, %12, %1, y0;\n\t"
+        "selp.f32 %2, %13, %14, z1;\n\tselp.f32 %2, %12, %2, z0;\n\t"
+        "selp.f32 %3, %16, %17, x1;\n\tselp.f32 %3, %15, %3, x0;\n\tselp.f32 %4, %16, %17, y1;\n\tselp.f32 %4, %15, %4, y0;\n\t"
+        "selp.f32 %5, %16, %17, z1;\n\tselp.f32 %5, %15, %5, z0;\n\t"
+        "selp.f32 %6, %19, %20, x1;\n\tselp.f32 %6, %18, %6, x0;\n\tselp.f32 %7, %19, %20, y1;\n\tselp.f32 %7, %18, %7, y0;\n\t"
+        "selp.f32 %8, %19, %20, z1;\n\tselp.f32 %8, %18, %8, z0;\n\t}"
+        : "=&f"(Akx), "=&f"(Aky), "=&f"(Akz), "=&f"(Bkx), "=&f"(Bky), "=&f"(Bkz), "=&f"(Ckx), "=&f"(Cky), "=&f"(Ckz)
+        : "r"(r.kx), "r"(r.ky), "r"(r.kz), "f"(A0), "f"(A1), "f"(A2), "f"(B0), "f"(B1), "f"(B2), "f"(C0), "f"(C1), "f"(C2));
+    const float Ax = __fsub_rn(Akx, __fmul_rn(r.Sx, Akz)), Ay = __fsub_rn(Aky, __fmul_rn(r.Sy, Akz));
+    const float Bx = __fsub_rn(Bkx, __fmul_rn(r.Sx, Bkz)), By = __fsub_rn(Bky, __fmul_rn(r.Sy, Bkz));
+    const float Cx = __fsub_rn(Ckx, __fmul_rn(r.Sx, Ckz)), Cy = __fsub_rn(Cky, __fmul_rn(r.Sy, Ckz));
     float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
     float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
     float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
@@ -241,10 +257,11 @@ __device__ __forceinline__ void travInit(const TraceParams& P, Trav& T, Hit& hit
     T.tg = make_uint2(0u, 0u);
     T.curInst = kInvalid;
     // nothing to traverse (the first travStep reports a miss): empty scene, zero direction (refract on total internal reflection), NaN ray
-    const bool none = P.nInst == 0 || (dx == 0.0f && dy == 0.0f && dz == 0.0f) || !(dx == dx && dy == dy && dz == dz && ox == ox && oy == oy && oz == oz);
+    // (|dx| + |dy| + |dz| > 0 is false for the zero direction and for a NaN component alike; no product, so nothing underflows)
+    const bool none = P.nInst == 0 || !(fabsf(dx) + fabsf(dy) + fabsf(dz) > 0.0f) || !(ox == ox && oy == oy && oz == oz);
     T.ng = make_uint2(0u, none ? 0u : 0x80000000u);
     T.r.kx = 0; T.r.ky = 0; T.r.kz = kNoShear; T.r.Sx = 0.0f; T.r.Sy = 0.0f; T.r.Sz = 0.0f;
-    if(!none) { setupSlab(T.r, ox, oy, oz, dx, dy, dz); if(!LAZY) setupShear(T.r, dx, dy, dz); }
+    if(!none) { setupSlab(T.r, ox, oy, oz, dx, dy, dz); if(!LAZY) setupShear<true>(T.r, dx, dy, dz); }
 }
 
 // The three kinds of traversal work.  travNode: the 8 children of the next node of the lane's node group; leaves T.ng / T.tg = the hit
@@ -382,7 +399,7 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
                     setupSlab(r, oox, ooy, ooz, sdx, sdy, sdz);
                 }
             }
-            if(enter && shear) setupShear(r, sdx, sdy, sdz);
+            if(enter && shear) setupShear<SPH>(r, sdx, sdy, sdz);   // SPH: the pool kernel
             if(enter) {
                 T.curInst = l3.y;
                 T.ng = make_uint2(l3.x, 0x80000000u);
@@ -458,7 +475,7 @@ __device__ __noinline__ V3 skyColor(V3 d, V3 lightDir, V3 scatterColor, bool str
     const V3 rayDir = (zero && !strict) ? v3(0, 0, 0) : normalize(d);
     const float y = divShared(fabsf(d.y + 1.5f), 3.0f);
     const V3 sd = normalize(-lightDir) - rayDir;
-    float sun = 1.0f - sqrtf(dot(sd, sd));
+    float sun = 1.0f - sqrtShared(dot(sd, sd));
     sun = clampf(sun, 0.0f, 2.0f);
     float glow = clampf(sun, 0.0f, 1.0f);
     const float s2 = sun * sun, s4 = s2 * s2, s8 = s4 * s4, s16 = s8 * s8, s32 = s16 * s16, s64 = s32 * s32;
@@ -470,10 +487,10 @@ __device__ __noinline__ V3 skyColor(V3 d, V3 lightDir, V3 scatterColor, bool str
     glow = powShared(glow, y);
     glow = clampf(glow, 0.0f, 1.0f);
     sun *= powShared(y * y, 1.0f / 1.65f);
-    glow *= sqrtf(y * y);          // pow(y * y, 1 / 2)
+    glow *= sqrtShared(y * y);          // pow(y * y, 1 / 2)
     sun += glow;
     const V3 sunColor = v3(1.0f, 0.6f, 0.05f) * sun;
-    const float atmosphere = sqrtf(1.0f - y);
+    const float atmosphere = sqrtShared(1.0f - y);
     const V3 skyScatter = mix3(v3(0.2f, 0.4f, 0.8f), scatterColor, divShared(atmosphere, 1.3f));
     return sunColor + skyScatter;
 }
@@ -627,7 +644,7 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
                     issue = true;
                 }
             } else {
-                hv = hv * mixf(0.4f, 0.8f, clampf(logf(h.t) / 8.0f, 0.0f, 1.0f));
+                hv = hv * mixf(0.4f, 0.8f, clampf(logShared(h.t) / 8.0f, 0.0f, 1.0f));
             }
         } else {  // RT_GENERIC, :168-268
             if(COUNT) cntT[CNT_GENHIT]++;
@@ -724,7 +741,7 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
                 // sample counts take one rolled loop over the twelve values: this code runs once per pixel but sits in the instruction
                 // caches of every warp.)
                 const float inv = (float)K.numSamples;
-                float q[12] = {accColor.x, accColor.y, accColor.z, accContrib, accNormal.x, accNormal.y, accNormal.z, logf(accDepth) * 0.25f,
+                float q[12] = {accColor.x, accColor.y, accColor.z, accContrib, accNormal.x, accNormal.y, accNormal.z, logShared(accDepth) * 0.25f,
                                accRough.x, accRough.y, accRough.z, accRoughA};
                 if((K.S & (K.S - 1u)) == 0u) {
                     const float rinv = 1.0f / inv;
@@ -820,7 +837,7 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             refractColor = hv;
         } else if(stage == ST_REFRACT_RET_BACK) {
             const V3 diffuse = v3(qDiff.x, qDiff.y, qDiff.z);
-            refractColor = mix3(v3(1, 1, 1), diffuse, logf(1.0f + qOrg.w)) * hv;
+            refractColor = mix3(v3(1, 1, 1), diffuse, logShared(1.0f + qOrg.w)) * hv;
         }
         // combine, :254-267
         {
