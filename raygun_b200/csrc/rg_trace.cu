@@ -443,12 +443,19 @@ __device__ __forceinline__ bool travPop(Trav& T, const uint2* __restrict__ stack
     return false;
 }
 
-// One step of the fixed order node -> primitive -> pop (a lane goes on with nodes only once its pending primitives are done);
+// One step of the fixed order node -> primitives -> pop (a lane goes on with nodes only once its pending primitives are done);
 // true when the traversal is complete.  wray: the world-space ray given to travInit (needed when an instance is entered or left).
+// The primitives a lane has at hand (up to three triangles of a leaf, or the instances of a TLAS leaf until one is entered) are done
+// in a tight loop, not one per step: measured against one per step (C2 4.19 -> 4.02 ms, C5 14.86 -> 14.16 ms), against looping over
+// the nodes too (4.05) and against looping over the nodes only (4.25).  RG_PRIM_LOOP_POOL: the same for the pool kernel.
+#ifndef RG_PRIM_LOOP_POOL
+#define RG_PRIM_LOOP_POOL 0
+#endif
 template <bool COUNT, bool SPH, class WR>
 __device__ __forceinline__ bool travStep(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
     if((T.ng.y & 0xff000000u) && !T.tg.y) travNode<COUNT>(P, T, stack, hit, tmin, cnt);
-    if(T.tg.y) travPrim<COUNT, SPH>(P, T, stack, hit, wray, tmin, cnt);
+    if(!SPH || RG_PRIM_LOOP_POOL) { while(T.tg.y) travPrim<COUNT, SPH>(P, T, stack, hit, wray, tmin, cnt); }
+    else if(T.tg.y) travPrim<COUNT, SPH>(P, T, stack, hit, wray, tmin, cnt);
     if(!(T.ng.y & 0xff000000u) && !T.tg.y) return travPop(T, stack, wray);
     return false;
 }
@@ -1197,7 +1204,7 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
             Trav T;
             const WorldRayRegs wr{{ro.x, ro.y, ro.z}, {rd.x, rd.y, rd.z}, rtmax};
             travInit<true>(P, T, hit, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z, rtmax);
-            for(uint32_t steps = 0; !travStep<COUNT, false>(P, T, stack, hit, wr, rtmin, cntT) && steps < kMaxStepsPerRay; ++steps) {}
+for(uint32_t steps = 0; !travStep<COUNT, false>(P, T, stack, hit, wr, rtmin, cntT) && steps < kMaxStepsPerRay; ++steps) {}
             // ---- shade: hit / miss program, then the frames that resume, up to the next traceRayEXT
             const int outcome = shadeContext<COUNT, MULTI, SEQ>(P, K, hit, ro, rd, rtmin, rtmax, hv, depth, curIOR, refDepth, rayType, missIndex, rayKind, recDepth, sp,
                                                                 FramesLocal{frames}, pix, &s_cnt[CNT_SKY][tid], cntT);
