@@ -1052,6 +1052,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
             if(rayCount == 0u && nEmpty >= RG_EXIT_THRESHOLD && hitCount) break;
             if(!exhausted && freeCount >= RG_REFILL_THRESHOLD && rayCount == 0u) break;
             bool done = false;
+            // (two steps per round of this loop -- half the votes and queue bookkeeping -- were measured: C3 43.2 -> 55.4 ms)
             if(myCtx != kNoCtx) done = travStep<COUNT, true>(P, T, stack, hit, WorldRayPool{&W.ray[0][myCtx]}, tmin, cntT) || ++steps > kMaxStepsPerRay;
             const uint32_t mDone = __ballot_sync(0xffffffffu, done);
             if(mDone) {
@@ -1083,7 +1084,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
 #define RG_LANES_REFILL 32       // idle lanes before a warp of the lanes kernel fetches new work items (swept 2..32: C2 7.9 ms at 2, 6.6 at 8, 5.4 at 20-28, 5.2 at 32)
 #endif
 #ifndef RG_LANES_MIN_BLOCKS
-#define RG_LANES_MIN_BLOCKS 5   // 96 registers, no spills; swept 4..8 with the round-2 node step: C2 4.75 / 4.48 / 4.56 / 4.49 / 4.68 ms
+#define RG_LANES_MIN_BLOCKS 6   // 80 registers (~100 B of spills); swept 4..8 with the round-2 traversal loop: C2 4.23 / 4.06 / 3.98 / 3.96 / 4.34 ms
 #endif
 // The second scheduler, for COHERENT workloads: one context per lane, state in registers, frames in local memory.  A warp takes 32
 // consecutive work items (one sample index of one 8x4 tile), so its lanes trace neighbouring rays and then run the same shader
