@@ -86,7 +86,7 @@ struct rg_ctx {
     // faster one; the comparison is repeated every kSchedReprobe frames so a changing scene can change the choice.
     int schedMode = RG_SCHED_AUTO, schedChosen = RG_SCHED_LANES, schedProbe = -1, schedLast = RG_SCHED_LANES;
     float schedMs[2] = {-1.0f, -1.0f};
-    uint32_t schedFrames = 0;
+    uint32_t schedFrames = 0, schedInterval = 256;
     cudaEvent_t ev[EV_N]{};
     bool haveFrame = false, haveAs = false, blasBuilt = false;
     uint32_t lastFlags = 0;
@@ -232,7 +232,8 @@ bool lanesSequential(rg_ctx* ctx) {
     return false;   // measured (B200, C2): 4.80 ms against 4.43 ms -- see DESIGN.md 4.1
 }
 
-constexpr uint32_t kSchedReprobe = 256;   // two probe frames (one per kernel) every 256: < 0.5 % even when the loser is 60 % slower
+constexpr uint32_t kSchedReprobe = 256;   // two probe frames (one per kernel) every 256 frames; every 4 096 when the loser took more than
+                                          // 1.5x the winner's time (C2: the pool kernel needs 12 ms against 4 ms -- 1 % of the run at 256)
 
 // Which trace kernel runs this frame.  AUTO: once the heavy-first tile order exists (second frame on), one frame is timed with
 // each scheduler (CUDA events around the kernel; the host waits for that one frame's kernel when it needs the number) and the
@@ -244,13 +245,17 @@ bool chooseScheduler(rg_ctx* c, uint32_t flags) {
         if(cudaEventSynchronize(c->ev[EV_PROBE1]) == cudaSuccess && cudaEventElapsedTime(&ms, c->ev[EV_PROBE0], c->ev[EV_PROBE1]) == cudaSuccess) c->schedMs[c->schedProbe] = ms;
         else c->schedMs[c->schedProbe] = 1e30f;
         c->schedProbe = -1;
-        if(c->schedMs[0] >= 0.0f && c->schedMs[1] >= 0.0f) { c->schedChosen = c->schedMs[1] < c->schedMs[0] ? RG_SCHED_POOL : RG_SCHED_LANES; c->schedFrames = 0; }
+        if(c->schedMs[0] >= 0.0f && c->schedMs[1] >= 0.0f) {
+            c->schedChosen = c->schedMs[1] < c->schedMs[0] ? RG_SCHED_POOL : RG_SCHED_LANES; c->schedFrames = 0;
+            const float lo = fminf(c->schedMs[0], c->schedMs[1]), hi = fmaxf(c->schedMs[0], c->schedMs[1]);
+            c->schedInterval = hi > 1.5f * lo ? 16u * kSchedReprobe : kSchedReprobe;
+        }
     }
     int mode = c->schedChosen;
     if(c->haveTileHistory && !(flags & RG_COUNT_TRAVERSAL)) {   // the instrumented kernel is slower: never a probe frame
         if(c->schedMs[0] < 0.0f) mode = c->schedProbe = RG_SCHED_LANES;
         else if(c->schedMs[1] < 0.0f) mode = c->schedProbe = RG_SCHED_POOL;
-        else if(++c->schedFrames >= kSchedReprobe) { c->schedMs[0] = c->schedMs[1] = -1.0f; mode = c->schedProbe = RG_SCHED_LANES; }
+        else if(++c->schedFrames >= c->schedInterval) { c->schedMs[0] = c->schedMs[1] = -1.0f; mode = c->schedProbe = RG_SCHED_LANES; }
     }
     c->schedLast = mode;
     return mode == RG_SCHED_POOL;
