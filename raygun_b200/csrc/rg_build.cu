@@ -344,7 +344,7 @@ __device__ void quantizeNode(Node8& nd, const float (*clo)[3], const float (*chi
         eb[a] = (uint8_t)(k + 127);
         scale[a] = __uint_as_float((uint32_t)eb[a] << 23);
     }
-    // stored with the bias of the traversal's byte decode (1 + q / 32768, rg_trace.cu byteF): 2^(e + 15)
+    // stored with the bias of the traversal's byte decode (binary32 formulation: 1 + q / 32768, rg_trace.cu byteF: 2^(e + 15); none for RG_HALF_SLAB)
     nd.ex = (uint8_t)(eb[0] + kExpBias); nd.ey = (uint8_t)(eb[1] + kExpBias); nd.ez = (uint8_t)(eb[2] + kExpBias);
     uint8_t* qlo[3] = {nd.qlox, nd.qloy, nd.qloz};
     uint8_t* qhi[3] = {nd.qhix, nd.qhiy, nd.qhiz};
@@ -443,18 +443,18 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
         for(int k = 0; k < n; ++k) slotOfChild[k] = (int)((packed >> (4 * k)) & 7u);
     }
 
-    // positions: leaves first, then internal children (the traversal tests positions pairwise and stops at the first empty pair)
+    // nibbles: leaves first, then internal children; the plane bytes of nibble m go to position posOfNibble(m) (rg_types.cuh)
     bool isInner[8];
     int posOfChild[8], childOfSlot[8];
     uint32_t nLeaf = 0, nInternal = 0;
     for(int s = 0; s < 8; ++s) childOfSlot[s] = -1;
     for(int k = 0; k < n; ++k) {
         isInner[k] = cCnt[k] > (uint32_t)kMaxLeafPrims;
-        if(!isInner[k]) posOfChild[k] = (int)nLeaf++;
+        if(!isInner[k]) posOfChild[k] = posOfNibble((int)nLeaf++);
         childOfSlot[slotOfChild[k]] = k;
     }
     for(int k = 0; k < n; ++k)
-        if(isInner[k]) posOfChild[k] = (int)(nLeaf + nInternal++);
+        if(isInner[k]) posOfChild[k] = posOfNibble((int)(nLeaf + nInternal++));
 
     Node8 nd;
     quantizeNode(nd, clo, chi, posOfChild, n);
@@ -468,18 +468,18 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
     for(int s = 0; s < 8; ++s) {   // code order: the order of the child nodes in memory
         const int k = childOfSlot[s];
         if(k < 0) continue;
-        const int j = posOfChild[k];
+        const int j = posOfChild[k], m = nibbleOfPos(j);
         refOfPos[j] = c[k];
         if(isInner[k]) {
             imask |= 1u << s;
-            codes = (codes & ~(0xFu << (4 * j))) | ((uint32_t)s << (4 * j));
-            vm |= 8u << (4 * j);
+            codes = (codes & ~(0xFu << (4 * m))) | ((uint32_t)s << (4 * m));
+            vm |= 8u << (4 * m);
             queueOut[qBase + ci] = make_uint2(c[k], childBase + ci);
             ++ci;
         } else {
             const uint32_t cnt = cCnt[k], first = refFirst(c[k], range);
-            vm |= ((1u << cnt) - 1u) << (4 * j);
-            for(uint32_t kk = 0; kk < cnt; ++kk) writeLeafPrim(leafSrc, primOffset + primBase + kLeafStride * (uint32_t)j + kk, vals[first + kk]);
+            vm |= ((1u << cnt) - 1u) << (4 * m);
+            for(uint32_t kk = 0; kk < cnt; ++kk) writeLeafPrim(leafSrc, primOffset + primBase + kLeafStride * (uint32_t)m + kk, vals[first + kk]);
         }
     }
     if(wideRef)
@@ -662,7 +662,7 @@ __global__ void k_requantize(uint32_t nWide, Node8* __restrict__ nodes, uint32_t
         const uint32_t cnt = refCount(r, range);
         if(cnt <= (uint32_t)kMaxLeafPrims) {
             const uint32_t first = refFirst(r, range);
-            for(uint32_t k = 0; k < cnt; ++k) writeLeafPrim(leafSrc, pb + kLeafStride * (uint32_t)j + k, vals[first + k]);
+            for(uint32_t k = 0; k < cnt; ++k) writeLeafPrim(leafSrc, pb + kLeafStride * (uint32_t)nibbleOfPos(j) + k, vals[first + k]);
         }
     }
     const uint8_t imask = nd.imask;

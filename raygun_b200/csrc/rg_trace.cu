@@ -166,6 +166,28 @@ __device__ __forceinline__ void childTest(uint32_t nx, uint32_t ny, uint32_t nz,
 #endif
 }
 
+#if RG_HALF_SLAB
+__device__ __forceinline__ __half2 asHalf2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+// TWO children of a node (positions 2 PAIR and 2 PAIR + 1: bytes SEL of the plane words) in packed binary16 arithmetic: every
+// instruction serves both.  One PRMT puts a plane byte q into the low byte of each half: the SUBNORMAL 2^-24 q, exact, and HFMA2 takes
+// subnormal operands at full rate; the node-local scaling of travNode keeps every plane distance inside binary16's range.  The near
+// planes use the low halves of cx / cy / cz (rounding errors given away downwards), the far planes the high halves (upwards).  The
+// results land in the low / high half of one mask = nibbles PAIR and PAIR + 4 of the hit mask (rg_types.cuh nibbleOfPos).
+// SASS per pair: 6 PRMT + 6 HFMA2 + 2 HMNMX2 + 2 VHMNMX (three inputs) + HSET2 + LOP3 = 18, against 2 x 20 in binary32.
+template <int SEL, int PAIR>
+__device__ __forceinline__ void pairTest(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, __half2 axy, __half2 azz, __half2 cx,
+                                         __half2 cy, __half2 cz, __half2 tmn, __half2 tmx, uint32_t& hn) {
+    const __half2 ax = __low2half2(axy), ay = __high2half2(axy);   // operand swizzles of HFMA2, no instructions
+    const __half2 tnx = __hfma2(asHalf2(__byte_perm(nx, 0u, SEL)), ax, __low2half2(cx)), tny = __hfma2(asHalf2(__byte_perm(ny, 0u, SEL)), ay, __low2half2(cy)),
+                  tnz = __hfma2(asHalf2(__byte_perm(nz, 0u, SEL)), azz, __low2half2(cz));
+    const __half2 tfx = __hfma2(asHalf2(__byte_perm(fx, 0u, SEL)), ax, __high2half2(cx)), tfy = __hfma2(asHalf2(__byte_perm(fy, 0u, SEL)), ay, __high2half2(cy)),
+                  tfz = __hfma2(asHalf2(__byte_perm(fz, 0u, SEL)), azz, __high2half2(cz));
+    const __half2 tn = __hmax2(__hmax2(tnx, tny), __hmax2(tnz, tmn));   // a NaN operand (never with finite scenes) is dropped: more hits, never fewer
+    const __half2 tf = __hmin2(__hmin2(tfx, tfy), __hmin2(tfz, tmx));
+    hn |= __hle2_mask(tn, tf) & (0x000F000Fu << (4 * PAIR));
+}
+#endif
+
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {   // default mode: nibble bit 3 = replicate the byte's sign
     uint32_t d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
@@ -284,6 +306,60 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* _
     const float sx = fabsf(__uint_as_float(n0.w << 23)), sy = __uint_as_float(((n0.w >> 8) & 0xffu) << 23),
                 sz = __uint_as_float(((n0.w >> 16) & 0xffu) << 23);
     const float px = __uint_as_float(n0.x) - r.ox, py = __uint_as_float(n0.y) - r.oy, pz = __uint_as_float(n0.z) - r.oz;
+#if RG_HALF_SLAB
+    // Plane distance of byte q on one axis: t(q) = q A + B with A = 2^e / d (per quantisation step) and B = (p - o) / d.  The children are
+    // tested in binary16, two per instruction (pairTest), on t'(q) = (t(q) - t0) s -- a monotone map, so the slab test is unchanged:
+    //   s   power of two that brings the STEEPEST axis to |A| s in [2^-10, 2^-9): a node spans < 1/2 in t' on every axis, and the half
+    //       operand 2^24 A s stays below 2^15;
+    //   t0  = B of the axis with the smallest |A| (the axis along which the ray crosses the node fastest): for a ray that hits the node
+    //       every |B - t0| is then at most the sum of two axis spans, so the roundings of binary16 (relative 2^-11: the multiplier,
+    //       the addend, the result) move a plane by < 1/2 quantisation step of ITS OWN axis -- the price is a child box that looks
+    //       ~1 % larger; a ray that misses the node by far has large |B - t0| and errors to match, but a gap as large.
+    // Everything the roundings can do is bounded by e (per axis: relative to |c| and |A|, plus the binary32 error of B, which is relative
+    // to |B| and cancels -- the slack of the binary32 formulation -- plus the subnormal spacing) and given away: near planes use c - e,
+    // far planes c + e, so near <= far holds for a flat child (qlo == qhi) too.  tests/test_slab_half_model.py restates this arithmetic
+    // in numpy and checks it against binary64 over millions of random nodes and rays (incl. axis-parallel and far-away ones).
+    // Overflow to +-inf only happens in the addends (planes > 65 504 node spans away: a true miss); q * finite never makes a NaN.
+    const float ax = sx * r.ix, ay = sy * r.iy, az = sz * r.iz;
+    const float bx = px * r.ix, by = py * r.iy, bz = pz * r.iz;
+    const float aax = fabsf(ax), aay = fabsf(ay), aaz = fabsf(az);
+    const uint32_t me = min(max(__float_as_uint(fmaxf(aax, fmaxf(aay, aaz))) & 0x7f800000u, 0x0A000000u), 0x79000000u);   // clamps: degenerate nodes / rays only
+    const float S = __uint_as_float(0x86000000u - me), s = __uint_as_float(0x7A000000u - me);   // 2^(14 - E), 2^(14 - E - 24); E = exponent of max |A|
+    float t0 = aax <= aay ? bx : by;
+    t0 = aaz < fminf(aax, aay) ? bz : t0;
+    const float t0s = t0 * s;
+    const float asx = ax * S, asy = ay * S, asz = az * S;
+    const float csx = fmaf(bx, s, -t0s), csy = fmaf(by, s, -t0s), csz = fmaf(bz, s, -t0s);   // (B - t0) s, exactly 0 on the axis of t0
+    // 1.02 x 2^-11 (rounding of the addend), 1.03 x 2^-27 (of the multiplier, times q <= 255), 2 x 2^-25 (subnormal spacing), error of B.
+    // The rounding of the RESULT needs no allowance: it is monotone and applied to both sides of near <= far alike.
+    const float kRelC = 5.0e-4f, kRelA = 7.7e-9f, kAbs = 6.0e-8f, kSlack = 7.3e-7f;
+    const float e0 = fmaf(fabsf(t0s), kSlack, kAbs);
+    const float ex = fmaf(fabsf(csx), kRelC, fmaf(fabsf(asx), kRelA, e0)), ey = fmaf(fabsf(csy), kRelC, fmaf(fabsf(asy), kRelA, e0)),
+                ez = fmaf(fabsf(csz), kRelC, fmaf(fabsf(asz), kRelA, e0));
+    const __half2 haxy = __floats2half2_rn(asx, asy), hazz = __floats2half2_rn(asz, asz);
+    const __half2 hcx = __floats2half2_rn(csx - ex, csx + ex), hcy = __floats2half2_rn(csy - ey, csy + ey), hcz = __floats2half2_rn(csz - ez, csz + ez);
+    // (tmin, hit.t) on the same scale, rounded outwards
+    const float tn0 = fmaf(tmin, s, -t0s), tf0 = fmaf(hit.t, s, -t0s);
+    const float tn1 = fmaf(fabsf(tn0), -kRelC, tn0) - kAbs, tf1 = fmaf(fabsf(tf0), kRelC, tf0) + kAbs;
+    const __half2 htmn = __floats2half2_rn(tn1, tn1), htmx = __floats2half2_rn(tf1, tf1);
+    const uint32_t mx = (uint32_t)(__float_as_int(r.ix) >> 31), my = (uint32_t)(__float_as_int(r.iy) >> 31), mz = (uint32_t)(__float_as_int(r.iz) >> 31);
+    const uint32_t vm = n1.w;
+    // nibbles 0..n-1 of vm are the occupied ones and pair i holds nibbles i and i + 4: all four pairs are in use from n = 4 on, and
+    // nodes nearly always have 8 children, so no pair is skipped (empty positions hold an inverted box and never hit)
+    uint32_t hn = 0;
+    {
+        const uint32_t nx = bitsel(mx, n3.z, n2.x), fx = bitsel(mx, n2.x, n3.z), ny = bitsel(my, n4.x, n2.z), fy = bitsel(my, n2.z, n4.x),
+                       nz = bitsel(mz, n4.z, n3.x), fz = bitsel(mz, n3.x, n4.z);
+        pairTest<0x4140, 0>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
+        pairTest<0x4342, 1>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
+    }
+    {
+        const uint32_t nx = bitsel(mx, n3.w, n2.y), fx = bitsel(mx, n2.y, n3.w), ny = bitsel(my, n4.y, n2.w), fy = bitsel(my, n2.w, n4.y),
+                       nz = bitsel(mz, n4.w, n3.y), fz = bitsel(mz, n3.y, n4.w);
+        pairTest<0x4140, 2>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
+        pairTest<0x4342, 3>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
+    }
+#else
     // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
     // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.
     // Near and far use the same q * adj, so a flat child box (qlo == qhi) always keeps near <= far.
@@ -322,6 +398,7 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* _
             childTest<3, 7>(nx, ny, nz, fx, fy, fz, ax, ay, az, onx, ony, onz, ofx, ofy, ofz, tmin, hit.t, hn);
         }
     }
+#endif
     // Internal children that were hit -> bits 24 + (code ^ octant) of the node group, so that the highest bit is the nearest child:
     // ONE table look-up per four children (PRMT: selector nibble = code ^ octant picks the byte 1 << nibble; nibble 8 yields 0),
     // then the eight distinct one-hot bytes are summed into the top byte by a multiplication.

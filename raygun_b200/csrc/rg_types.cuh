@@ -16,14 +16,15 @@
 namespace rg {
 
 // Compressed 8-wide node (after Ylitie, Karras, Laine 2017).  Child boxes are quantised to 8 bits
-// relative to the node origin p with per-axis power-of-two scale 2^e.  The n children of a node sit in
-// POSITIONS 0..n-1 (leaves first, then internal children, empty positions last with an inverted box), so
-// the traversal tests them two at a time and stops at the first empty pair.  Every internal child also has
+// relative to the node origin p with per-axis power-of-two scale 2^e.  The n children of a node own
+// NIBBLES 0..n-1 of codes / vm (leaves first, then internal children); the plane bytes of nibble m sit at byte
+// POSITION posOfNibble(m) of the six plane arrays (empty positions hold an inverted box), so that the traversal
+// tests the children two at a time (positions 2i, 2i + 1 = nibbles i, i + 4).  Every internal child also has
 // an octant CODE c (bit 2/1/0 = +x/+y/+z side of the node centre where possible): XOR-ing the code with the
 // ray's direction octant yields a front-to-back order without sorting.
-//   codes  nibble j = code of the internal child at position j (8 for a leaf / empty position)
-//   vm     nibble j = bit 3: internal child; bits 0..2: valid primitives of the leaf at position j
-//          (primitive k of position j is element (primBase & 0x7fffffff) + 3 j + k of the primitive array: stride 3,
+//   codes  nibble m = code of the internal child at position j (8 for a leaf / empty position), m = nibbleOfPos(j)
+//   vm     nibble m = bit 3: internal child; bits 0..2: valid primitives of the leaf at position j
+//          (primitive k of that leaf is element (primBase & 0x7fffffff) + 3 m + k of the primitive array: stride 3,
 //          unused elements are never read)
 //   imask  bit c = an internal child with code c exists; child nodes are stored contiguously from childBase
 //          in code order
@@ -77,7 +78,16 @@ constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kInvalid = 0xffffffffu;
 constexpr int kMaxLeafPrims = 3;
 constexpr uint32_t kPrimGroupBit = 0x80000000u;   // Node8::primBase / traversal stack entries
-constexpr uint32_t kExpBias = 15;                 // Node8::ex/ey/ez hold e + 127 + kExpBias: the plane of byte q is p + q * 2^e
+// RG_HALF_SLAB (default): the traversal tests the children of a node TWO AT A TIME in packed binary16 arithmetic (rg_trace.cu pairTest):
+// children at positions 2i and 2i + 1 share every instruction, and their results land in the low / high half of one mask, so the nibbles of
+// codes / vm / the primitive group are dealt out as nibbleOfPos below.  0: one child at a time in binary32 (round 1 / 2 formulation).
+#ifndef RG_HALF_SLAB
+#define RG_HALF_SLAB 1
+#endif
+constexpr uint32_t kExpBias = RG_HALF_SLAB ? 0 : 15;   // Node8::ex/ey/ez hold e + 127 + kExpBias: the plane of byte q is p + q * 2^e
+// nibble of codes / vm (and the triple of primitive-array elements) that belongs to the child whose plane bytes sit at position j
+__host__ __device__ constexpr int nibbleOfPos(int j) { return RG_HALF_SLAB ? (j >> 1) + 4 * (j & 1) : j; }
+__host__ __device__ constexpr int posOfNibble(int m) { return RG_HALF_SLAB ? ((m & 3) << 1) | (m >> 2) : m; }   // the inverse
 constexpr uint32_t kLeafStride = 3;               // primitive array elements reserved per leaf child
 
 struct Hit { float t, u, v; uint32_t inst, prim; };
