@@ -259,6 +259,22 @@ struct WorldRayPool {   // structure-of-arrays: component k of context c at p[k 
     __device__ __forceinline__ float tmax() const { return p[7 * kPoolCtx]; }
 };
 
+// Where the traversal stack of a ray lives.  StackLocal: the thread's local memory (through L1).  StackHybrid<D>: the first D entries in
+// shared memory (entry i of thread t at sh[i * 128 + t]: conflict-free 64-bit accesses, no L1 lines, no write-backs of dead entries), the rest
+// -- deep trees only -- in local memory.
+struct StackLocal {
+    uint2* p;
+    __device__ __forceinline__ void put(int i, uint2 v) const { p[i] = v; }
+    __device__ __forceinline__ uint2 get(int i) const { return p[i]; }
+};
+template <int D>
+struct StackHybrid {
+    uint2* sh;   // + threadIdx.x already
+    uint2* p;    // local part: entries D..kStackSize-1
+    __device__ __forceinline__ void put(int i, uint2 v) const { if(i < D) sh[i * 128] = v; else p[i - D] = v; }
+    __device__ __forceinline__ uint2 get(int i) const { return i < D ? sh[i * 128] : p[i - D]; }
+};
+
 // Resumable closest-hit traversal.  The state of one ray lives in registers (+ a stack in local memory) and travStep advances
 // it by ONE node test and / or ONE primitive test, so a warp can hand a finished lane its next ray at any step, and can leave
 // the traversal loop to shade while some lanes are still on their way.
@@ -288,16 +304,16 @@ __device__ __forceinline__ void travInit(const TraceParams& P, Trav& T, Hit& hit
 
 // The three kinds of traversal work.  travNode: the 8 children of the next node of the lane's node group; leaves T.ng / T.tg = the hit
 // children / primitives of that node (primitives the lane still held are parked on its stack: postponed tests).
-template <bool COUNT>
-__device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, uint2* __restrict__ stack, const Hit& hit, float tmin, uint32_t* cnt) {
+template <bool COUNT, class ST>
+__device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, const ST& stack, const Hit& hit, float tmin, uint32_t* cnt) {
     RayCtx& r = T.r;
-    if(T.tg.y && T.sp < kStackSize) stack[T.sp++] = T.tg;
+    if(T.tg.y && T.sp < kStackSize) stack.put(T.sp++, T.tg);
     uint2 ng = T.ng;
     const int bit = 31 - __clz(ng.y);
     ng.y &= ~(1u << bit);
     const uint32_t slot = (uint32_t)(bit - 24) ^ r.octinv;
     const uint32_t rel = __popc(ng.y & 0xffu & ((1u << slot) - 1u));
-    if((ng.y & 0xff000000u) && T.sp < kStackSize) stack[T.sp++] = ng;
+    if((ng.y & 0xff000000u) && T.sp < kStackSize) stack.put(T.sp++, ng);
     const Node8* nodes = T.curInst != kInvalid ? P.blasNodes : P.tlasNodes;
     const uint4* np = reinterpret_cast<const uint4*>(nodes + (ng.x + rel));
     const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
@@ -424,8 +440,8 @@ __device__ __forceinline__ bool missesSphere(const float4 sph, float ox, float o
 // travPrim: ONE primitive of the lane's primitive group -- a triangle test inside an instance, entering an instance in the TLAS.
 // SPH: test the mesh's bounding sphere before entering an instance (pool scheduler: incoherent rays over many instances; the lanes
 // kernel leaves it out -- on the example scene the extra load and test in its hot loop cost 5 % and reject nothing)
-template <bool COUNT, bool SPH, class WR>
-__device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
+template <bool COUNT, bool SPH, class WR, class ST>
+__device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, const ST& stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
     RayCtx& r = T.r;
     const uint32_t bit = (uint32_t)(__ffs(T.tg.y) - 1);
     T.tg.y &= T.tg.y - 1u;
@@ -446,9 +462,9 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
                 // the oracle's ((1*ox + 0*oy) + 0*oz) + t is exactly ox + t
                 const float tox = __fadd_rn(ox, __uint_as_float(l0.w)), toy = __fadd_rn(oy, __uint_as_float(l1.w)), toz = __fadd_rn(oz, __uint_as_float(l2.w));
                 if(SPH && missesSphere(sph, tox, toy, toz, sdx, sdy, sdz)) return;
-                if(T.tg.y) stack[T.sp++] = T.tg;
-                if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
-                stack[T.sp++] = make_uint2(kInvalid, 0x1000u);
+                if(T.tg.y) stack.put(T.sp++, T.tg);
+                if(T.ng.y & 0xff000000u) stack.put(T.sp++, T.ng);
+                stack.put(T.sp++, make_uint2(kInvalid, 0x1000u));
                 r.ox = tox; r.oy = toy; r.oz = toz;
                 shear = r.kz == kNoShear;   // first instance of this ray
             } else {
@@ -466,13 +482,13 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
                 if((sdx == 0.0f && sdy == 0.0f && sdz == 0.0f) || (SPH && missesSphere(sph, oox, ooy, ooz, sdx, sdy, sdz))) {
                     enter = false;
                 } else {
-                    if(T.tg.y) stack[T.sp++] = T.tg;
-                    if(T.ng.y & 0xff000000u) stack[T.sp++] = T.ng;
+                    if(T.tg.y) stack.put(T.sp++, T.tg);
+                    if(T.ng.y & 0xff000000u) stack.put(T.sp++, T.ng);
                     // the world-space slab / shear constants ride on the stack while the instance is traversed
-                    stack[T.sp++] = make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy));
-                    stack[T.sp++] = make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx));
-                    stack[T.sp++] = make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz));
-                    stack[T.sp++] = make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8));
+                    stack.put(T.sp++, make_uint2(__float_as_uint(r.ix), __float_as_uint(r.iy)));
+                    stack.put(T.sp++, make_uint2(__float_as_uint(r.iz), __float_as_uint(r.Sx)));
+                    stack.put(T.sp++, make_uint2(__float_as_uint(r.Sy), __float_as_uint(r.Sz)));
+                    stack.put(T.sp++, make_uint2(kInvalid, r.octinv | ((uint32_t)r.kx << 4) | ((uint32_t)r.ky << 6) | ((uint32_t)r.kz << 8)));
                     setupSlab(r, oox, ooy, ooz, sdx, sdy, sdz);
                 }
             }
@@ -499,19 +515,19 @@ __device__ __forceinline__ void travPrim(const TraceParams& P, Trav& T, uint2* _
 }
 
 // travPop: the lane has neither nodes nor primitives at hand: next entry of its stack.  True when the stack is empty (ray done).
-template <class WR>
-__device__ __forceinline__ bool travPop(Trav& T, const uint2* __restrict__ stack, const WR& wray) {
+template <class WR, class ST>
+__device__ __forceinline__ bool travPop(Trav& T, const ST& stack, const WR& wray) {
     RayCtx& r = T.r;
     while(true) {
         if(T.sp == 0) return true;
-        T.ng = stack[--T.sp];
+        T.ng = stack.get(--T.sp);
         if(T.ng.x != kInvalid) break;
         // leave the instance: back to the world-space ray
         T.curInst = kInvalid;
         r.ox = wray.ox(); r.oy = wray.oy(); r.oz = wray.oz();
         if(!(T.ng.y & 0x1000u)) {   // a general instance: direction-derived constants come back from the stack
             r.octinv = T.ng.y & 7u; r.kx = (int)((T.ng.y >> 4) & 3u); r.ky = (int)((T.ng.y >> 6) & 3u); r.kz = (int)((T.ng.y >> 8) & 3u);
-            const uint2 c2 = stack[--T.sp], c1 = stack[--T.sp], c0 = stack[--T.sp];
+            const uint2 c2 = stack.get(--T.sp), c1 = stack.get(--T.sp), c0 = stack.get(--T.sp);
             r.ix = __uint_as_float(c0.x); r.iy = __uint_as_float(c0.y); r.iz = __uint_as_float(c1.x);
             r.Sx = __uint_as_float(c1.y); r.Sy = __uint_as_float(c2.x); r.Sz = __uint_as_float(c2.y);
         }
@@ -528,8 +544,8 @@ __device__ __forceinline__ bool travPop(Trav& T, const uint2* __restrict__ stack
 #ifndef RG_PRIM_LOOP_POOL
 #define RG_PRIM_LOOP_POOL 0
 #endif
-template <bool COUNT, bool SPH, class WR>
-__device__ __forceinline__ bool travStep(const TraceParams& P, Trav& T, uint2* __restrict__ stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
+template <bool COUNT, bool SPH, class WR, class ST>
+__device__ __forceinline__ bool travStep(const TraceParams& P, Trav& T, const ST& stack, Hit& hit, const WR& wray, float tmin, uint32_t* cnt) {
     if((T.ng.y & 0xff000000u) && !T.tg.y) travNode<COUNT>(P, T, stack, hit, tmin, cnt);
     if(!SPH || RG_PRIM_LOOP_POOL) { while(T.tg.y) travPrim<COUNT, SPH>(P, T, stack, hit, wray, tmin, cnt); }
     else if(T.tg.y) travPrim<COUNT, SPH>(P, T, stack, hit, wray, tmin, cnt);
@@ -1130,7 +1146,7 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
             if(!exhausted && freeCount >= RG_REFILL_THRESHOLD && rayCount == 0u) break;
             bool done = false;
             // (two steps per round of this loop -- half the votes and queue bookkeeping -- were measured: C3 43.2 -> 55.4 ms)
-            if(myCtx != kNoCtx) done = travStep<COUNT, true>(P, T, stack, hit, WorldRayPool{&W.ray[0][myCtx]}, tmin, cntT) || ++steps > kMaxStepsPerRay;
+            if(myCtx != kNoCtx) done = travStep<COUNT, true>(P, T, StackLocal{stack}, hit, WorldRayPool{&W.ray[0][myCtx]}, tmin, cntT) || ++steps > kMaxStepsPerRay;
             const uint32_t mDone = __ballot_sync(0xffffffffu, done);
             if(mDone) {
                 if(done) {   // park the closest hit; the lane is free for the next ray
@@ -1160,8 +1176,12 @@ __global__ void __launch_bounds__(128, RG_TRACE_MIN_BLOCKS) k_trace_pool(const T
 #ifndef RG_LANES_REFILL
 #define RG_LANES_REFILL 32       // idle lanes before a warp of the lanes kernel fetches new work items (swept 2..32: C2 7.9 ms at 2, 6.6 at 8, 5.4 at 20-28, 5.2 at 32)
 #endif
+#ifndef RG_LANES_SHSTACK
+#define RG_LANES_SHSTACK 0       // lanes kernel: traversal stack entries per ray kept in shared memory (0: all of them in local memory).  Measured: 8 / 12 / 16
+                                 // entries C2 4.21 ms against 3.56 (two predicated accesses per push / pop, and L1 loses what the carve-out takes): off
+#endif
 #ifndef RG_LANES_MIN_BLOCKS
-#define RG_LANES_MIN_BLOCKS 6   // 80 registers (~100 B of spills); swept 4..8 with the round-2 traversal loop: C2 4.23 / 4.06 / 3.98 / 3.96 / 4.34 ms
+#define RG_LANES_MIN_BLOCKS 7   // 72 registers (~150 B of spills); swept 5..8 with the binary16 node test: C2 3.74 / 3.68 / 3.55 / 3.66 ms, C5 13.19 / 12.93 / 12.48 / 12.73 ms
 #endif
 // The second scheduler, for COHERENT workloads: one context per lane, state in registers, frames in local memory.  A warp takes 32
 // consecutive work items (one sample index of one 8x4 tile), so its lanes trace neighbouring rays and then run the same shader
@@ -1197,7 +1217,14 @@ __global__ void __launch_bounds__(128, RG_LANES_MIN_BLOCKS) k_trace_lanes(const 
     const uint32_t total = myChunks * kChunkTiles * 32u * (SEQ ? 1u : S);
 
     float4 frames[kCtxQuads + (SEQ ? 3 : 0)];   // suspended shader invocations (local memory) [+ the pixel's sums]
-    uint2 stack[kStackSize];
+#if RG_LANES_SHSTACK
+    __shared__ uint2 s_stack[RG_LANES_SHSTACK * 128];
+    uint2 stackLocal[kStackSize - RG_LANES_SHSTACK];
+    const StackHybrid<RG_LANES_SHSTACK> stack{s_stack + tid, stackLocal};
+#else
+    uint2 stackLocal[kStackSize];
+    const StackLocal stack{stackLocal};
+#endif
     uint32_t cntT[CNT_N];
     if(COUNT) {
 #pragma unroll
@@ -1318,7 +1345,7 @@ __global__ void k_trace_rays(const TraceParams P, const float* __restrict__ rays
     uint32_t cnt[CNT_N];
     const WorldRayRegs wr{{q[0], q[1], q[2]}, {q[3], q[4], q[5]}, q[7]};
     travInit<true>(P, T, hit, q[0], q[1], q[2], q[3], q[4], q[5], q[7]);
-    for(uint32_t steps = 0; !travStep<false, true>(P, T, stack, hit, wr, q[6], cnt) && steps < kMaxStepsPerRay; ++steps) {}
+    for(uint32_t steps = 0; !travStep<false, true>(P, T, StackLocal{stack}, hit, wr, q[6], cnt) && steps < kMaxStepsPerRay; ++steps) {}
     tuv[3 * i] = hit.t; tuv[3 * i + 1] = hit.u; tuv[3 * i + 2] = hit.v;
     instPrim[2 * i] = hit.inst; instPrim[2 * i + 1] = hit.prim;
 }
