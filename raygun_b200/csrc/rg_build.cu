@@ -361,6 +361,13 @@ __device__ void quantizeNode(Node8& nd, const float (*clo)[3], const float (*chi
             qlo[a][s] = (uint8_t)ql; qhi[a][s] = (uint8_t)qh;
         }
     }
+#if RG_PLANE_DIFF
+    for(int a = 0; a < 3; ++a)
+        for(int w = 0; w < 2; ++w) {   // high words -> hi - lo (mod 2^32), see rg_types.cuh
+            uint32_t* h = reinterpret_cast<uint32_t*>(qhi[a]) + w;
+            *h -= reinterpret_cast<const uint32_t*>(qlo[a])[w];
+        }
+#endif
 }
 
 template <class LeafSource>

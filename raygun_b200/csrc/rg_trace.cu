@@ -168,6 +168,11 @@ __device__ __forceinline__ void childTest(uint32_t nx, uint32_t ny, uint32_t nz,
 
 #if RG_HALF_SLAB
 __device__ __forceinline__ __half2 asHalf2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t madlo(uint32_t a, uint32_t b, uint32_t c) {   // a * b + c as ONE IMAD (FMA pipe), opaque to the optimiser
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 // TWO children of a node (positions 2 PAIR and 2 PAIR + 1: bytes SEL of the plane words) in packed binary16 arithmetic: every
 // instruction serves both.  One PRMT puts a plane byte q into the low byte of each half: the SUBNORMAL 2^-24 q, exact, and HFMA2 takes
 // subnormal operands at full rate; the node-local scaling of travNode keeps every plane distance inside binary16's range.  The near
@@ -358,11 +363,28 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, const ST
     const float tn0 = fmaf(tmin, s, -t0s), tf0 = fmaf(hit.t, s, -t0s);
     const float tn1 = fmaf(fabsf(tn0), -kRelC, tn0) - kAbs, tf1 = fmaf(fabsf(tf0), kRelC, tf0) + kAbs;
     const __half2 htmn = __floats2half2_rn(tn1, tn1), htmx = __floats2half2_rn(tf1, tf1);
-    const uint32_t mx = (uint32_t)(__float_as_int(r.ix) >> 31), my = (uint32_t)(__float_as_int(r.iy) >> 31), mz = (uint32_t)(__float_as_int(r.iz) >> 31);
     const uint32_t vm = n1.w;
     // nibbles 0..n-1 of vm are the occupied ones and pair i holds nibbles i and i + 4: all four pairs are in use from n = 4 on, and
     // nodes nearly always have 8 children, so no pair is skipped (empty positions hold an inverted box and never hit)
     uint32_t hn = 0;
+#if RG_PLANE_DIFF
+    // near / far plane words by the sign of the direction: lo + s * (hi - lo) with s in {0, 1}, the difference words come from the builder
+    const uint32_t sx1 = __float_as_uint(r.ix) >> 31, sy1 = __float_as_uint(r.iy) >> 31, sz1 = __float_as_uint(r.iz) >> 31;
+    const uint32_t sx0 = madlo(sx1, 0xffffffffu, 1u), sy0 = madlo(sy1, 0xffffffffu, 1u), sz0 = madlo(sz1, 0xffffffffu, 1u);   // 1 - s
+    {
+        const uint32_t nx = madlo(sx1, n3.z, n2.x), fx = madlo(sx0, n3.z, n2.x), ny = madlo(sy1, n4.x, n2.z), fy = madlo(sy0, n4.x, n2.z),
+                       nz = madlo(sz1, n4.z, n3.x), fz = madlo(sz0, n4.z, n3.x);
+        pairTest<0x4140, 0>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
+        pairTest<0x4342, 1>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
+    }
+    {
+        const uint32_t nx = madlo(sx1, n3.w, n2.y), fx = madlo(sx0, n3.w, n2.y), ny = madlo(sy1, n4.y, n2.w), fy = madlo(sy0, n4.y, n2.w),
+                       nz = madlo(sz1, n4.w, n3.y), fz = madlo(sz0, n4.w, n3.y);
+        pairTest<0x4140, 2>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
+        pairTest<0x4342, 3>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
+    }
+#else
+    const uint32_t mx = (uint32_t)(__float_as_int(r.ix) >> 31), my = (uint32_t)(__float_as_int(r.iy) >> 31), mz = (uint32_t)(__float_as_int(r.iz) >> 31);
     {
         const uint32_t nx = bitsel(mx, n3.z, n2.x), fx = bitsel(mx, n2.x, n3.z), ny = bitsel(my, n4.x, n2.z), fy = bitsel(my, n2.z, n4.x),
                        nz = bitsel(mz, n4.z, n3.x), fz = bitsel(mz, n3.x, n4.z);
@@ -375,6 +397,7 @@ __device__ __forceinline__ void travNode(const TraceParams& P, Trav& T, const ST
         pairTest<0x4140, 2>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
         pairTest<0x4342, 3>(nx, ny, nz, fx, fy, fz, haxy, hazz, hcx, hcy, hcz, htmn, htmx, hn);
     }
+#endif
 #else
     // plane distance t = q * (2^e / d) + (p - o) / d.  The second term cancels against the first, so its rounding
     // error (relative to |(p - o) / d|, NOT to t) is what can make the slab test miss: widen near / far by that much.

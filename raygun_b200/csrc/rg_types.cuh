@@ -84,6 +84,12 @@ constexpr uint32_t kPrimGroupBit = 0x80000000u;   // Node8::primBase / traversal
 #ifndef RG_HALF_SLAB
 #define RG_HALF_SLAB 1
 #endif
+// RG_PLANE_DIFF (with RG_HALF_SLAB): the "high" plane words of a node hold hi - lo as 32-bit integers (mod 2^32), so that the traversal
+// picks the near / far planes of an axis by the ray's sign s in {0, 1} as lo + s * diff and lo + (1 - s) * diff: integer multiply-adds
+// on the FMA pipe instead of bit selects on the ALU pipe, which is the one the node step saturates.
+#ifndef RG_PLANE_DIFF
+#define RG_PLANE_DIFF RG_HALF_SLAB
+#endif
 constexpr uint32_t kExpBias = RG_HALF_SLAB ? 0 : 15;   // Node8::ex/ey/ez hold e + 127 + kExpBias: the plane of byte q is p + q * 2^e
 // nibble of codes / vm (and the triple of primitive-array elements) that belongs to the child whose plane bytes sit at position j
 __host__ __device__ constexpr int nibbleOfPos(int j) { return RG_HALF_SLAB ? (j >> 1) + 4 * (j & 1) : j; }
