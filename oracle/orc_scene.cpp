@@ -24,8 +24,15 @@ void buildRec(Bvh2& bvh, const std::vector<Box>& boxes, uint32_t first, uint32_t
         const float c[3] = {0.5f * (ib.lo[0] + ib.hi[0]), 0.5f * (ib.lo[1] + ib.hi[1]), 0.5f * (ib.lo[2] + ib.hi[2])};
         cb.grow(c);
     }
-    for(int a = 0; a < 3; ++a) {  // padded: the slab arithmetic is not exact
-        const float e = 2e-6f * std::max(std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])), b.hi[a] - b.lo[a]) + 1e-30f;
+    // padded: neither the slab arithmetic nor the triangle test is exact.  The padding of EVERY axis follows the largest coordinate of
+    // the box: the rounding noise of the watertight test scales with the operands of all three axes, so a flat box (a floor at y = 0)
+    // must not be padded by its own (zero) extent only -- a ray leaving such a plane with a tiny un-normalised direction is reported
+    // as a hit by the loop over all triangles (the definition) at a t that is pure noise, and the accelerator has to visit the leaf
+    // (found by tests/test_gpu_traversal.py::test_skewed_and_grazing_rays)
+    float m = 0.0f;
+    for(int a = 0; a < 3; ++a) m = std::max(m, std::max(std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])), b.hi[a] - b.lo[a]));
+    for(int a = 0; a < 3; ++a) {
+        const float e = 2e-6f * m + 1e-30f;
         bvh.nodes[nodeIdx].lo[a] = b.lo[a] - e; bvh.nodes[nodeIdx].hi[a] = b.hi[a] + e;
     }
     if(count <= 4) { bvh.nodes[nodeIdx].left = first; bvh.nodes[nodeIdx].count = count; return; }

@@ -72,6 +72,38 @@ def test_negative_zero_direction_components(example_scene, oracle_example):
     assert bad == 0, f"{bad} of {len(rays)} rays with -0 direction components differ from the oracle"
 
 
+def test_skewed_and_grazing_rays(example_scene, oracle_example):
+    """What the packed binary16 node test (rg_trace.cu pairTest) has to get right: direction components that differ by many orders of
+    magnitude (its node-local scaling follows the steepest axis, the fastest axis falls towards the subnormal range), rays that graze
+    flat geometry, origins thousands of node sizes away.  Closest hits stay bit-exact; tests/test_slab_half_model.py has the arithmetic."""
+    import raygun_b200 as rg
+    sd = example_scene
+    rt = rg.Raytracer(64, 36)
+    rt.load_scene(sd)
+    rays = _random_rays(sd, 9000, 21)
+    rng = np.random.default_rng(22)
+    n = len(rays)
+    rays[:, 3:6] *= (10.0 ** -rng.uniform(0, 9, (n, 3)) * (rng.random((n, 3)) < 0.6) + (rng.random((n, 3)) >= 0.6)).astype(np.float32)
+    rays[:, 3:6] = np.where(np.abs(rays[:, 3:6]).max(axis=1, keepdims=True) > 0, rays[:, 3:6], np.float32(1.0))
+    graze = np.arange(0, n, 5)                      # nearly inside the plane of the triangle the origin sits on: y barely moves
+    rays[graze, 4] = rays[graze, 4] * np.float32(1e-6)
+    far = np.arange(3, n, 9)                        # the same line, started far behind
+    nrm = np.linalg.norm(rays[far, 3:6].astype(np.float64), axis=1, keepdims=True)
+    rays[far, :3] = (rays[far, :3] - rays[far, 3:6] / nrm * (10.0 ** rng.uniform(1, 4, (len(far), 1)))).astype(np.float32)
+    rays[far, 7] = np.float32(3.0e38)
+    tuv, ip = rt.debug_trace_rays(rays)
+    bad = []
+    for k in range(n):
+        hit, t, u, v, inst, prim = oracle_example.closest_hit(rays[k, :3], rays[k, 3:6], 0.01, float(rays[k, 7]), brute=(k % 8 == 0))
+        if hit:
+            ok = ip[k, 0] == inst and ip[k, 1] == prim and tuv[k, 0] == np.float32(t) and tuv[k, 1] == np.float32(u) and tuv[k, 2] == np.float32(v)
+        else:
+            ok = ip[k, 0] == 0xffffffff
+        if not ok:
+            bad.append((k, hit, t, inst, prim, int(ip[k, 0]), int(ip[k, 1]), float(tuv[k, 0])))
+    assert not bad, f"{len(bad)} of {n} skewed / grazing rays differ from the oracle, first: {bad[:5]}"
+
+
 def _torture_scene(S, seed=3):
     """Three meshes (a triangle soup with degenerate, duplicated, tiny and huge triangles; a box; one triangle) under 48 instances with
     rotations, non-uniform and NEGATIVE scales, shear, pure translations, exact duplicates (ties on the instance id), tiny and large scales."""
