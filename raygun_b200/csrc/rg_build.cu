@@ -305,8 +305,8 @@ __global__ void k_reset_flags(uint32_t* flags, uint32_t n) {
 
 // ---------------------------------------------------------------------------------------------
 // Collapse the binary tree into 8-wide compressed nodes; one thread per wide node, level by level.
-struct LeafSourceTri { const float4* vertices; const uint32_t* indices; uint32_t vtxOff, idxOff; Tri* out; };
-struct LeafSourceInst { const InstTrav* inst; InstTrav* out; };
+struct LeafSourceTri { static constexpr uint32_t kMaxPrims = kMaxLeafTris; const float4* vertices; const uint32_t* indices; uint32_t vtxOff, idxOff; Tri* out; };
+struct LeafSourceInst { static constexpr uint32_t kMaxPrims = kMaxLeafInsts; const InstTrav* inst; InstTrav* out; };
 
 __device__ __forceinline__ uint32_t refCount(uint32_t ref, const uint2* range) {
     if(ref & kLeafBit) return 1u;
@@ -401,13 +401,13 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
     if(bref & kLeafBit) { fetch(0, bref); n = 1; }
     else { const BNode root = bnodes[bref]; fetch(0, root.left); fetch(1, root.right); n = 2; }
 
-    // phase 0: open subtrees with more than kMaxLeafPrims primitives (largest surface first);
+    // phase 0: open subtrees with more than LeafSource::kMaxPrims primitives (largest surface first);
     // phase 1: with free slots left, open small subtrees too (tighter boxes, one primitive per slot).
     for(int phase = 0; phase < 2; ++phase) {
         while(n < 8) {
             int best = -1; float bestArea = -1.0f;
             for(int k = 0; k < n; ++k) {
-                const bool open = phase == 0 ? (cCnt[k] > (uint32_t)kMaxLeafPrims) : (cCnt[k] > 1u);
+                const bool open = phase == 0 ? (cCnt[k] > LeafSource::kMaxPrims) : (cCnt[k] > 1u);
                 if(open && cArea[k] > bestArea) { bestArea = cArea[k]; best = k; }
             }
             if(best < 0) break;
@@ -456,7 +456,7 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
     uint32_t nLeaf = 0, nInternal = 0;
     for(int s = 0; s < 8; ++s) childOfSlot[s] = -1;
     for(int k = 0; k < n; ++k) {
-        isInner[k] = cCnt[k] > (uint32_t)kMaxLeafPrims;
+        isInner[k] = cCnt[k] > LeafSource::kMaxPrims;
         if(!isInner[k]) posOfChild[k] = posOfNibble((int)nLeaf++);
         childOfSlot[slotOfChild[k]] = k;
     }
@@ -667,7 +667,7 @@ __global__ void k_requantize(uint32_t nWide, Node8* __restrict__ nodes, uint32_t
         loadRefBox(r, bnodes, primBox, vals, clo[n], chi[n]);
         posOfChild[n++] = j;
         const uint32_t cnt = refCount(r, range);
-        if(cnt <= (uint32_t)kMaxLeafPrims) {
+        if(cnt <= LeafSource::kMaxPrims) {
             const uint32_t first = refFirst(r, range);
             for(uint32_t k = 0; k < cnt; ++k) writeLeafPrim(leafSrc, pb + kLeafStride * (uint32_t)nibbleOfPos(j) + k, vals[first + k]);
         }

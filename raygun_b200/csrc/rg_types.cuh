@@ -76,7 +76,17 @@ static_assert(sizeof(BNode) == 32, "BNode");
 
 constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kInvalid = 0xffffffffu;
-constexpr int kMaxLeafPrims = 3;
+// Primitives per leaf child (<= 3: a leaf child owns three bits of its vm nibble).  Measured with the binary16 node test (C2 / C3 / C4
+// trace ms): 3 triangles and 3 instances 3.55 / 41.1 / 23.1; 2 and 2: 3.51 / 40.0 / 21.3; 1 and 1: 3.59 / 38.4 / 20.4 -- entering an
+// instance (ray transform, set-up, BLAS root) costs far more than one more box in a TLAS node, a triangle test about as much as a
+// third of a node step.
+#ifndef RG_MAX_LEAF_TRIS
+#define RG_MAX_LEAF_TRIS 2
+#endif
+#ifndef RG_MAX_LEAF_INSTS
+#define RG_MAX_LEAF_INSTS 1
+#endif
+constexpr int kMaxLeafTris = RG_MAX_LEAF_TRIS, kMaxLeafInsts = RG_MAX_LEAF_INSTS;
 constexpr uint32_t kPrimGroupBit = 0x80000000u;   // Node8::primBase / traversal stack entries
 // RG_HALF_SLAB (default): the traversal tests the children of a node TWO AT A TIME in packed binary16 arithmetic (rg_trace.cu pairTest):
 // children at positions 2i and 2i + 1 share every instruction, and their results land in the low / high half of one mask, so the nibbles of
