@@ -103,6 +103,35 @@ __global__ void k_inst_boxes(const InstShade* __restrict__ inst, const float* __
     d_inst_boxes(blockIdx.x * blockDim.x + threadIdx.x, inst, meshBoxes, nInst, primBox, sceneBox);
 }
 
+// The world box of an instance, cut down to the box of its mesh's bounding sphere mapped by the 3x4 (an ellipsoid: half extent r |row| per
+// axis around the mapped centre).  The corner box of a rotated mesh box is up to sqrt(2) (sqrt(3)) times too wide per axis; for round
+// meshes the sphere box is exact under any rotation.  Runs AFTER the Morton keys were taken from the corner boxes (their order stays
+// bit-identical to the oracle's) and before the refit, so only the boxes the TLAS nodes are quantised from shrink.  Conservative: radius
+// and centre carry their rounding errors outwards, and the result is the intersection of two boxes that both contain the mesh.
+__device__ __forceinline__ void d_tighten_inst_box(uint32_t i, const InstShade* __restrict__ inst, const float4* __restrict__ meshSpheres, uint32_t nMeshes,
+                                                   Aabb* __restrict__ primBox) {
+    const InstShade in = inst[i];
+    if(!meshSpheres || in.mesh >= nMeshes) return;
+    const float4 sph = meshSpheres[in.mesh];
+    if(!(sph.w < 3.0e38f)) return;   // no sphere for this mesh (k_mesh_sphere_store)
+    const float r = sqrtf(sph.w) * 1.000002f;
+    Aabb b = primBox[i];
+#pragma unroll
+    for(int a = 0; a < 3; ++a) {
+        const float m0 = in.o2w[4 * a], m1 = in.o2w[4 * a + 1], m2 = in.o2w[4 * a + 2], m3 = in.o2w[4 * a + 3];
+        const float wc = fmaf(m0, sph.x, fmaf(m1, sph.y, fmaf(m2, sph.z, m3)));
+        const float len = sqrtf(fmaf(m0, m0, fmaf(m1, m1, m2 * m2)));
+        const float e = r * len * 1.000002f + 4.0e-7f * (fabsf(m0 * sph.x) + fabsf(m1 * sph.y) + fabsf(m2 * sph.z) + fabsf(m3));
+        b.lo[a] = fmaxf(b.lo[a], wc - e); b.hi[a] = fminf(b.hi[a], wc + e);
+    }
+    primBox[i] = b;
+}
+__global__ void k_tighten_inst_boxes(const InstShade* __restrict__ inst, const float4* __restrict__ meshSpheres, uint32_t nMeshes, uint32_t nInst,
+                                     Aabb* __restrict__ primBox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if(i < nInst) d_tighten_inst_box(i, inst, meshSpheres, nMeshes, primBox);
+}
+
 __device__ __forceinline__ void d_morton(uint32_t p, const Aabb* __restrict__ primBox, uint32_t n, const int32_t* __restrict__ sceneBox,
                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     if(p >= n) return;
@@ -610,6 +639,7 @@ __global__ void __launch_bounds__(1024) k_tlas_fused(const TlasFusedArgs A) {
     for(uint32_t i = tid; i < n; i += nt) d_morton(i, A.primBox, n, A.sceneBox, A.keys0, A.vals0);
     __syncthreads();
     for(uint32_t i = tid; i < n; i += nt) {   // rank sort by (key, index): the order of a stable sort
+        d_tighten_inst_box(i, A.shade, A.meshSpheres, A.nMeshes, A.primBox);   // the keys are taken; the boxes are next read by the refit
         const uint32_t ki = A.keys0[i];
         uint32_t rank = 0;
         for(uint32_t j = 0; j < n; ++j) { const uint32_t kj = A.keys0[j]; rank += (kj < ki || (kj == ki && j < i)) ? 1u : 0u; }
@@ -788,9 +818,11 @@ void LbvhScratch::release() {
 }
 
 namespace {
-void lbvhCommon(LbvhScratch& s, uint32_t n, cudaStream_t st) {
+struct TightenArgs { const InstShade* inst; const float4* meshSpheres; uint32_t nMeshes; };
+void lbvhCommon(LbvhScratch& s, uint32_t n, cudaStream_t st, const TightenArgs* tighten = nullptr) {
     k_morton<<<cdiv(n, 256), 256, 0, st>>>(s.primBox, n, s.sceneBox, s.keys[0], s.vals[0]);
     s.launches++;
+    if(tighten) { k_tighten_inst_boxes<<<cdiv(n, 128), 128, 0, st>>>(tighten->inst, tighten->meshSpheres, tighten->nMeshes, n, s.primBox); s.launches++; }
     radixSort(s, n, st);
     if(n >= 2) {
         k_hierarchy<<<cdiv(n - 1, 128), 128, 0, st>>>(s.keys[s.sortedBuf], n, s.bnodes, s.range, s.parent, s.flags);
@@ -871,7 +903,8 @@ void buildTlas(LbvhScratch& s, const rg_instance* raw, uint32_t nInst, const uin
     k_init_build<<<1, 32, 0, st>>>(s.sceneBox, s.counters);
     k_inst_boxes<<<cdiv(n, 128), 128, 0, st>>>(instShade, meshBoxes, n, s.primBox, s.sceneBox);
     s.launches += 3;
-    lbvhCommon(s, n, st);
+    const TightenArgs tighten{instShade, meshSpheres, nMeshes};
+    lbvhCommon(s, n, st, &tighten);
     LeafSourceInst ls{instTrav, tlasLeavesOut};
     collapseGrid(s, n, tlasNodes, 0, 0, ls, st);   // fully asynchronous
 }
