@@ -432,7 +432,10 @@ __device__ void collapseItem(const uint2 it, uint2* __restrict__ queueOut, uint3
 
     // phase 0: open subtrees with more than LeafSource::kMaxPrims primitives (largest surface first);
     // phase 1: with free slots left, open small subtrees too (tighter boxes, one primitive per slot).
-    for(int phase = 0; phase < 2; ++phase) {
+#ifndef RG_COLLAPSE_PHASES
+#define RG_COLLAPSE_PHASES 2
+#endif
+    for(int phase = 0; phase < RG_COLLAPSE_PHASES; ++phase) {
         while(n < 8) {
             int best = -1; float bestArea = -1.0f;
             for(int k = 0; k < n; ++k) {
