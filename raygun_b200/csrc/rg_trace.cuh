@@ -13,7 +13,10 @@ constexpr int kStackSize = 48;     // traversal stack entries (uint2) per ray: T
 constexpr int kPoolCtx = RG_POOL_CTX;   // ray-tree contexts (pixel samples in progress) per warp
 constexpr int kCtxQuads = kMaxFrames * 8 + 2;   // float4 per context in global memory: 8 per frame + the payload members only observable at recDepth 0
 constexpr int kMaxPeers = 8;        // GPUs of one node
-constexpr uint32_t kChunkTiles = 16; // tiles per round-robin chunk in partitioned mode
+#ifndef RG_CHUNK_TILES
+#define RG_CHUNK_TILES 16
+#endif
+constexpr uint32_t kChunkTiles = RG_CHUNK_TILES; // tiles per round-robin chunk in partitioned mode
 
 struct TraceParams {
     const Node8* tlasNodes;

@@ -104,6 +104,11 @@ constexpr uint32_t kExpBias = RG_HALF_SLAB ? 0 : 15;   // Node8::ex/ey/ez hold e
 // nibble of codes / vm (and the triple of primitive-array elements) that belongs to the child whose plane bytes sit at position j
 __host__ __device__ constexpr int nibbleOfPos(int j) { return RG_HALF_SLAB ? (j >> 1) + 4 * (j & 1) : j; }
 __host__ __device__ constexpr int posOfNibble(int m) { return RG_HALF_SLAB ? ((m & 3) << 1) | (m >> 2) : m; }   // the inverse
+static_assert(posOfNibble(nibbleOfPos(0)) == 0 && posOfNibble(nibbleOfPos(1)) == 1 && posOfNibble(nibbleOfPos(2)) == 2 && posOfNibble(nibbleOfPos(3)) == 3 &&
+              posOfNibble(nibbleOfPos(4)) == 4 && posOfNibble(nibbleOfPos(5)) == 5 && posOfNibble(nibbleOfPos(6)) == 6 && posOfNibble(nibbleOfPos(7)) == 7,
+              "posOfNibble must invert nibbleOfPos");
+static_assert(!RG_HALF_SLAB || (nibbleOfPos(0) == 0 && nibbleOfPos(1) == 4 && nibbleOfPos(2) == 1 && nibbleOfPos(3) == 5),
+              "pair i = positions 2i, 2i + 1 = nibbles i, i + 4 (the low / high half of pairTest's mask)");
 constexpr uint32_t kLeafStride = 3;               // primitive array elements reserved per leaf child
 
 struct Hit { float t, u, v; uint32_t inst, prim; };
