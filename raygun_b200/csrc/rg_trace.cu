@@ -912,8 +912,9 @@ __device__ __forceinline__ int shadeContext(const TraceParams& P, const ShadeCon
             continue;
         }
         const float4 qDiff = f.ld(Q_DIFF_TRANSP), qSpec = f.ld(Q_SPEC_REFL);
-        float4 qBase = f.ld(Q_BASE_ROUGH), qRcol = f.ld(Q_RCOL_RDEPTH);
         int stage = (flags >> 8) & 0xff;
+        // the reflection result is stored when the refraction ray is issued: earlier stages compute it below (and never read the slot)
+        float4 qBase = f.ld(Q_BASE_ROUGH), qRcol = stage >= ST_REFRACT_RET_FRONT ? f.ld(Q_RCOL_RDEPTH) : make_float4(1.0f, 1.0f, 1.0f, 0.0f);
         const bool frontFacing = ((flags >> 16) & 1) != 0;
         const int rc = (flags >> 20) & 0xff;
         const V3 D = v3(qDir.x, qDir.y, qDir.z), n = v3(qN.x, qN.y, qN.z);
