@@ -15,8 +15,11 @@ Workload (both arms use the same rule, so their `config` objects are identical):
 
   value   device-resident: instances / UBO already in HBM, nothing read back; CUDA-event time on the library's stream,
           max over ranks; L2 flushed (256 MiB memset) before every timed frame.
-  e2e     the same frame through the public host API (rg_set_ubo + rg_set_instances from host memory, rg_render,
-          read-back of the RGBA8 frame into pinned host memory), wall clock, max over ranks; L2 flushed before every frame too.
+  e2e     the same frame through the public host API (rg_set_ubo + rg_set_instances from host memory, rg_render, the RGBA8
+          frame in pinned host memory when the step ends), wall clock, max over ranks; L2 flushed before every frame too.
+          N = 1: the final kernel stores the frame straight into the pinned host buffer (rg_set_gather_target on host memory:
+          the 8.3 MB cross PCIe as the kernel's own stores, no separate copy; --e2e-copy times the cudaMemcpy read-back
+          instead); after the timed loop the buffer is compared with a regular rg_read_rgba8 of the same frame.
   N > 1   one process per GPU (torchrun); the frame is split into N column bands for the post chain, the trace is dealt
           round-robin in tile chunks and every finished pixel is stored straight into its owners' G-buffers over NVLink
           (CUDA IPC mappings); every band's RGBA8 pixels are stored by the final kernel into rank 0's frame buffer.
@@ -250,6 +253,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-copy", action="store_true", help="N = 1: time the e2e read-back as a cudaMemcpy instead of the zero-copy host frame")
     ap.add_argument("--split", default="columns", choices=["columns", "rows"])
     ap.add_argument("--mgpu", default="partition", choices=["partition", "overdraw"],
                     help="N > 1: 'partition' = tiles traced round-robin, G-buffer pixels stored to their owners over NVLink; 'overdraw' = every band re-traces its halo")
@@ -352,9 +356,12 @@ def main():
     # ---------------- timed: end to end through the host API (same L2 flush per frame as above, so e2e >= value at every N)
     out_pinned = torch.empty((H, W, 4) if rank == 0 and world > 1 else (rt.region_size[1], rt.region_size[0], 4), dtype=torch.uint8, pin_memory=True)
     out_np = out_pinned.numpy()
+    zero_copy = world == 1 and not args.e2e_copy
+    if zero_copy:
+        rt.set_gather_target(out_pinned.data_ptr())   # pinned host memory is device-addressable (UVA): k_fxaa_blit writes it directly
     for _ in range(2):
         rt.render_frame(ubo, flags, inst_raw)
-        rt.read_rgba8(out_np) if world == 1 else rt.sync()
+        rt.read_rgba8(out_np) if world == 1 and not zero_copy else rt.sync()
     barrier()
     t0 = time.perf_counter()
     flush_s = 0.0
@@ -366,7 +373,9 @@ def main():
         rt.updateRenderTarget(ubo)          # 192 B host -> device
         rt.setupTopLevelAS(inst_raw)        # n x 64 B host -> device (pinned staging inside the library)
         rt.doRaytracing(flags)
-        if world == 1:
+        if zero_copy:
+            rt.sync()                       # the frame is in out_pinned: the last kernel stored it there
+        elif world == 1:
             rt.read_rgba8(out_np)           # RGBA8 frame device -> pinned host
         else:
             rt.sync()
@@ -377,6 +386,10 @@ def main():
     e2e_ms = (time.perf_counter() - t0 - flush_s) * 1e3
     h2d = 192 + inst_raw.nbytes
     d2h = W * H * 4
+    if zero_copy:   # untimed: the frame the kernel stored into host memory is the frame a read-back returns
+        rt.set_gather_target(0)
+        if not np.array_equal(out_np, rt.read_rgba8()):
+            raise RuntimeError("bench: the zero-copy host frame differs from rg_read_rgba8")
 
     # ---------------- reduce over ranks: max time, summed rays
     tk = float(np.mean(trace_ms_frames))
@@ -508,7 +521,9 @@ def main():
                 "sections_ms": {k: v / args.steps for k, v in sections.items()}, "wall_ms_per_step_incl_flush": wall_ms / args.steps,
                 "clocks": clocks,
                 "e2e": {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "frame_to_host": ("stored by the final kernel into pinned host memory (zero-copy), verified against rg_read_rgba8 after the loop" if zero_copy
+                                          else ("cudaMemcpy read-back into pinned host memory" if world == 1 else "peer stores into rank 0's frame, read back by rank 0"))},
                 "gpu_launches": int(launches_total), "roofline": roofline}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline

@@ -231,7 +231,9 @@ int rg_sync_error(rg_ctx* ctx);
 
 /* Tile gather over NVLink: the final kernel (FXAA + 8-bit convert) stores this context's region
  * straight into `d_target` (a width x height RGBA8 frame that may live on a PEER GPU: either a
- * pointer in the same process with peer access enabled, or one opened from a CUDA IPC handle). */
+ * pointer in the same process with peer access enabled, or one opened from a CUDA IPC handle).
+ * Pinned host memory works as well (unified addressing): the frame then reaches the host as the
+ * kernel's own stores over PCIe, without a separate copy -- valid after rg_sync (bench.py, e2e). */
 int rg_set_gather_target(rg_ctx* ctx, void* d_target_rgba8);   /* rg_resize clears it: the buffer has the old frame's stride */
 /* 64-byte cudaIpcMemHandle_t of this context's full-frame gather buffer (allocated on demand) and
  * its opening on another process' context. */
