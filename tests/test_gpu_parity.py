@@ -677,3 +677,27 @@ def test_random_materials_lights_and_cameras(rgmod, O, S, example_scene, seed):
         for a, b in (("rays_primary", "primary"), ("rays_shadow", "shadow"), ("rays_reflect", "reflect"), ("rays_refract", "refract"), ("sky_lookups", "skylookup")):
             assert abs(tm[a] - c[b]) <= max(4, 2e-4 * c[b]), (a, tm[a], c[b])
         rt.close()
+
+
+def test_frame_stored_into_pinned_host_memory(rgmod, S, example_scene):
+    """rg_set_gather_target on PINNED HOST memory (unified addressing): the final kernel stores the RGBA8 frame there itself, no copy --
+    bench.py's e2e path at N = 1.  The host buffer must equal a regular rg_read_rgba8 of the same frame, with and without FXAA, and a
+    cleared target must stop the stores (replaces the blit + present of render_system.cpp:130-159 for a headless consumer)."""
+    import torch
+    rg = rgmod
+    W, H = 320, 180
+    rt = rg.Raytracer(W, H)
+    rt.load_scene(example_scene)
+    inst = rt.pack_instances(example_scene.inst_xform, example_scene.inst_meta)
+    host = torch.zeros((H, W, 4), dtype=torch.uint8, pin_memory=True)
+    rt.set_gather_target(host.data_ptr())
+    for ns, flags in ((1, rg.RG_FXAA), (4, 0)):
+        rt.render_frame(S.example_ubo(W, H, num_samples=ns), flags, inst)
+        rt.sync()
+        assert np.array_equal(host.numpy(), rt.read_rgba8()), (ns, flags)
+    rt.set_gather_target(0)
+    host.zero_()
+    rt.render_frame(S.example_ubo(W, H, num_samples=1), rg.RG_FXAA, inst)
+    rt.sync()
+    assert not host.numpy().any()
+    rt.close()
