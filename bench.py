@@ -20,6 +20,9 @@ Workload (both arms use the same rule, so their `config` objects are identical):
           N = 1: the final kernel stores the frame straight into the pinned host buffer (rg_set_gather_target on host memory:
           the 8.3 MB cross PCIe as the kernel's own stores, no separate copy; --e2e-copy times the cudaMemcpy read-back
           instead); after the timed loop the buffer is compared with a regular rg_read_rgba8 of the same frame.
+          N > 1: ONE frame in POSIX shared memory, page-locked and mapped by every rank (rg_host_frame_register): every GPU stores
+          its band into it over its own PCIe link and rank 0 reads the assembled frame without a copy; compared after the loop
+          with the frame gathered over NVLink into rank 0's device buffer (--e2e-copy times that path instead).
   N > 1   one process per GPU (torchrun); the frame is split into N column bands for the post chain, the trace is dealt
           round-robin in tile chunks and every finished pixel is stored straight into its owners' G-buffers over NVLink
           (CUDA IPC mappings); every band's RGBA8 pixels are stored by the final kernel into rank 0's frame buffer.
@@ -253,7 +256,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-copy", action="store_true", help="N = 1: time the e2e read-back as a cudaMemcpy instead of the zero-copy host frame")
+    ap.add_argument("--e2e-copy", action="store_true", help="time the e2e read-back as a cudaMemcpy (N > 1: of rank 0's gathered frame) instead of the zero-copy host frame")
     ap.add_argument("--split", default="columns", choices=["columns", "rows"])
     ap.add_argument("--mgpu", default="partition", choices=["partition", "overdraw"],
                     help="N > 1: 'partition' = tiles traced round-robin, G-buffer pixels stored to their owners over NVLink; 'overdraw' = every band re-traces its halo")
@@ -274,7 +277,7 @@ def main():
 
     import torch
     import raygun_b200 as rg
-    from raygun_b200.parallel import band_region, share_gather_handle, overdraw, attach_partition
+    from raygun_b200.parallel import band_region, share_gather_handle, overdraw, attach_partition, open_shared_host_frame
 
     dist = None
     if world > 1:
@@ -298,7 +301,7 @@ def main():
         attach_partition(dist, rt, rank, world)
 
     # gather target: rank 0's full-frame buffer, mapped into every other rank through CUDA IPC (NVLink peer stores)
-    peer_ptr = None
+    peer_ptr = own = None
     if world > 1:
         handle = None
         if rank == 0:
@@ -357,8 +360,18 @@ def main():
     out_pinned = torch.empty((H, W, 4) if rank == 0 and world > 1 else (rt.region_size[1], rt.region_size[0], 4), dtype=torch.uint8, pin_memory=True)
     out_np = out_pinned.numpy()
     zero_copy = world == 1 and not args.e2e_copy
+    shared = None
     if zero_copy:
         rt.set_gather_target(out_pinned.data_ptr())   # pinned host memory is device-addressable (UVA): k_fxaa_blit writes it directly
+    elif world > 1 and not args.e2e_copy:
+        # one frame in POSIX shared memory, mapped by every rank: each GPU stores its band over its own PCIe link, rank 0 reads no copy
+        def agree(ok):
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item())
+        shared = open_shared_host_frame(dist, rt, rank, W, H, agree)   # None on every rank if any rank could not: the copy path below
+        if shared is not None:
+            rt.set_gather_target(shared.device_ptr)
     for _ in range(2):
         rt.render_frame(ubo, flags, inst_raw)
         rt.read_rgba8(out_np) if world == 1 and not zero_copy else rt.sync()
@@ -377,6 +390,9 @@ def main():
             rt.sync()                       # the frame is in out_pinned: the last kernel stored it there
         elif world == 1:
             rt.read_rgba8(out_np)           # RGBA8 frame device -> pinned host
+        elif shared is not None:
+            rt.sync()
+            dist.barrier()                  # all bands have landed in the shared host frame (shared.array on rank 0)
         else:
             rt.sync()
             dist.barrier()                  # all bands have landed in rank 0's frame buffer
@@ -390,6 +406,18 @@ def main():
         rt.set_gather_target(0)
         if not np.array_equal(out_np, rt.read_rgba8()):
             raise RuntimeError("bench: the zero-copy host frame differs from rg_read_rgba8")
+    shared_used = shared is not None
+    if shared is not None:   # untimed: the same frame once more through rank 0's device buffer (NVLink peer stores) and a read-back
+        host_frame = shared.array.copy() if rank == 0 else None
+        rt.set_gather_target(own if rank == 0 else peer_ptr)
+        barrier()
+        rt.render_frame(ubo, flags, inst_raw)
+        barrier()
+        if rank == 0:
+            rt.read_gathered_rgba8(out_np)
+            if not np.array_equal(out_np, host_frame):
+                raise RuntimeError("bench: the shared host frame differs from the frame gathered in rank 0's device buffer")
+        shared.close()
 
     # ---------------- reduce over ranks: max time, summed rays
     tk = float(np.mean(trace_ms_frames))
@@ -523,7 +551,10 @@ def main():
                 "e2e": {"value": rays_total / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "frame_to_host": ("stored by the final kernel into pinned host memory (zero-copy), verified against rg_read_rgba8 after the loop" if zero_copy
-                                          else ("cudaMemcpy read-back into pinned host memory" if world == 1 else "peer stores into rank 0's frame, read back by rank 0"))},
+                                          else ("cudaMemcpy read-back into pinned host memory" if world == 1 else
+                                                ("every rank's final kernel stores its band into ONE frame in POSIX shared memory (page-locked, mapped by every rank): no copy; "
+                                                 "verified against the frame gathered over NVLink after the loop" if shared_used else
+                                                 "peer stores into rank 0's frame, read back by rank 0")))},
                 "gpu_launches": int(launches_total), "roofline": roofline}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline

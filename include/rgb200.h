@@ -19,6 +19,7 @@
 #ifndef RGB200_H
 #define RGB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -235,6 +236,14 @@ int rg_sync_error(rg_ctx* ctx);
  * Pinned host memory works as well (unified addressing): the frame then reaches the host as the
  * kernel's own stores over PCIe, without a separate copy -- valid after rg_sync (bench.py, e2e). */
 int rg_set_gather_target(rg_ctx* ctx, void* d_target_rgba8);   /* rg_resize clears it: the buffer has the old frame's stride */
+/* Page-lock and map `bytes` of ordinary host memory (page aligned: a POSIX shared-memory mapping, a
+ * malloc'ed frame) so that it can serve as a gather target; *d_ptr is the address to pass to
+ * rg_set_gather_target.  With one mapping of the same shared-memory frame per process, every GPU of
+ * a node stores its band of the frame into host memory over its own PCIe link and the consumer reads
+ * the assembled frame without any copy (bench.py, e2e at N > 1).  No reference counterpart (the
+ * reference presents through the swapchain, render_system.cpp:130-159). */
+int rg_host_frame_register(rg_ctx* ctx, void* host_ptr, size_t bytes, void** d_ptr);
+int rg_host_frame_unregister(rg_ctx* ctx, void* host_ptr);
 /* 64-byte cudaIpcMemHandle_t of this context's full-frame gather buffer (allocated on demand) and
  * its opening on another process' context. */
 int rg_gather_buffer_export(rg_ctx* ctx, void* handle64, void** d_ptr);

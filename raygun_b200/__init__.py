@@ -39,6 +39,7 @@ ABI_SYMBOLS = (
     "rg_gather_buffer_open", "rg_gather_buffer_close", "rg_read_gathered_rgba8", "rg_debug_blas_sort", "rg_debug_tlas_sort", "rg_debug_trace_rays",
     "rg_debug_bvh_stats", "rg_debug_upload_gbuffer", "rg_debug_run_post", "rg_launch_count", "rg_timer_begin", "rg_timer_end", "rg_flush_l2", "rg_debug_last_trace_rays_ms",
     "rg_set_trace_scheduler", "rg_set_entities", "rg_set_entities_device", "rg_debug_read_instances", "rg_physics_step_spheres", "rg_set_partition", "rg_peer_export", "rg_peer_attach", "rg_peer_detach_all", "rg_sync_error",
+    "rg_host_frame_register", "rg_host_frame_unregister",
 )
 
 
@@ -287,6 +288,15 @@ class Raytracer:
 
     def sync_error(self) -> int:
         return int(self.lib.rg_sync_error(self.h))
+
+    def host_frame_register(self, host_ptr: int, nbytes: int) -> int:
+        """Page-lock + map host memory (e.g. a shared-memory frame); returns the address for set_gather_target."""
+        p = C.c_void_p()
+        self._ck(self.lib.rg_host_frame_register(self.h, C.c_void_p(host_ptr), C.c_size_t(nbytes), C.byref(p)))
+        return p.value
+
+    def host_frame_unregister(self, host_ptr: int):
+        self._ck(self.lib.rg_host_frame_unregister(self.h, C.c_void_p(host_ptr)))
 
     def set_gather_target(self, dptr):
         self._ck(self.lib.rg_set_gather_target(self.h, C.c_void_p(dptr or 0)))

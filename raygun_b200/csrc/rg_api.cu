@@ -814,6 +814,31 @@ int rg_set_gather_target(rg_ctx* ctx, void* d_target_rgba8) {
     return 0;
 }
 
+int rg_host_frame_register(rg_ctx* ctx, void* host_ptr, size_t bytes, void** d_ptr) {
+    if(!ctx || !host_ptr || !bytes || !d_ptr) return fail(ctx, "rg_host_frame_register: null");
+    USE_DEVICE();
+    const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+    if(e != cudaSuccess) { cudaGetLastError(); return fail(ctx, "rg_host_frame_register: cudaHostRegister failed: %s", cudaGetErrorString(e)); }
+    void* d = nullptr;
+    if(cudaHostGetDevicePointer(&d, host_ptr, 0) != cudaSuccess || !d) {
+        cudaGetLastError(); cudaHostUnregister(host_ptr);
+        return fail(ctx, "rg_host_frame_register: the registered memory has no device address");
+    }
+    *d_ptr = d;
+    return 0;
+}
+
+int rg_host_frame_unregister(rg_ctx* ctx, void* host_ptr) {
+    if(!ctx || !host_ptr) return 1;
+    USE_DEVICE();
+    void* d = nullptr;
+    if(cudaHostGetDevicePointer(&d, host_ptr, 0) == cudaSuccess && ctx->gatherTarget == d) ctx->gatherTarget = nullptr;
+    cudaGetLastError();
+    CK(cudaStreamSynchronize(ctx->stream));   // no kernel of this context still stores into it
+    CK(cudaHostUnregister(host_ptr));
+    return 0;
+}
+
 int rg_gather_buffer_export(rg_ctx* ctx, void* handle64, void** d_ptr) {
     if(!ctx) return 1;
     USE_DEVICE();

@@ -71,3 +71,76 @@ def attach_partition_in_process(rts):
         for q in range(world):
             if q != r:
                 rt.peer_attach(q, descs[q], open_ipc=False)
+
+
+class SharedHostFrame:
+    """A width x height RGBA8 frame in POSIX shared memory, page-locked and mapped into the CUDA address space of the calling process
+    (rg_host_frame_register).  Every rank of a node opens the SAME segment and makes it its gather target: each GPU's final kernel then
+    stores its band of the frame into host memory over its own PCIe link, and the consumer (rank 0) reads the assembled frame from
+    `array` without any device -> host copy.  No reference counterpart (the reference presents through its swapchain)."""
+
+    def __init__(self, rt, name: str, width: int, height: int, create: bool):
+        import mmap
+        import os
+        import numpy as np
+        self.rt, self.path, self.owner = rt, os.path.join("/dev/shm", name), create
+        nbytes = width * height * 4
+        fd = os.open(self.path, (os.O_CREAT | os.O_RDWR) if create else os.O_RDWR, 0o600)
+        try:
+            if create:
+                os.ftruncate(fd, nbytes)
+            self.mm = mmap.mmap(fd, nbytes)
+        finally:
+            os.close(fd)
+        self.array = np.frombuffer(self.mm, dtype=np.uint8).reshape(height, width, 4)
+        self.host_ptr = self.array.ctypes.data
+        self.device_ptr = 0
+        try:
+            self.device_ptr = rt.host_frame_register(self.host_ptr, nbytes)
+        except Exception:
+            self.close()    # nothing is left behind in /dev/shm when the memory cannot be page-locked
+            raise
+
+    def close(self):
+        import os
+        if self.device_ptr:
+            self.rt.host_frame_unregister(self.host_ptr)
+            self.device_ptr = 0
+        self.array = None
+        try:
+            self.mm.close()
+        except BufferError:
+            pass
+        if self.owner and os.path.exists(self.path):
+            os.unlink(self.path)
+
+
+def open_shared_host_frame(dist, rt, rank: int, width: int, height: int, agree=None):
+    """Rank 0 creates the segment and publishes its name; every rank maps and registers it (collective).  Returns None on EVERY rank
+    when any rank could not (no /dev/shm, locked-memory limit ...): `agree(ok) -> bool` is the all-ranks AND (bench.py passes an
+    all_reduce; without it a failure raises)."""
+    import os
+    frame, err = None, None
+    name = [None]
+    if rank == 0:
+        try:
+            frame = SharedHostFrame(rt, f"rgb200_frame_{os.getpid()}", width, height, create=True)
+            name[0] = os.path.basename(frame.path)
+        except Exception as e:   # noqa: BLE001 -- any failure means "fall back", decided together below
+            err = e
+    dist.broadcast_object_list(name, src=0)
+    if rank != 0 and name[0] is not None:
+        try:
+            frame = SharedHostFrame(rt, name[0], width, height, create=False)
+        except Exception as e:   # noqa: BLE001
+            err = e
+    ok = frame is not None
+    all_ok = agree(ok) if agree is not None else ok
+    if agree is None and err is not None:
+        raise err
+    if not all_ok:
+        if frame is not None:
+            frame.close()
+        return None
+    dist.barrier()
+    return frame

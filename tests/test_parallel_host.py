@@ -66,3 +66,73 @@ def test_gather_handshake_world2_gloo():
     for rank, ok, regions, full, first, last in res:
         assert ok and full and first == 0 and last == 1
         assert regions == [(0, 0, 320, 360), (320, 0, 640, 360)]
+
+
+class _FakeRt:
+    """Stands in for raygun_b200.Raytracer on a machine without a GPU: "registration" returns the host address itself (what
+    unified addressing gives), or fails on request."""
+    def __init__(self, fail=False):
+        self.fail, self.registered = fail, set()
+
+    def host_frame_register(self, host_ptr, nbytes):
+        if self.fail:
+            raise RuntimeError("cudaHostRegister failed (test)")
+        self.registered.add(host_ptr)
+        return host_ptr
+
+    def host_frame_unregister(self, host_ptr):
+        self.registered.discard(host_ptr)
+
+
+def _shared_frame_worker(rank, world, port, q, fail_rank):
+    import torch
+    from raygun_b200.parallel import open_shared_host_frame
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def agree(ok):
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    W, H = 64, 16
+    rt = _FakeRt(fail=(rank == fail_rank))
+    frame = open_shared_host_frame(dist, rt, rank, W, H, agree)
+    if frame is None:
+        q.put((rank, None, None, len(rt.registered)))
+    else:
+        x0, y0, x1, y1 = band_region(W, H, rank, world)
+        frame.array[y0:y1, x0:x1] = rank + 1      # what this rank's final kernel stores: its band of the ONE frame
+        dist.barrier()
+        seen = frame.array[:, :, 0].copy()         # every rank (rank 0 is the consumer) sees the assembled frame, no copy
+        path = frame.path
+        dist.barrier()
+        frame.close()
+        dist.barrier()
+        q.put((rank, seen, os.path.exists(path), len(rt.registered)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1, 0])
+def test_shared_host_frame_world2_gloo(fail_rank):
+    """The e2e frame of N > 1 (bench.py): one POSIX shared-memory frame mapped by every rank; all ranks fall back together when one
+    of them cannot register it."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shared_frame_worker, args=(r, 2, port, q, fail_rank)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, seen, still_there, registered in res:
+        assert registered == 0                      # nothing stays page-locked
+        if fail_rank >= 0:
+            assert seen is None
+        else:
+            assert not still_there                  # the owner unlinked the segment
+            assert (seen[:, :32] == 1).all() and (seen[:, 32:] == 2).all()
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("rgb200_frame_")]
