@@ -147,3 +147,17 @@ def test_half_slab_is_conservative_everywhere():
 def test_byte_to_subnormal_half_is_exact():
     q = np.arange(256, dtype=np.uint16)
     assert (q.view(np.float16).astype(np.float64) == q * 2.0 ** -24).all()   # what PRMT(word, 0, 0x4140) builds per half
+
+
+def test_model_constants_are_the_kernels():
+    """The numpy restatement above checks what rg_trace.cu compiles only as long as the two carry the same constants."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "raygun_b200", "csrc", "rg_trace.cu")).read()
+    m = re.search(r"kRelC = ([0-9.e+-]+)f, kRelA = ([0-9.e+-]+)f, kAbs = ([0-9.e+-]+)f, kSlack = ([0-9.e+-]+)f;", src)
+    assert m, "margin constants not found in travNode"
+    assert tuple(F(float(v)) for v in m.groups()) == (K_REL_C, K_REL_A, K_ABS, K_SLACK)
+    for magic in ("0x86000000u - me", "0x7A000000u - me", "0x0A000000u", "0x79000000u", "__byte_perm(nx, 0u, SEL)", "pairTest<0x4140, 0>", "pairTest<0x4342, 1>"):
+        assert magic in src, magic
+    types = open(os.path.join(os.path.dirname(__file__), "..", "raygun_b200", "csrc", "rg_types.cuh")).read()
+    assert "#define RG_HALF_SLAB 1" in types   # the formulation under test is the one that ships
